@@ -1,0 +1,118 @@
+"""ctypes binding of the C-ABI in include/b200bt.h (libb200bt.so, built in-tree).
+
+There is no fallback: if the shared library is missing, or a compute entry
+point is called without an sm_100 device, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libb200bt.so"
+
+
+class B200btError(RuntimeError):
+    """Non-zero status from the C-ABI."""
+
+    def __init__(self, fn: str, status: int, message: str):
+        super().__init__(f"{fn} failed with status {status}: {message}")
+        self.status = status
+
+
+class Individual(C.Structure):
+    _fields_ = [
+        ("rsi_row", C.c_int32),
+        ("rsi_lo", C.c_float),
+        ("rsi_hi", C.c_float),
+        ("reserved", C.c_int32),
+        ("take_profit", C.c_double),
+        ("stop_loss", C.c_double),
+        ("position_size", C.c_double),
+    ]
+
+
+class SweepConfig(C.Structure):
+    _fields_ = [
+        ("initial_capital", C.c_double),
+        ("minute0", C.c_int64),
+        ("bar_minutes", C.c_int32),
+        ("primary", C.c_int32),
+        ("secondary_mask", C.c_int32),
+        ("variant", C.c_int32),
+    ]
+
+
+LANE_STATS_FIELDS = (
+    "n_records", "n_wins", "n_losses", "total_profit", "total_loss", "net_profit",
+    "max_drawdown", "sharpe_ratio", "n_days", "largest_profit", "largest_loss",
+    "sum_duration_bars", "score", "win_rate", "profit_factor", "trade_hash",
+)
+
+EVENT_EXIT = 0x40000000
+EVENT_SELL = 0x80000000
+EVENT_BAR_MASK = 0x3FFFFFFF
+
+PRIMARY = {"sharpe_ratio": 0, "return_pct": 1, "profit_factor": 2, "win_rate": 3, "net_profit": 4}
+SECONDARY = {"max_drawdown": 1, "win_rate": 2, "profit_factor": 4}
+
+_vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
+
+_SIGNATURES = {
+    "b200bt_abi_version": (C.c_int, []),
+    "b200bt_last_error": (C.c_char_p, []),
+    "b200bt_launch_count": (C.c_int64, []),
+    "b200bt_rsi_bank": (C.c_int, [_vp, _i, _i64, _i64, C.POINTER(C.c_int), _i, _i, _vp, _vp]),
+    "b200bt_sweep": (C.c_int, [_vp, _i64, _vp, _i64, _i, _i, _i64, _vp, _vp, _i,
+                               C.POINTER(SweepConfig), _vp, _vp, _i64, _vp]),
+    "b200bt_fitness_reduce": (C.c_int, [_vp, _i, _i, _vp, _vp]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names the header declares (used by the CPU-side ABI test)."""
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """Load libb200bt.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU or PyTorch fallback for this engine)")
+    lib = C.CDLL(str(LIB_PATH), mode=getattr(os, "RTLD_NOW", 2))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.b200bt_abi_version() != 1:
+        raise ImportError("libb200bt.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args):
+    lib = load()
+    status = getattr(lib, name)(*args)
+    if status != 0:
+        raise B200btError(name, status, lib.b200bt_last_error().decode("utf-8", "replace"))
+
+
+def launch_count() -> int:
+    return int(load().b200bt_launch_count())
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

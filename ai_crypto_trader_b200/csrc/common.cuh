@@ -1,0 +1,72 @@
+// Shared helpers for the b200bt kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "b200bt.h"
+
+namespace b200bt {
+
+void set_error(const char* fmt, ...);
+int check_device();
+extern std::atomic<int64_t> g_launches;
+
+inline int cuda_status(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return B200BT_OK;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+
+#define B200BT_REQUIRE(cond, code, ...)        \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::b200bt::set_error(__VA_ARGS__);  \
+            return (code);                     \
+        }                                      \
+    } while (0)
+
+#define B200BT_LAUNCH_CHECK(what)                                       \
+    do {                                                                \
+        ::b200bt::g_launches.fetch_add(1, std::memory_order_relaxed);   \
+        cudaError_t e__ = cudaGetLastError();                           \
+        if (e__ != cudaSuccess) return ::b200bt::cuda_status(e__, what); \
+    } while (0)
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ double shfl_up_d(double v, int d) {
+    return __shfl_up_sync(FULL, v, d);
+}
+__device__ __forceinline__ double shfl_d(double v, int src) {
+    return __shfl_sync(FULL, v, src);
+}
+__device__ __forceinline__ double shfl_xor_d(double v, int m) {
+    return __shfl_xor_sync(FULL, v, m);
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += shfl_xor_d(v, m);
+    return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = fmax(v, shfl_xor_d(v, m));
+    return v;
+}
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = fmin(v, shfl_xor_d(v, m));
+    return v;
+}
+
+// splitmix64 finaliser: the trade-hash mixer (oracle/sim_oracle.c uses the same).
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+}  // namespace b200bt

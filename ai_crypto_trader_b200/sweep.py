@@ -1,0 +1,226 @@
+"""Population-fitness sweep: the GA hot path on the GPU.
+
+Host side of `b200bt_sweep` (include/b200bt.h).  For every (individual, symbol)
+lane it evaluates what the reference evaluates serially in Python:
+
+    trades  = StrategyEvaluationSystem._simulate_trades(id, params, bars)   strategy_evaluation.py:746
+    metrics = StrategyPerformanceMetrics.calculate_metrics(trades)          :32
+    score   = StrategyEvaluationSystem._calculate_strategy_score(metrics)   :579
+
+and reduces fitness(individual) = mean over symbols of score.  (The
+composition simulate -> metrics -> score is the reference's own, see
+cross_validate_strategy :682-691; the mean over symbols mirrors its mean over
+folds, :1030-1060.)
+
+PyTorch is used for device memory and streams only; all arithmetic happens in
+the hand-written sm_100a kernels behind the C-ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .synth import EPOCH_2024_MINUTES
+
+DEFAULT_GOALS = {  # config.json: evolution.optimization_goals
+    "primary": "sharpe_ratio",
+    "secondary": ["max_drawdown", "win_rate", "profit_factor"],
+}
+
+
+def _f32_up(x: float) -> np.float32:
+    """Smallest float32 >= x."""
+    f = np.float32(x)
+    return f if float(f) >= x else np.nextafter(f, np.float32(np.inf))
+
+
+def _f32_down(x: float) -> np.float32:
+    """Largest float32 <= x."""
+    f = np.float32(x)
+    return f if float(f) <= x else np.nextafter(f, np.float32(-np.inf))
+
+
+class MarketData:
+    """Device-resident fp32 OHLCV, field-major SoA [5][S][N] (open, high, low, close, volume).
+
+    Mirrors the role of HistoricalDataManager.market_data_cache
+    (backtesting/data_manager.py:218-220): load once, reuse across calls.
+    """
+
+    def __init__(self, ohlcv, symbols: Optional[Sequence[str]] = None,
+                 minute0: int = EPOCH_2024_MINUTES, bar_minutes: int = 1,
+                 device: Optional[torch.device] = None, pinned_source: bool = False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("MarketData needs a CUDA device (sm_100); this engine has no CPU path")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if isinstance(ohlcv, torch.Tensor):
+            host = ohlcv
+        else:
+            host = torch.from_numpy(np.ascontiguousarray(ohlcv, dtype=np.float32))
+        if host.dim() != 3 or host.shape[0] != 5:
+            raise ValueError("ohlcv must have shape [5][S][N] (open, high, low, close, volume)")
+        self.ohlcv = host.to(self.device, non_blocking=True).contiguous()
+        self.S = int(self.ohlcv.shape[1])
+        self.N = int(self.ohlcv.shape[2])
+        self.symbols = list(symbols) if symbols is not None else [f"SYN{i:03d}USDT" for i in range(self.S)]
+        self.minute0 = int(minute0)
+        self.bar_minutes = int(bar_minutes)
+
+    @property
+    def close(self) -> torch.Tensor:
+        return self.ohlcv[3]
+
+    @property
+    def high(self) -> torch.Tensor:
+        return self.ohlcv[1]
+
+    @property
+    def low(self) -> torch.Tensor:
+        return self.ohlcv[2]
+
+    @property
+    def open(self) -> torch.Tensor:
+        return self.ohlcv[0]
+
+    @property
+    def volume(self) -> torch.Tensor:
+        return self.ohlcv[4]
+
+
+def rsi_bank(close: torch.Tensor, periods: Sequence[int], fill: bool = True,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """RSI for every window in `periods`: close [S][N] fp32 -> [S][P][N] fp32.
+
+    ta.momentum.RSIIndicator semantics as used at binance_ml_strategy.py:112.
+    """
+    assert close.is_cuda and close.dtype == torch.float32 and close.dim() == 2
+    S, N = close.shape
+    P = len(periods)
+    if out is None:
+        out = torch.empty((S, P, N), dtype=torch.float32, device=close.device)
+    arr = (C.c_int * P)(*[int(p) for p in periods])
+    with torch.cuda.device(close.device):
+        _lib.call("b200bt_rsi_bank", close.data_ptr(), S, N, close.stride(0), arr, P, 1 if fill else 0,
+                  out.data_ptr(), _lib.current_stream())
+    return out
+
+
+def decode_population(population: List[Dict], period_row: Dict[int, int]) -> np.ndarray:
+    """List of GA parameter dicts -> packed b200bt_individual array (numpy structured)."""
+    dt = np.dtype([("rsi_row", "<i4"), ("rsi_lo", "<f4"), ("rsi_hi", "<f4"), ("reserved", "<i4"),
+                   ("take_profit", "<f8"), ("stop_loss", "<f8"), ("position_size", "<f8")])
+    assert dt.itemsize == C.sizeof(_lib.Individual)
+    out = np.zeros(len(population), dtype=dt)
+    for i, p in enumerate(population):
+        period = int(p.get("rsi_period", 14))
+        if period not in period_row:
+            raise KeyError(f"rsi_period {period} is not in the RSI bank {sorted(period_row)}")
+        out["rsi_row"][i] = period_row[period]
+        out["rsi_lo"][i] = _f32_up(float(p.get("rsi_oversold", 30)))
+        out["rsi_hi"][i] = _f32_down(float(p.get("rsi_overbought", 70)))
+        # strategy_evaluation.py:762-764, :773-774 (same float64 expressions)
+        out["take_profit"][i] = p.get("take_profit", 3) / 100
+        out["stop_loss"][i] = p.get("stop_loss", 2) / 100
+        out["position_size"][i] = 10000 * (min(p.get("max_position_size", 5), 20) / 100)
+    return out
+
+
+class PopulationSweep:
+    """Evaluate a GA population against device-resident market data.
+
+    `sweep.fitness_function` is a callable usable as GeneticAlgorithm's
+    `fitness_function`; it carries a `.batch` attribute that evaluates the whole
+    population in one kernel launch (see genetic_algorithm.GeneticAlgorithm).
+    """
+
+    def __init__(self, market: MarketData, rsi_periods: Iterable[int] = range(5, 31),
+                 optimization_goals: Optional[Dict] = None, initial_capital: float = 10000.0,
+                 event_cap: int = 0):
+        self.market = market
+        self.periods = sorted(set(int(p) for p in rsi_periods))
+        self.period_row = {p: i for i, p in enumerate(self.periods)}
+        goals = optimization_goals or DEFAULT_GOALS
+        self.cfg = _lib.SweepConfig(
+            initial_capital=float(initial_capital), minute0=market.minute0, bar_minutes=market.bar_minutes,
+            primary=_lib.PRIMARY[goals.get("primary", "sharpe_ratio")],
+            secondary_mask=sum(_lib.SECONDARY.get(m, 0) for m in goals.get("secondary", [])), variant=0)
+        self.event_cap = int(event_cap)
+        self.bank = rsi_bank(market.close, self.periods)
+        self._stats = None
+        self._events = None
+        self._pop = 0
+        self._pinned_in = None
+        self._pinned_out = None
+
+    # -- device-side evaluation (inputs already resident) -------------------
+    def evaluate_device(self, indiv_dev: torch.Tensor, order_dev: Optional[torch.Tensor], pop: int,
+                        fitness_dev: torch.Tensor) -> None:
+        m = self.market
+        if self._stats is None or self._pop != pop:
+            self._stats = torch.empty((pop, m.S, 16), dtype=torch.float64, device=m.device)
+            self._events = (torch.zeros((pop, m.S, self.event_cap), dtype=torch.int32, device=m.device)
+                            if self.event_cap else None)
+            self._pop = pop
+        with torch.cuda.device(m.device):
+            st = _lib.current_stream()
+            _lib.call("b200bt_sweep", m.close.data_ptr(), m.close.stride(0), self.bank.data_ptr(),
+                      self.bank.stride(1), len(self.periods), m.S, m.N, indiv_dev.data_ptr(),
+                      _lib.ptr(order_dev), pop, C.byref(self.cfg), self._stats.data_ptr(),
+                      _lib.ptr(self._events), self.event_cap, st)
+            _lib.call("b200bt_fitness_reduce", self._stats.data_ptr(), pop, m.S, fitness_dev.data_ptr(), st)
+
+    # -- host-facing evaluation --------------------------------------------
+    def evaluate(self, population: List[Dict]) -> np.ndarray:
+        """fitness (float64[pop]) of a list of parameter dicts; H2D of the decoded
+        population and D2H of the fitness vector happen inside this call."""
+        pop = len(population)
+        dev = self.market.device
+        packed = decode_population(population, self.period_row)
+        order = np.argsort(packed["rsi_row"], kind="stable").astype(np.int32)
+        nbytes = packed.nbytes
+        if self._pinned_in is None or self._pinned_in.numel() < nbytes + order.nbytes:
+            self._pinned_in = torch.empty(nbytes + order.nbytes, dtype=torch.uint8, pin_memory=True)
+            self._pinned_out = torch.empty(pop, dtype=torch.float64, pin_memory=True)
+        if self._pinned_out.numel() < pop:
+            self._pinned_out = torch.empty(pop, dtype=torch.float64, pin_memory=True)
+        hin = self._pinned_in.numpy()
+        hin[:nbytes] = packed.view(np.uint8)
+        hin[nbytes:nbytes + order.nbytes] = order.view(np.uint8)
+        staged = self._pinned_in[:nbytes + order.nbytes].to(dev, non_blocking=True)
+        indiv_dev = staged[:nbytes]
+        order_dev = staged[nbytes:].view(torch.int32)
+        fit = torch.empty(pop, dtype=torch.float64, device=dev)
+        self.evaluate_device(indiv_dev, order_dev, pop, fit)
+        out = self._pinned_out[:pop]
+        out.copy_(fit, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        self.h2d_bytes = nbytes + order.nbytes
+        self.d2h_bytes = pop * 8
+        return out.numpy().copy()
+
+    def lane_stats(self) -> Dict[str, np.ndarray]:
+        """Per-lane metrics of the last evaluation: dict field -> [pop][S] array."""
+        raw = self._stats.cpu().numpy()
+        out = {name: raw[:, :, i] for i, name in enumerate(_lib.LANE_STATS_FIELDS[:-1])}
+        out["trade_hash"] = np.ascontiguousarray(raw[:, :, 15]).view(np.uint64)
+        return out
+
+    def events(self) -> Optional[np.ndarray]:
+        """First `event_cap` event words per lane, uint32 [pop][S][cap] (see B200BT_EVENT_*)."""
+        if self._events is None:
+            return None
+        return self._events.cpu().numpy().view(np.uint32)
+
+    @property
+    def fitness_function(self):
+        sweep = self
+
+        def fitness(individual: Dict) -> float:
+            return float(sweep.evaluate([individual])[0])
+
+        fitness.batch = lambda population: [float(x) for x in sweep.evaluate(population)]
+        return fitness

@@ -1,0 +1,169 @@
+/*
+ * b200bt.h -- C-ABI of the B200-native backtest / evolution / Monte-Carlo engine.
+ *
+ * This is the drop-in boundary below the reference's Python call surface
+ * (zd87pl/ai-crypto-trader).  The reference has no FFI
+ * of its own -- every function on the path is plain Python -- so each entry
+ * point below cites the reference function (file:line, relative to the
+ * reference tree) whose arithmetic it replaces.  All pointers are DEVICE
+ * pointers unless a name ends in `_host`.  No torch types cross this
+ * boundary: sizes are plain integers, `stream` is a `cudaStream_t` passed as
+ * `void*`.  Every function returns 0 on success and a non-zero status on
+ * failure (a `cudaError_t` value, or one of the B200BT_E* codes); nothing
+ * throws across the boundary.  `b200bt_last_error()` returns a thread-local,
+ * human-readable description of the last failure.
+ *
+ * There is NO CPU fallback behind this ABI.  If no sm_100 device is present
+ * the compute entry points return B200BT_ENODEVICE.
+ */
+#ifndef B200BT_H_
+#define B200BT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200BT_ABI_VERSION 1
+
+#define B200BT_OK 0
+#define B200BT_EINVAL 10001   /* bad argument (null pointer, size <= 0, ...)   */
+#define B200BT_ENODEVICE 10002 /* no CUDA device / wrong architecture          */
+#define B200BT_ELIMIT 10003   /* argument exceeds a documented limit           */
+
+typedef void* b200bt_stream_t; /* cudaStream_t */
+
+int b200bt_abi_version(void);
+const char* b200bt_last_error(void);
+/* Number of kernels launched by this library in this process (all threads);
+ * bench.py reports the delta over the timed region as `gpu_launches`. */
+int64_t b200bt_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Family 1: rolling indicators over fp32 OHLCV.
+ * Series layout: row-major [S][N] fp32, one row per symbol ("SoA per field").
+ * Bank layout:   row-major [S][P][N] fp32, one row per (symbol, period).
+ * Arithmetic is fp64 internally (so that a float64 CPU evaluation of the same
+ * recurrence rounds to the same fp32 value), outputs are fp32.
+ * NaN policy follows TechnicalAnalyzer._handle_nan_values
+ * (binance_ml_strategy.py:28-38): leading undefined values are back-filled
+ * with the first defined value (`fill=1`) or written as NaN (`fill=0`).
+ * ------------------------------------------------------------------------ */
+
+/* RSI bank.  Replaces ta.momentum.RSIIndicator(close, window=w).rsi() as called
+ * at binance_ml_strategy.py:112 (and services/market_monitor_service.py:228),
+ * for every window in periods_host[0..P).  Wilder smoothing
+ * ewm(alpha=1/w, adjust=False) of up/down moves; rsi = 100 where the smoothed
+ * down move is 0. */
+int b200bt_rsi_bank(const float* close, int S, int64_t N, int64_t ld,
+                    const int* periods_host, int P, int fill,
+                    float* out, b200bt_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Family 2: the per-bar entry/exit/stop/PnL state machine over
+ * (GA-individual x symbol) lanes.
+ * Replaces, for a whole population at once:
+ *   StrategyEvaluationSystem._simulate_trades   services/strategy_evaluation.py:746-878
+ *   StrategyPerformanceMetrics.calculate_metrics services/strategy_evaluation.py:32-228
+ *   StrategyEvaluationSystem._calculate_strategy_score              :579-633
+ * which GeneticAlgorithm.evaluate_population (services/genetic_algorithm.py:119-133)
+ * calls once per individual.
+ * ------------------------------------------------------------------------ */
+
+/* One GA individual, already decoded by the host:
+ *  rsi_row       row of the RSI bank holding this individual's rsi_period
+ *  rsi_lo        `rsi < rsi_oversold`  is evaluated as  r < rsi_lo  (fp32)
+ *  rsi_hi        `rsi > rsi_overbought` is evaluated as r > rsi_hi  (fp32)
+ *                (host rounds the float64 thresholds up/down to fp32 so the
+ *                 fp32 compare decides exactly like the float64 one)
+ *  take_profit   take_profit/100  (float64, strategy_evaluation.py:773)
+ *  stop_loss     stop_loss/100    (float64, :774)
+ *  position_size dollars, 10000*min(max_position_size,20)/100 (:762-764)
+ */
+typedef struct b200bt_individual {
+    int32_t rsi_row;
+    float rsi_lo;
+    float rsi_hi;
+    int32_t reserved;
+    double take_profit;
+    double stop_loss;
+    double position_size;
+} b200bt_individual; /* 40 bytes */
+
+/* Per-lane result, 16 x 8 bytes.  Field meaning follows calculate_metrics
+ * (strategy_evaluation.py:187-225) on the lane's trade RECORDS (an entry and
+ * an exit record per round trip, as the reference emits them). */
+typedef struct b200bt_lane_stats {
+    double n_records;      /* total_trades                                   */
+    double n_wins;         /* #records with pnl > 0                          */
+    double n_losses;       /* #records with pnl < 0                          */
+    double total_profit;   /* sum of positive pnl                            */
+    double total_loss;     /* sum of negative pnl (<= 0)                     */
+    double net_profit;     /* total_profit + total_loss                      */
+    double max_drawdown;   /* fraction of peak equity                        */
+    double sharpe_ratio;   /* daily-bucket Sharpe, sqrt(252) annualised      */
+    double n_days;         /* distinct calendar days holding a record        */
+    double largest_profit;
+    double largest_loss;
+    double sum_duration_bars; /* sum over round trips of exit_bar-entry_bar  */
+    double score;          /* _calculate_strategy_score                      */
+    double win_rate;
+    double profit_factor;  /* +inf when total_loss == 0 (reference :113)     */
+    uint64_t trade_hash;   /* xor of mix64(event_index, bar, side) over all events */
+} b200bt_lane_stats; /* 128 bytes */
+
+/* Scoring rule (config.json evolution.optimization_goals). */
+#define B200BT_PRIMARY_SHARPE 0
+#define B200BT_PRIMARY_RETURN_PCT 1
+#define B200BT_PRIMARY_PROFIT_FACTOR 2
+#define B200BT_PRIMARY_WIN_RATE 3
+#define B200BT_PRIMARY_NET_PROFIT 4
+#define B200BT_SEC_MAX_DRAWDOWN 1
+#define B200BT_SEC_WIN_RATE 2
+#define B200BT_SEC_PROFIT_FACTOR 4
+
+typedef struct b200bt_sweep_config {
+    double initial_capital;  /* 10000.0 (strategy_evaluation.py:33,761)       */
+    int64_t minute0;         /* minutes since 1970-01-01T00:00Z of bar 0      */
+    int32_t bar_minutes;     /* bar spacing; day = (minute0+t*bar_minutes)/1440 */
+    int32_t primary;         /* B200BT_PRIMARY_*                              */
+    int32_t secondary_mask;  /* B200BT_SEC_* bits                             */
+    int32_t variant;         /* kernel variant selector, 0 = default          */
+} b200bt_sweep_config;
+
+/* Event word written to the optional trade buffer: bits 0..29 bar index,
+ * bit 30 = 1 for an exit record, bit 31 = 1 for side "sell"
+ * (short entry / long exit).  */
+#define B200BT_EVENT_EXIT 0x40000000u
+#define B200BT_EVENT_SELL 0x80000000u
+
+/* Run the population sweep.
+ *  price   [S][N] fp32 (row stride ld_price)       close prices
+ *  rsi     [S][P][N] fp32 (row stride ld_rsi)      RSI bank
+ *  indiv   [pop] individuals (device)
+ *  order   [pop] int32 (device) evaluation order of individuals (a permutation;
+ *          the host sorts by rsi_row so neighbouring warps share a stream);
+ *          may be NULL for identity
+ *  stats   [pop][S] lane stats (device, out)
+ *  events  optional [pop][S][event_cap] uint32 (device, out), first event_cap
+ *          event words per lane; NULL to skip
+ * Limits: N < 2^30.
+ */
+int b200bt_sweep(const float* price, int64_t ld_price,
+                 const float* rsi, int64_t ld_rsi, int P,
+                 int S, int64_t N,
+                 const b200bt_individual* indiv, const int32_t* order, int pop,
+                 const b200bt_sweep_config* cfg_host,
+                 b200bt_lane_stats* stats,
+                 uint32_t* events, int64_t event_cap,
+                 b200bt_stream_t stream);
+
+/* fitness[i] = mean over symbols of stats[i][s].score  (float64, device). */
+int b200bt_fitness_reduce(const b200bt_lane_stats* stats, int pop, int S,
+                          double* fitness, b200bt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200BT_H_ */

@@ -1,0 +1,141 @@
+"""Generate the committed golden fixtures by EXECUTING the reference's own code.
+
+Run in the build container (where /root/reference exists):
+
+    python tests/golden/make_golden.py
+
+Writes (all small, committed):
+    tests/golden/sim_cases.json   parameter sets + reference metrics / score
+    tests/golden/sim_cases.npz    fp32 inputs + reference trade records
+    tests/golden/ga_run.json      seeded GeneticAlgorithm trajectory
+Inputs are the fp32 synthetic series of ai_crypto_trader_b200.synth; the RSI
+bank is oracle.indicators_ref.rsi_bank (float64 pandas, rounded to fp32).
+The reference functions executed are
+    StrategyEvaluationSystem._simulate_trades      services/strategy_evaluation.py:746
+    StrategyPerformanceMetrics.calculate_metrics   :32
+    StrategyEvaluationSystem._calculate_strategy_score :579
+    GeneticAlgorithm                               services/genetic_algorithm.py:27
+"""
+from __future__ import annotations
+
+import json
+import math
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+OUT = Path(__file__).resolve().parent
+
+from ai_crypto_trader_b200 import synth  # noqa: E402
+from oracle import indicators_ref, ref_runner, simulate_ref  # noqa: E402
+
+N_BARS = 6000          # 4.2 days of 1-minute bars
+PERIODS = list(range(5, 31))
+
+CASES = [
+    # name, params
+    ("default", {}),
+    ("ga_typical", {"rsi_period": 14, "rsi_overbought": 70, "rsi_oversold": 30, "take_profit": 3, "stop_loss": 2}),
+    ("fast_rsi_tight", {"rsi_period": 5, "rsi_overbought": 65, "rsi_oversold": 35, "take_profit": 1, "stop_loss": 1}),
+    ("slow_rsi_wide", {"rsi_period": 30, "rsi_overbought": 85, "rsi_oversold": 15, "take_profit": 10, "stop_loss": 5}),
+    ("leverage_floats", {"rsi_period": 9, "rsi_overbought": 71, "rsi_oversold": 33, "take_profit": 2.7312, "stop_loss": 0.5519}),
+    ("tiny_tp_sl", {"rsi_period": 7, "rsi_overbought": 66, "rsi_oversold": 34, "take_profit": 0.05, "stop_loss": 0.05}),
+    ("no_trades", {"rsi_period": 20, "rsi_overbought": 99.99, "rsi_oversold": 0.01, "take_profit": 3, "stop_loss": 2}),
+    ("big_position", {"rsi_period": 11, "rsi_overbought": 68, "rsi_oversold": 32, "take_profit": 2, "stop_loss": 1, "max_position_size": 50}),
+    ("short_bias", {"rsi_period": 6, "rsi_overbought": 65, "rsi_oversold": 15, "take_profit": 1, "stop_loss": 3}),
+    ("inverted_thresholds", {"rsi_period": 10, "rsi_overbought": 40, "rsi_oversold": 60, "take_profit": 2, "stop_loss": 2}),
+]
+
+SCALARS = ["total_trades", "win_rate", "profit_factor", "sharpe_ratio", "max_drawdown", "average_profit",
+           "average_loss", "largest_profit", "largest_loss", "total_profit", "total_loss", "net_profit",
+           "return_pct", "avg_trade_duration", "risk_reward_ratio"]
+
+
+def jsonable(x):
+    x = float(x)
+    if math.isinf(x):
+        return "inf" if x > 0 else "-inf"
+    if math.isnan(x):
+        return "nan"
+    return x
+
+
+def make_sim():
+    ses, metrics_cls = ref_runner.strategy_evaluation()
+    goals = ref_runner.optimization_goals()
+    arrays = {}
+    cases = []
+    for sym in (0, 3):
+        d = synth.synth_symbol(sym, N_BARS)
+        bank = indicators_ref.rsi_bank(d["close"], PERIODS)
+        arrays[f"close_{sym}"] = d["close"]
+        for period in sorted({c[1].get("rsi_period", 14) for c in CASES}):
+            arrays[f"rsi_{sym}_{period}"] = bank[PERIODS.index(period)]
+        for name, params in CASES:
+            period = params.get("rsi_period", 14)
+            rsi_row = bank[PERIODS.index(period)]
+            points = simulate_ref.market_points(d["close"], rsi_row, f"SYN{sym:03d}USDT", synth.EPOCH_2024_MINUTES)
+            ts_to_bar = {p["timestamp"]: i for i, p in enumerate(points)}
+            trades = ses._simulate_trades(name, dict(params), points)            # REFERENCE
+            m = metrics_cls.calculate_metrics(trades)                            # REFERENCE
+            score = ses._calculate_strategy_score(m)                             # REFERENCE
+            key = f"{name}_{sym}"
+            arrays[f"bar_{key}"] = np.array([ts_to_bar[t["timestamp"]] for t in trades], dtype=np.int64)
+            arrays[f"sell_{key}"] = np.array([t["side"] == "sell" for t in trades], dtype=np.bool_)
+            arrays[f"price_{key}"] = np.array([t["price"] for t in trades], dtype=np.float64)
+            arrays[f"qty_{key}"] = np.array([t["quantity"] for t in trades], dtype=np.float64)
+            arrays[f"pnl_{key}"] = np.array([t["pnl"] for t in trades], dtype=np.float64)
+            arrays[f"equity_{key}"] = np.array(m.get("equity_curve", [10000.0]), dtype=np.float64)
+            daily = m.get("daily_returns", {})
+            arrays[f"daily_{key}"] = np.array([daily[k] for k in sorted(daily)], dtype=np.float64)
+            cases.append({"key": key, "name": name, "symbol": sym, "params": params,
+                          "metrics": {k: jsonable(m[k]) for k in SCALARS}, "score": jsonable(score),
+                          "n_records": len(trades)})
+            print(f"{key:28s} records={len(trades):5d} score={float(score):.6g}")
+    np.savez_compressed(OUT / "sim_cases.npz", **arrays)
+    (OUT / "sim_cases.json").write_text(json.dumps(
+        {"n_bars": N_BARS, "periods": PERIODS, "minute0": synth.EPOCH_2024_MINUTES, "goals": goals,
+         "cases": cases}, indent=1))
+
+
+def make_ga():
+    GA = ref_runner.genetic_algorithm_class()
+    ranges = synth.param_ranges()
+
+    def fitness(ind):
+        # deterministic toy fitness: smooth, non-degenerate, no data involved
+        s = 0.0
+        for i, (k, (lo, hi)) in enumerate(ranges.items()):
+            x = (ind[k] - lo) / (hi - lo)
+            s += math.sin(3.0 * x + 0.37 * i) * (1.0 + 0.1 * i)
+        return s
+
+    runs = []
+    for pop, gens, seed, seeded in ((20, 10, 42, True), (64, 5, 7, False)):
+        ga = GA(param_ranges=ranges, fitness_function=fitness, population_size=pop, generations=gens,
+                mutation_rate=0.2, crossover_rate=0.8, elitism_pct=0.1, random_seed=seed)
+        seed_ind = {k: (lo + hi) // 2 if isinstance(lo, int) and isinstance(hi, int) else 0.5 * (lo + hi)
+                    for k, (lo, hi) in ranges.items()}
+        seed_ind["take_profit"] = 300      # out of range: initialize_population clamps (:96-103)
+        seed_ind["rsi_period"] = 1
+        seeds = [seed_ind] if seeded else None
+        best = ga.run(seeded_individuals=seeds)
+        hist = ga.get_generation_history()
+        runs.append({
+            "pop": pop, "generations": gens, "seed": seed, "seeded": seeds,
+            "best": best, "best_fitness": ga.best_fitness,
+            "final_population": ga.population, "final_fitness": ga.fitness_scores,
+            "history": [{k: h[k] for k in ("generation", "best_fitness", "avg_fitness", "min_fitness",
+                                           "best_individual", "diversity")} for h in hist],
+            "diversity": ga.get_population_diversity(),
+        })
+        print(f"GA pop={pop} gens={gens} seed={seed}: best_fitness={ga.best_fitness:.6f}")
+    (OUT / "ga_run.json").write_text(json.dumps({"runs": runs}, indent=1))
+
+
+if __name__ == "__main__":
+    make_sim()
+    make_ga()

@@ -1,0 +1,136 @@
+"""GPU parity of the indicator bank and the population sweep against the CPU oracle
+(and, through the committed fixtures, against the reference's own code)."""
+import numpy as np
+import pytest
+
+from conftest import unjson
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda(native_lib):
+    import torch
+    assert torch.cuda.is_available(), "gpu-marked tests need a CUDA device"
+    torch.cuda.set_device(0)
+    return torch
+
+
+def _bank_mismatch(got, want):
+    neq = got != want
+    neq &= ~(np.isnan(got) & np.isnan(want))
+    return int(neq.sum())
+
+
+@pytest.mark.parametrize("n_bars", [1, 3, 29, 30, 31, 127, 128, 4095, 4096, 4097, 10000, 70001])
+def test_rsi_bank_bitwise_vs_float64_oracle(torch_cuda, n_bars):
+    torch = torch_cuda
+    from ai_crypto_trader_b200 import synth
+    from ai_crypto_trader_b200.sweep import rsi_bank
+    from oracle import indicators_ref
+    periods = [2, 5, 14, 30, 47]
+    ohlcv = synth.synth_ohlcv(3, n_bars)
+    got = rsi_bank(torch.from_numpy(ohlcv[3]).cuda(), periods).cpu().numpy()
+    for s in range(3):
+        want = indicators_ref.rsi_bank(ohlcv[3, s], periods)
+        bad = _bank_mismatch(got[s], want)
+        # fp64 evaluation rounded once to fp32: identical up to double-rounding ties (~1e-8 of values)
+        assert bad <= max(0, int(2e-6 * want.size)), (n_bars, s, bad)
+        np.testing.assert_allclose(got[s], want, rtol=2e-7, atol=0)
+
+
+def test_rsi_bank_nan_mode_and_flat_series(torch_cuda):
+    torch = torch_cuda
+    from ai_crypto_trader_b200.sweep import rsi_bank
+    from oracle import indicators_ref
+    n = 500
+    close = np.full((1, n), 123.25, dtype=np.float32)
+    close[0, 200:] += np.linspace(0, 5, 300).astype(np.float32)   # flat, then strictly rising
+    got = rsi_bank(torch.from_numpy(close).cuda(), [14], fill=False).cpu().numpy()[0]
+    want = indicators_ref.rsi_bank(close[0], [14], fill=False)
+    assert np.isnan(got[0, :13]).all() and not np.isnan(got[0, 13:]).any()
+    assert _bank_mismatch(got, want) == 0
+    assert (got[0, 13:200] == 100.0).all()   # no down moves -> 100 (ta: where(emadn == 0, 100, ...))
+
+
+def test_sweep_matches_reference_fixtures(torch_cuda, sim_golden):
+    """The kernel against records produced by the reference's own _simulate_trades /
+    calculate_metrics / _calculate_strategy_score: bit-exact bars and sides, float64 metrics."""
+    torch = torch_cuda
+    from ai_crypto_trader_b200 import _lib
+    from ai_crypto_trader_b200.sweep import MarketData, PopulationSweep
+    meta, arrays = sim_golden
+    syms = sorted({c["symbol"] for c in meta["cases"]})
+    n = meta["n_bars"]
+    ohlcv = np.zeros((5, len(syms), n), dtype=np.float32)
+    for j, s in enumerate(syms):
+        ohlcv[3, j] = arrays[f"close_{s}"]
+    market = MarketData(ohlcv, minute0=meta["minute0"])
+    sweep = PopulationSweep(market, rsi_periods=meta["periods"], optimization_goals=meta["goals"], event_cap=4096)
+    # the bank the kernel consumes must be the fixture's bank
+    bank = sweep.bank.cpu().numpy()
+    names = []
+    for c in meta["cases"]:
+        if c["name"] not in names:
+            names.append(c["name"])
+    by_name = {c["name"]: c["params"] for c in meta["cases"]}
+    for j, s in enumerate(syms):
+        for name in names:
+            period = by_name[name].get("rsi_period", 14)
+            assert np.array_equal(bank[j, sweep.period_row[period]], arrays[f"rsi_{s}_{period}"]), (s, period)
+    population = [dict(by_name[nm]) for nm in names]
+    fitness = sweep.evaluate(population)
+    stats = sweep.lane_stats()
+    events = sweep.events()
+    for c in meta["cases"]:
+        i, j, key = names.index(c["name"]), syms.index(c["symbol"]), c["key"]
+        nrec = c["n_records"]
+        assert int(stats["n_records"][i, j]) == nrec, key
+        ev = events[i, j, :nrec]
+        assert (ev & _lib.EVENT_BAR_MASK).tolist() == arrays[f"bar_{key}"].tolist(), key
+        assert ((ev >> 31) == 1).tolist() == arrays[f"sell_{key}"].tolist(), key
+        m = c["metrics"]
+        for field, ref_name in (("total_profit", "total_profit"), ("total_loss", "total_loss"),
+                                ("net_profit", "net_profit"), ("win_rate", "win_rate"),
+                                ("max_drawdown", "max_drawdown"), ("sharpe_ratio", "sharpe_ratio"),
+                                ("largest_profit", "largest_profit"), ("largest_loss", "largest_loss"),
+                                ("profit_factor", "profit_factor")):
+            assert stats[field][i, j] == pytest.approx(unjson(m[ref_name]), rel=1e-10, abs=1e-12), (key, field)
+        assert stats["score"][i, j] == pytest.approx(unjson(c["score"]), rel=1e-9, abs=1e-12), key
+        # equity curve end point: 1e-5 relative is the north-star tolerance; we hold 1e-12
+        assert 10000.0 + stats["net_profit"][i, j] == pytest.approx(arrays[f"equity_{key}"][-1], rel=1e-12), key
+    want_fit = [np.mean([unjson(c["score"]) for c in meta["cases"] if c["name"] == nm]) for nm in names]
+    np.testing.assert_allclose(fitness, want_fit, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("n_bars,pop,n_sym", [(1, 4, 1), (31, 8, 2), (33, 8, 1), (1000, 64, 3), (50001, 96, 2)])
+def test_sweep_vs_c_oracle_random_populations(torch_cuda, n_bars, pop, n_sym):
+    from ai_crypto_trader_b200 import _lib, synth
+    from ai_crypto_trader_b200.sweep import MarketData, PopulationSweep
+    from oracle import indicators_ref, sim_oracle
+    ohlcv = synth.synth_ohlcv(n_sym, n_bars, first_symbol=5)
+    market = MarketData(ohlcv)
+    cap = 512
+    sweep = PopulationSweep(market, event_cap=cap)
+    population = synth.random_population(pop, seed=n_bars)
+    # make a few lanes extreme: always in the market / leverage floats
+    population[0].update(rsi_oversold=35, rsi_overbought=65, rsi_period=5, take_profit=1, stop_loss=1)
+    population[1].update(take_profit=0.5, stop_loss=0.5)
+    fitness = sweep.evaluate(population)
+    stats, events = sweep.lane_stats(), sweep.events()
+    cfg = sim_oracle.config_of(market.minute0, 1)
+    scores = np.zeros((pop, n_sym))
+    for s in range(n_sym):
+        bank = indicators_ref.rsi_bank(ohlcv[3, s], sweep.periods)
+        for i, p in enumerate(population):
+            want, ev, _ = sim_oracle.lane(ohlcv[3, s], bank[sweep.period_row[p["rsi_period"]]], p, cfg, event_cap=cap)
+            assert int(stats["n_records"][i, s]) == int(want["n_records"]), (i, s)
+            assert int(stats["trade_hash"][i, s]) == int(want["trade_hash"]), (i, s)
+            assert np.array_equal(events[i, s, :len(ev)], ev), (i, s)
+            for f in ("n_wins", "n_losses", "n_days", "sum_duration_bars"):
+                assert stats[f][i, s] == want[f], (i, s, f)
+            for f in ("total_profit", "total_loss", "net_profit", "max_drawdown", "sharpe_ratio", "largest_profit",
+                      "largest_loss", "win_rate", "profit_factor", "score"):
+                assert stats[f][i, s] == pytest.approx(float(want[f]), rel=1e-9, abs=1e-11), (i, s, f)
+            scores[i, s] = want["score"]
+    np.testing.assert_allclose(fitness, scores.mean(axis=1), rtol=1e-9, atol=1e-11)

@@ -1,0 +1,77 @@
+"""The oracle restatements (Python and C) against fixtures produced by executing
+the reference's own _simulate_trades / calculate_metrics / _calculate_strategy_score
+(tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import unjson
+from oracle import sim_oracle, simulate_ref
+
+
+def _case_inputs(meta, arrays, case):
+    sym = case["symbol"]
+    period = case["params"].get("rsi_period", 14)
+    return arrays[f"close_{sym}"], arrays[f"rsi_{sym}_{period}"]
+
+
+def test_python_restatement_matches_reference_records(sim_golden):
+    meta, arrays = sim_golden
+    for case in meta["cases"]:
+        close, rsi = _case_inputs(meta, arrays, case)
+        pts = simulate_ref.market_points(close, rsi, f"SYN{case['symbol']:03d}USDT", meta["minute0"])
+        recs = simulate_ref.simulate_trades(dict(case["params"]), pts)
+        key = case["key"]
+        assert len(recs) == case["n_records"], key
+        ts_to_bar = {p["timestamp"]: i for i, p in enumerate(pts)}
+        assert [ts_to_bar[r["timestamp"]] for r in recs] == arrays[f"bar_{key}"].tolist(), key
+        assert [r["side"] == "sell" for r in recs] == arrays[f"sell_{key}"].tolist(), key
+        # same float64 expressions -> bit-identical
+        assert np.array_equal(np.array([r["pnl"] for r in recs]), arrays[f"pnl_{key}"]), key
+        assert np.array_equal(np.array([r["quantity"] for r in recs]), arrays[f"qty_{key}"]), key
+        assert np.array_equal(np.array([r["price"] for r in recs]), arrays[f"price_{key}"]), key
+        m = simulate_ref.calculate_metrics(recs)
+        for name, want in case["metrics"].items():
+            want = unjson(want)
+            got = float(m[name])
+            assert got == want or (np.isnan(got) and np.isnan(want)), (key, name, got, want)
+        assert np.array_equal(np.array(m["equity_curve"]), arrays[f"equity_{key}"]), key
+        got_score = float(simulate_ref.strategy_score(m, meta["goals"]))
+        assert got_score == unjson(case["score"]), key
+
+
+def test_c_oracle_matches_reference(sim_golden):
+    meta, arrays = sim_golden
+    cfg = sim_oracle.config_of(meta["minute0"], 1, meta["goals"])
+    for case in meta["cases"]:
+        close, rsi = _case_inputs(meta, arrays, case)
+        key = case["key"]
+        st, ev, pnl = sim_oracle.lane(close, rsi, case["params"], cfg, event_cap=8192)
+        assert int(st["n_records"]) == case["n_records"], key
+        assert (ev & 0x3FFFFFFF).tolist() == arrays[f"bar_{key}"].tolist(), key
+        assert ((ev >> 31) == 1).tolist() == arrays[f"sell_{key}"].tolist(), key
+        # same operations in the same order, -ffp-contract=off: bit-identical pnl
+        assert np.array_equal(pnl, arrays[f"pnl_{key}"]), key
+        m = case["metrics"]
+        # Python's sum() is compensated (3.12), C accumulates plainly: 1e-12 relative
+        for got, want in ((st["total_profit"], m["total_profit"]), (st["total_loss"], m["total_loss"]),
+                          (st["net_profit"], m["net_profit"]), (st["win_rate"], m["win_rate"]),
+                          (st["max_drawdown"], m["max_drawdown"]), (st["sharpe_ratio"], m["sharpe_ratio"]),
+                          (st["largest_profit"], m["largest_profit"]), (st["largest_loss"], m["largest_loss"]),
+                          (st["profit_factor"], m["profit_factor"]), (st["score"], case["score"])):
+            want = unjson(want)
+            assert got == pytest.approx(want, rel=1e-11, abs=1e-12), (key, got, want)
+        assert int(st["n_days"]) == len(arrays[f"daily_{key}"]), key
+        if case["n_records"]:
+            dur = m["avg_trade_duration"] * (case["n_records"] // 2)
+            assert st["sum_duration_bars"] == pytest.approx(dur, rel=1e-12), key
+
+
+def test_c_oracle_event_cap_and_hash_are_consistent(sim_golden):
+    meta, arrays = sim_golden
+    cfg = sim_oracle.config_of(meta["minute0"], 1, meta["goals"])
+    case = next(c for c in meta["cases"] if c["key"] == "fast_rsi_tight_0")
+    close, rsi = _case_inputs(meta, arrays, case)
+    st_a, ev_a, _ = sim_oracle.lane(close, rsi, case["params"], cfg, event_cap=16)
+    st_b, ev_b, _ = sim_oracle.lane(close, rsi, case["params"], cfg, event_cap=4096)
+    assert st_a["trade_hash"] == st_b["trade_hash"] != 0
+    assert len(ev_a) == 16 and np.array_equal(ev_a, ev_b[:16])
