@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(SW_WARPS * 32)
 sweep_kernel(const float* __restrict__ price, int64_t ld_price,
              const float* __restrict__ rsi, int64_t ld_rsi, int P, int S, int64_t N,
              const b200bt_individual* __restrict__ indiv, const int32_t* __restrict__ order, int pop,
-             const __grid_constant__ b200bt_sweep_config cfg,
+             const b200bt_sweep_config cfg,  // NOT __grid_constant__: nvcc 12.9 then forwards the param load over a.equity's loop-carried value
+
              b200bt_lane_stats* __restrict__ stats, uint32_t* __restrict__ events, int64_t ev_cap) {
     const int lane = threadIdx.x & 31;
     const int64_t gw = (int64_t)blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
