@@ -10,7 +10,7 @@ import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libb200bt.so"
+LIB_PATH = Path(os.environ.get("B200BT_LIB", _HERE / "libb200bt.so"))
 
 
 class B200btError(RuntimeError):

@@ -29,71 +29,99 @@
 namespace b200bt {
 
 constexpr int SW_WARPS = 8;         // warps (lanes of the sweep) per CTA
-constexpr int SW_V = 4;             // 32-bar windows loaded per group
+#ifndef B200BT_SW_MIN_BLOCKS
+#define B200BT_SW_MIN_BLOCKS 3
+#endif
+constexpr int SW_MIN_BLOCKS = B200BT_SW_MIN_BLOCKS;    // CTAs per SM the register budget is held to (<= 64 regs/thread)
+constexpr int SW_GROUP = 128;       // bars per cp.async group (per stream)
+constexpr int SW_STAGES = 4;        // shared-memory ring depth per warp
+constexpr int SW_EVQ = 128;         // event queue entries per warp (>= 32 + 64 new events per window pair)
 constexpr float SW_MARGIN = 1e-6f;  // relative width of the fp32 screening band
 
-struct LaneConst {
+// Warp-uniform per-lane constants of the bar scan (shared memory; read on events only).
+struct ScanConst {
     float os_f, ob_f;
     // screening multipliers: candidate (c) and definite (d) bounds
     float hiL_c, hiL_d, loL_c, loL_d;  // long : TP above, SL below
     float hiS_c, hiS_d, loS_c, loS_d;  // short: SL above, TP below
-    double tp, sl, size, fee1, fee2;
 };
 
-struct LaneAcc {
+// Everything only the event-batch code touches lives in shared memory (one slot
+// per warp) so that the bar scan keeps a small register footprint.
+struct WarpAcc {
+    double tp, sl, size, fee1, fee2;
     double equity, peak, maxdd;
     double tot_profit, tot_loss, largest_p, largest_l;
     double day_sum, pivot, s1, s2;
     long long day_cur;
     long long sum_dur;
     unsigned long long hash;
+    uint32_t* ev_out;
     unsigned n_win, n_loss, n_days, n_events;
     int day_valid, pivot_set;
 };
 
-__device__ __forceinline__ void day_complete(LaneAcc& a, double x) {
+// Per-warp shared-memory working set.
+struct __align__(16) WarpShared {
+    float ring[SW_STAGES][2][SW_GROUP];  // cp.async ring: [stage][0 price | 1 rsi][bar]
+    uint2 evq[SW_EVQ];                   // event queue: (event word, price bits), consumed 32 at a time
+    WarpAcc acc;
+    ScanConst sc;
+};
+
+struct DayAcc {
+    double pivot, s1, s2;
+    unsigned n_days;
+    int pivot_set;
+};
+
+__device__ __forceinline__ void day_complete(DayAcc& a, double x) {
     // shifted-data accumulation of the daily pnl sums (exactly 0 variance for equal days)
     if (!a.pivot_set) { a.pivot = x; a.pivot_set = 1; }
-    double y = x - a.pivot;
+    const double y = x - a.pivot;
     a.s1 += y;
     a.s2 += y * y;
     a.n_days += 1;
 }
 
-// Consume `cnt` queued events (lane j holds event j; even j = entry record,
-// odd j = exit record of the same round trip).
-__device__ __forceinline__ void process_batch(int cnt, unsigned w, float pf, const LaneConst& c,
-                                              LaneAcc& a, const b200bt_sweep_config& cfg,
-                                              uint32_t* ev_out, int64_t ev_cap) {
+// Consume `cnt` queued events starting at queue position `qtail` (lane j takes
+// event j; even j = entry record, odd j = exit record of the same round trip).
+__device__ __noinline__ void process_batch(WarpShared* __restrict__ ws, unsigned qtail, int cnt,
+                                           long long minute0, int bar_minutes, int64_t ev_cap) {
     const int lane = threadIdx.x & 31;
+    WarpAcc* __restrict__ acc = &ws->acc;
     const bool active = lane < cnt;
+    const uint2 evt = ws->evq[(qtail + lane) & (SW_EVQ - 1)];
+    const unsigned w = evt.x;
+    const float pf = __uint_as_float(evt.y);
     const bool is_exit = active && (w & B200BT_EVENT_EXIT);
     const float p_prev = __shfl_up_sync(FULL, pf, 1);
     const unsigned w_prev = __shfl_up_sync(FULL, w, 1);
-    const long long bar = (long long)(w & 0x3fffffffu);
+    const unsigned bar = w & 0x3fffffffu;
 
     double pnl = 0.0;
     int dur = 0;
     if (active) {
         if (is_exit) {
             const double e = (double)p_prev, px = (double)pf;
-            const double qty = __ddiv_rn(c.size, e);
+            const double qty = __ddiv_rn(acc->size, e);
             const double diff = (w_prev & B200BT_EVENT_SELL) ? __dsub_rn(e, px) : __dsub_rn(px, e);
-            pnl = __dsub_rn(__dmul_rn(qty, diff), c.fee2);
-            dur = (int)(bar - (long long)(w_prev & 0x3fffffffu));
+            pnl = __dsub_rn(__dmul_rn(qty, diff), acc->fee2);
+            dur = (int)(bar - (w_prev & 0x3fffffffu));
         } else {
-            pnl = -c.fee1;
+            pnl = -acc->fee1;
         }
     }
     // wins / losses
     const bool win = active && pnl > 0.0, loss = active && pnl < 0.0;
-    a.n_win += __popc(__ballot_sync(FULL, win));
-    a.n_loss += __popc(__ballot_sync(FULL, loss));
-    a.tot_profit += warp_sum_d(win ? pnl : 0.0);
-    a.tot_loss += warp_sum_d(loss ? pnl : 0.0);
-    a.largest_p = fmax(a.largest_p, warp_max_d(win ? pnl : 0.0));
-    a.largest_l = fmin(a.largest_l, warp_min_d(loss ? pnl : 0.0));
-    a.sum_dur += __reduce_add_sync(FULL, dur);
+    const unsigned n_win = acc->n_win + __popc(__ballot_sync(FULL, win));
+    const unsigned n_loss = acc->n_loss + __popc(__ballot_sync(FULL, loss));
+    const double tot_profit = acc->tot_profit + warp_sum_d(win ? pnl : 0.0);
+    const double tot_loss = acc->tot_loss + warp_sum_d(loss ? pnl : 0.0);
+    double largest_p = acc->largest_p, largest_l = acc->largest_l;
+    if (__any_sync(FULL, pnl > largest_p)) largest_p = fmax(largest_p, warp_max_d(win ? pnl : 0.0));   // rare after warm-up
+    if (__any_sync(FULL, pnl < largest_l)) largest_l = fmin(largest_l, warp_min_d(loss ? pnl : 0.0));
+    const long long sum_dur = acc->sum_dur + __reduce_add_sync(FULL, dur);
 
     // equity curve: inclusive scan of pnl, running peak, drawdown
     double cs = pnl;
@@ -102,210 +130,303 @@ __device__ __forceinline__ void process_batch(int cnt, unsigned w, float pf, con
         double up = shfl_up_d(cs, d);
         if (lane >= d) cs += up;
     }
-    const double eq = a.equity + cs;
+    const double eq = acc->equity + cs;
     double pk = active ? eq : -INFINITY;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         double up = shfl_up_d(pk, d);
         if (lane >= d) pk = fmax(pk, up);
     }
-    pk = fmax(pk, a.peak);
-    double dd = 0.0;
-    if (active && eq < pk) dd = __ddiv_rn(__dsub_rn(pk, eq), pk);
-    a.maxdd = fmax(a.maxdd, warp_max_d(dd));
-    a.equity = shfl_d(eq, cnt - 1);
-    a.peak = shfl_d(pk, cnt - 1);
+    pk = fmax(pk, acc->peak);
+    double maxdd = acc->maxdd;
+    {
+        // dd_j = (pk-eq)/pk; a new maximum needs (pk-eq) > maxdd*pk (screen with a safety factor, then divide)
+        const double gap = __dsub_rn(pk, eq);
+        const bool cand = active && gap > 0.0 && gap >= maxdd * pk * (1.0 - 1e-12);
+        if (__any_sync(FULL, cand)) maxdd = fmax(maxdd, warp_max_d(cand ? __ddiv_rn(gap, pk) : 0.0));
+    }
+    const double batch_sum = shfl_d(cs, 31);
+    const double equity_out = acc->equity + batch_sum;
+    const double peak_out = shfl_d(pk, cnt - 1);
 
     // daily buckets: segmented sum by calendar day over the batch, merged with the carry day
-    long long day = active ? (cfg.minute0 + bar * (long long)cfg.bar_minutes) / 1440 : 0;
-    const long long day_prev = __shfl_up_sync(FULL, day, 1);
-    const long long day_next = __shfl_down_sync(FULL, day, 1);
-    const bool head = active && (lane == 0 || day != day_prev);
-    const bool tail = active && (lane == cnt - 1 || day != day_next);
-    double seg = pnl;
-    bool flag = head;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        double up = shfl_up_d(seg, d);
-        int fup = __shfl_up_sync(FULL, (int)flag, d);
-        if (lane >= d && !flag) { seg += up; flag = fup; }
-    }
+    const long long day = active ? (minute0 + (long long)bar * bar_minutes) / 1440 : 0;
+    DayAcc da{acc->pivot, acc->s1, acc->s2, acc->n_days, acc->pivot_set};
+    const int day_valid = acc->day_valid;
+    const long long day_cur = acc->day_cur;
+    double day_sum = acc->day_sum;
     const long long first_day = __shfl_sync(FULL, day, 0);
-    const bool merge_carry = a.day_valid && (first_day == a.day_cur);
-    // a tail in the first segment (its day == first_day) absorbs the carry
-    if (tail && merge_carry && day == first_day) seg += a.day_sum;
-    const bool last_seg_tail = tail && (lane == cnt - 1);
-    // completed days: every tail except the batch's last one (which stays open) ...
-    double x = (tail && !last_seg_tail) ? seg : 0.0;
-    unsigned done = __ballot_sync(FULL, tail && !last_seg_tail);
-    // ... plus the carried day when the batch starts on a later day
-    const bool carry_done = a.day_valid && !merge_carry;
-    // fold completed days in time order (carry first, then lanes ascending): cheap, rare
-    if (carry_done) day_complete(a, a.day_sum);
-    while (done) {
-        int j = __ffs(done) - 1;
-        done &= done - 1;
-        day_complete(a, shfl_d(x, j));
+    const long long last_day = __shfl_sync(FULL, day, cnt - 1);
+    if (first_day == last_day && (!day_valid || first_day == day_cur)) {
+        // common case: the whole batch falls into the open day
+        day_sum = (day_valid ? day_sum : 0.0) + batch_sum;
+    } else {
+        const long long day_prev = __shfl_up_sync(FULL, day, 1);
+        const long long day_next = __shfl_down_sync(FULL, day, 1);
+        const bool head = active && (lane == 0 || day != day_prev);
+        const bool tail = active && (lane == cnt - 1 || day != day_next);
+        double seg = pnl;
+        bool flag = head;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            double up = shfl_up_d(seg, d);
+            int fup = __shfl_up_sync(FULL, (int)flag, d);
+            if (lane >= d && !flag) { seg += up; flag = fup; }
+        }
+        const bool merge_carry = day_valid && (first_day == day_cur);
+        // a tail in the first segment (its day == first_day) absorbs the carry
+        if (tail && merge_carry && day == first_day) seg += day_sum;
+        const bool last_seg_tail = tail && (lane == cnt - 1);
+        // completed days: every tail except the batch's last one (which stays open) ...
+        const double x = (tail && !last_seg_tail) ? seg : 0.0;
+        unsigned done = __ballot_sync(FULL, tail && !last_seg_tail);
+        // ... plus the carried day when the batch starts on a later day;
+        // fold in time order (carry first, then lanes ascending)
+        if (day_valid && !merge_carry) day_complete(da, day_sum);
+        while (done) {
+            const int j = __ffs(done) - 1;
+            done &= done - 1;
+            day_complete(da, shfl_d(x, j));
+        }
+        day_sum = shfl_d(seg, cnt - 1);
     }
-    a.day_sum = shfl_d(seg, cnt - 1);
-    a.day_cur = __shfl_sync(FULL, day, cnt - 1);
-    a.day_valid = 1;
 
     // trade hash + optional event buffer
-    unsigned long long h = active ? mix64(((unsigned long long)(a.n_events + lane) << 32) | w) : 0ull;
-    unsigned hlo = __reduce_xor_sync(FULL, (unsigned)h);
-    unsigned hhi = __reduce_xor_sync(FULL, (unsigned)(h >> 32));
-    a.hash ^= ((unsigned long long)hhi << 32) | hlo;
+    const unsigned n_events = acc->n_events;
+    const unsigned long long h = active ? mix64(((unsigned long long)(n_events + lane) << 32) | w) : 0ull;
+    const unsigned hlo = __reduce_xor_sync(FULL, (unsigned)h);
+    const unsigned hhi = __reduce_xor_sync(FULL, (unsigned)(h >> 32));
+    uint32_t* ev_out = acc->ev_out;
     if (ev_out && active) {
-        long long idx = (long long)a.n_events + lane;
+        const long long idx = (long long)n_events + lane;
         if (idx < ev_cap) ev_out[idx] = w;
     }
-    a.n_events += cnt;
+    __syncwarp();
+    if (lane == 0) {
+        acc->n_win = n_win; acc->n_loss = n_loss;
+        acc->tot_profit = tot_profit; acc->tot_loss = tot_loss;
+        acc->largest_p = largest_p; acc->largest_l = largest_l;
+        acc->sum_dur = sum_dur;
+        acc->equity = equity_out; acc->peak = peak_out; acc->maxdd = maxdd;
+        acc->pivot = da.pivot; acc->s1 = da.s1; acc->s2 = da.s2; acc->n_days = da.n_days; acc->pivot_set = da.pivot_set;
+        acc->day_sum = day_sum; acc->day_cur = last_day; acc->day_valid = 1;
+        acc->hash ^= ((unsigned long long)hhi << 32) | hlo;
+        acc->n_events = n_events + cnt;
+    }
+    __syncwarp();
 }
 
-__global__ void __launch_bounds__(SW_WARPS * 32)
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+// Machine state of one lane (warp-uniform registers).
+struct Machine {
+    int pos;                                   // 0 flat, +1 long, -1 short
+    float e;                                   // entry price
+    float rlo, rhi, plo, phi;                  // event thresholds of the current state (screening bounds)
+    unsigned qhead;                            // events pushed so far (queue head)
+};
+
+__device__ __forceinline__ bool fires(const Machine& m, float p, float r) {
+    return (r < m.rlo) | (r > m.rhi) | (p <= m.plo) | (p >= m.phi);
+}
+
+// Advance the machine through every event of one 32-bar window (lane l holds bar t0+l).
+__device__ __forceinline__ void scan_window(const float p, const float r, const int t0, const int lane,
+                                            WarpShared* __restrict__ ws, Machine& m) {
+    unsigned live = FULL;  // bars of the window not yet consumed
+    while (true) {
+        const unsigned hit = __ballot_sync(FULL, fires(m, p, r)) & live;
+        if (hit == 0) break;
+        const int kk = __ffs(hit) - 1;
+        const float pk = __shfl_sync(FULL, p, kk);
+        const float rk = __shfl_sync(FULL, r, kk);
+        live = (kk == 31) ? 0u : (FULL << (kk + 1));
+        const ScanConst& c = ws->sc;
+        unsigned word;
+        if (m.pos == 0) {
+            // entry (strategy_evaluation.py:784-813): long has priority over short
+            m.e = pk;
+            if (rk < c.os_f) {
+                m.pos = 1;
+                m.rlo = -INFINITY; m.rhi = c.ob_f;
+                m.phi = pk * c.hiL_c; m.plo = pk * c.loL_c;
+                word = (unsigned)(t0 + kk);
+            } else {
+                m.pos = -1;
+                m.rlo = c.os_f; m.rhi = INFINITY;
+                m.phi = pk * c.hiS_c; m.plo = pk * c.loS_c;
+                word = (unsigned)(t0 + kk) | B200BT_EVENT_SELL;
+            }
+        } else {
+            // exit candidate (:815-847)
+            const float phi_d = m.e * (m.pos > 0 ? c.hiL_d : c.hiS_d);
+            const float plo_d = m.e * (m.pos > 0 ? c.loL_d : c.loS_d);
+            const bool definite = (rk < m.rlo) || (rk > m.rhi) || (pk >= phi_d) || (pk <= plo_d);
+            if (!definite) {
+                // inside the fp32 screening band: decide with the reference's float64 expression
+                const double ed = (double)m.e, pd = (double)pk;
+                const double q = (m.pos > 0) ? __ddiv_rn(__dsub_rn(pd, ed), ed) : __ddiv_rn(__dsub_rn(ed, pd), ed);
+                if (!(q >= ws->acc.tp || q <= -ws->acc.sl)) continue;
+            }
+            word = (unsigned)(t0 + kk) | B200BT_EVENT_EXIT | (m.pos > 0 ? B200BT_EVENT_SELL : 0u);
+            m.pos = 0;
+            m.rlo = c.os_f; m.rhi = c.ob_f;
+            m.plo = -INFINITY; m.phi = INFINITY;
+        }
+        if (lane == 0) ws->evq[m.qhead & (SW_EVQ - 1)] = make_uint2(word, __float_as_uint(pk));
+        ++m.qhead;
+    }
+}
+
+__global__ void __launch_bounds__(SW_WARPS * 32, SW_MIN_BLOCKS)
 sweep_kernel(const float* __restrict__ price, int64_t ld_price,
              const float* __restrict__ rsi, int64_t ld_rsi, int P, int S, int64_t N,
              const b200bt_individual* __restrict__ indiv, const int32_t* __restrict__ order, int pop,
-             const b200bt_sweep_config cfg,  // NOT __grid_constant__: nvcc 12.9 then forwards the param load over a.equity's loop-carried value
-
+             const b200bt_sweep_config cfg,  // NOT __grid_constant__: nvcc 12.9 miscompiled a loop-carried value with it
              b200bt_lane_stats* __restrict__ stats, uint32_t* __restrict__ events, int64_t ev_cap) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane = threadIdx.x & 31;
-    const int64_t gw = (int64_t)blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
-    if (gw >= (int64_t)pop * S) return;
-    const int sym = (int)(gw / pop);
-    const int k = (int)(gw % pop);
+    // CTA b evaluates SW_WARPS consecutive individuals of the host's evaluation order on one symbol;
+    // all symbols of the first (most expensive) individuals are dispatched first, so the grid drains
+    // in longest-processing-time-first order and the tail consists of cheap lanes.
+    const int sym = (int)(blockIdx.x % (unsigned)S);
+    const int k = (int)(blockIdx.x / (unsigned)S) * SW_WARPS + (threadIdx.x >> 5);
+    if (k >= pop) return;
     const int ind = order ? order[k] : k;
     const b200bt_individual iv = indiv[ind];
+    WarpShared* ws = reinterpret_cast<WarpShared*>(s_raw) + (threadIdx.x >> 5);
 
-    LaneConst c;
-    c.os_f = iv.rsi_lo;
-    c.ob_f = iv.rsi_hi;
-    c.tp = iv.take_profit;
-    c.sl = iv.stop_loss;
-    c.size = iv.position_size;
-    c.fee1 = __dmul_rn(c.size, 0.001);
-    c.fee2 = __dmul_rn(c.size, 0.002);
-    {
-        const double m = (double)SW_MARGIN;
-        c.hiL_c = (float)((1.0 + c.tp) * (1.0 - m));
-        c.hiL_d = (float)((1.0 + c.tp) * (1.0 + m));
-        c.loL_c = (float)((1.0 - c.sl) * (1.0 + m));
-        c.loL_d = (float)((1.0 - c.sl) * (1.0 - m));
-        c.loS_c = (float)((1.0 - c.tp) * (1.0 + m));
-        c.loS_d = (float)((1.0 - c.tp) * (1.0 - m));
-        c.hiS_c = (float)((1.0 + c.sl) * (1.0 - m));
-        c.hiS_d = (float)((1.0 + c.sl) * (1.0 + m));
+    if (lane == 0) {
+        ScanConst c;
+        c.os_f = iv.rsi_lo;
+        c.ob_f = iv.rsi_hi;
+        const double mg = (double)SW_MARGIN, tp = iv.take_profit, sl = iv.stop_loss;
+        c.hiL_c = (float)((1.0 + tp) * (1.0 - mg));
+        c.hiL_d = (float)((1.0 + tp) * (1.0 + mg));
+        c.loL_c = (float)((1.0 - sl) * (1.0 + mg));
+        c.loL_d = (float)((1.0 - sl) * (1.0 - mg));
+        c.loS_c = (float)((1.0 - tp) * (1.0 + mg));
+        c.loS_d = (float)((1.0 - tp) * (1.0 - mg));
+        c.hiS_c = (float)((1.0 + sl) * (1.0 - mg));
+        c.hiS_d = (float)((1.0 + sl) * (1.0 + mg));
+        ws->sc = c;
+        WarpAcc a;
+        a.tp = tp; a.sl = sl; a.size = iv.position_size;
+        a.fee1 = __dmul_rn(a.size, 0.001); a.fee2 = __dmul_rn(a.size, 0.002);
+        a.equity = cfg.initial_capital; a.peak = cfg.initial_capital; a.maxdd = 0.0;
+        a.tot_profit = a.tot_loss = a.largest_p = a.largest_l = 0.0;
+        a.day_sum = a.pivot = a.s1 = a.s2 = 0.0;
+        a.day_cur = 0; a.sum_dur = 0; a.hash = 0ull;
+        a.ev_out = events ? events + ((int64_t)ind * S + sym) * ev_cap : nullptr;
+        a.n_win = a.n_loss = a.n_days = a.n_events = 0;
+        a.day_valid = a.pivot_set = 0;
+        ws->acc = a;
     }
-    LaneAcc a;
-    a.equity = cfg.initial_capital;
-    a.peak = cfg.initial_capital;
-    a.maxdd = 0.0;
-    a.tot_profit = a.tot_loss = a.largest_p = a.largest_l = 0.0;
-    a.day_sum = a.pivot = a.s1 = a.s2 = 0.0;
-    a.day_cur = 0;
-    a.sum_dur = 0;
-    a.hash = 0ull;
-    a.n_win = a.n_loss = a.n_days = a.n_events = 0;
-    a.day_valid = a.pivot_set = 0;
+    __syncwarp();
 
     const float* __restrict__ pr = price + (int64_t)sym * ld_price;
     const float* __restrict__ rr = rsi + ((int64_t)sym * P + iv.rsi_row) * ld_rsi;
-    uint32_t* ev_out = events ? events + ((int64_t)ind * S + sym) * ev_cap : nullptr;
+    const long long minute0 = cfg.minute0;
+    const int bar_minutes = cfg.bar_minutes;
 
-    // machine state (warp-uniform)
-    int pos = 0;
-    float e = 0.f;
-    float rlo = c.os_f, rhi = c.ob_f, plo = -INFINITY, phi = INFINITY, plo_d = -INFINITY, phi_d = INFINITY;
-    // event queue: lane j holds event j of the current batch
-    unsigned q_w = 0;
-    float q_p = 0.f;
-    int qn = 0;
+    Machine m;
+    m.pos = 0; m.e = 0.f;
+    m.rlo = iv.rsi_lo; m.rhi = iv.rsi_hi; m.plo = -INFINITY; m.phi = INFINITY;
+    m.qhead = 0;
+    unsigned qtail = 0;
 
-    const float qnan = __int_as_float(0x7fc00000);
-    const int64_t ngroups = (N + 32 * SW_V - 1) / (32 * SW_V);
-    float pn[SW_V], rn[SW_V];
+    // Streams are staged through a per-warp shared-memory ring filled with cp.async
+    // (16 B per thread = 128 bars per instruction when the rows are 16-byte aligned):
+    // SW_STAGES-1 groups are always in flight, no registers are tied up by prefetch.
+    constexpr int G = SW_GROUP;               // bars per group
+    float* sp = &ws->ring[0][0][0];
+    const int n = (int)N;
+    const int n_full = n / G;                 // groups copied without bounds checks
+    const int n_groups = (n + G - 1) / G;
+    const bool vec16 = ((((uintptr_t)pr) | ((uintptr_t)rr)) & 15) == 0;
+    auto issue = [&](int g) {
+        float* dst = sp + (g % SW_STAGES) * (2 * G);
+        if (g < n_full) {
+            const float* gp = pr + (int64_t)g * G;
+            const float* gr = rr + (int64_t)g * G;
+            if (vec16) {
 #pragma unroll
-    for (int v = 0; v < SW_V; ++v) {
-        int64_t t = (int64_t)v * 32 + lane;
-        pn[v] = t < N ? __ldg(pr + t) : qnan;
-        rn[v] = t < N ? __ldg(rr + t) : qnan;
-    }
-    for (int64_t g = 0; g < ngroups; ++g) {
-        float pv[SW_V], rv[SW_V];
+                for (int i = 0; i < G / 128; ++i) {
+                    cp_async16(dst + i * 128 + lane * 4, gp + i * 128 + lane * 4);
+                    cp_async16(dst + G + i * 128 + lane * 4, gr + i * 128 + lane * 4);
+                }
+            } else {
 #pragma unroll
-        for (int v = 0; v < SW_V; ++v) { pv[v] = pn[v]; rv[v] = rn[v]; }
-        if (g + 1 < ngroups) {
-#pragma unroll
-            for (int v = 0; v < SW_V; ++v) {
-                int64_t t = ((g + 1) * SW_V + v) * 32 + lane;
-                pn[v] = t < N ? __ldg(pr + t) : qnan;
-                rn[v] = t < N ? __ldg(rr + t) : qnan;
+                for (int i = 0; i < G / 32; ++i) {
+                    cp_async4(dst + i * 32 + lane, gp + i * 32 + lane);
+                    cp_async4(dst + G + i * 32 + lane, gr + i * 32 + lane);
+                }
+            }
+        } else if (g < n_groups) {
+            // ragged last group: guarded loads, NaN beyond the series (NaN never fires an event)
+            const float qnan = __int_as_float(0x7fc00000);
+            for (int i = lane; i < G; i += 32) {
+                const int t = g * G + i;
+                dst[i] = t < n ? __ldg(pr + t) : qnan;
+                dst[G + i] = t < n ? __ldg(rr + t) : qnan;
             }
         }
+        cp_async_commit();  // always commit (possibly empty) so the group accounting stays uniform
+    };
 #pragma unroll
-        for (int v = 0; v < SW_V; ++v) {
-            const float p = pv[v], r = rv[v];
-            const int64_t t0 = (g * SW_V + v) * 32;
-            int start = 0;
-            while (true) {
-                const bool ev = (lane >= start) && (r < rlo || r > rhi || p <= plo || p >= phi);
-                const unsigned m = __ballot_sync(FULL, ev);
-                if (m == 0) break;
-                const int kk = __ffs(m) - 1;
-                const float pk = __shfl_sync(FULL, p, kk);
-                const float rk = __shfl_sync(FULL, r, kk);
-                start = kk + 1;
-                unsigned word;
-                if (pos == 0) {
-                    // entry (strategy_evaluation.py:784-813): long has priority over short
-                    e = pk;
-                    if (rk < c.os_f) {
-                        pos = 1;
-                        rlo = -INFINITY; rhi = c.ob_f;
-                        phi = e * c.hiL_c; phi_d = e * c.hiL_d;
-                        plo = e * c.loL_c; plo_d = e * c.loL_d;
-                        word = (unsigned)(t0 + kk);
-                    } else {
-                        pos = -1;
-                        rlo = c.os_f; rhi = INFINITY;
-                        phi = e * c.hiS_c; phi_d = e * c.hiS_d;
-                        plo = e * c.loS_c; plo_d = e * c.loS_d;
-                        word = (unsigned)(t0 + kk) | B200BT_EVENT_SELL;
-                    }
-                } else {
-                    // exit candidate (:815-847)
-                    bool definite = (rk < rlo) || (rk > rhi) || (pk >= phi_d) || (pk <= plo_d);
-                    if (!definite) {
-                        const double ed = (double)e, pd = (double)pk;
-                        const double q = (pos > 0) ? __ddiv_rn(__dsub_rn(pd, ed), ed)
-                                                   : __ddiv_rn(__dsub_rn(ed, pd), ed);
-                        if (!(q >= c.tp || q <= -c.sl)) continue;  // inside the screening band, no exit
-                    }
-                    word = (unsigned)(t0 + kk) | B200BT_EVENT_EXIT | (pos > 0 ? B200BT_EVENT_SELL : 0u);
-                    pos = 0;
-                    rlo = c.os_f; rhi = c.ob_f;
-                    plo = plo_d = -INFINITY; phi = phi_d = INFINITY;
-                }
-                if (lane == qn) { q_w = word; q_p = pk; }
-                if (++qn == 32) {
-                    process_batch(32, q_w, q_p, c, a, cfg, ev_out, ev_cap);
-                    qn = 0;
+    for (int g = 0; g < SW_STAGES - 1; ++g) issue(g);
+    for (int g = 0; g < n_groups; ++g) {
+        issue(g + SW_STAGES - 1);
+        cp_async_wait<SW_STAGES - 1>();       // group g has landed
+        __syncwarp();
+        const float* cur = sp + (g % SW_STAGES) * (2 * G) + lane;
+#pragma unroll 1
+        for (int v = 0; v < G / 32; v += 2) {
+            // two windows per step: both ballots are issued before either is needed
+            const float p0 = cur[v * 32], r0 = cur[G + v * 32];
+            const float p1 = cur[v * 32 + 32], r1 = cur[G + v * 32 + 32];
+            const unsigned h0 = __ballot_sync(FULL, fires(m, p0, r0));
+            const unsigned h1 = __ballot_sync(FULL, fires(m, p1, r1));
+            if (h0 | h1) {
+                const int t0 = g * G + v * 32;
+                if (h0) scan_window(p0, r0, t0, lane, ws, m);
+                scan_window(p1, r1, t0 + 32, lane, ws, m);
+                while (m.qhead - qtail >= 32) {
+                    __syncwarp();
+                    process_batch(ws, qtail, 32, minute0, bar_minutes, ev_cap);
+                    qtail += 32;
                 }
             }
         }
+        __syncwarp();                         // stage is refilled by the next iteration's issue
     }
-    if (pos != 0) {
+    cp_async_wait<0>();
+    if (m.pos != 0) {
         // force-close at the last bar (:849-876)
         const float pl = __ldg(pr + (N - 1));
-        const unsigned word = (unsigned)(N - 1) | B200BT_EVENT_EXIT | (pos > 0 ? B200BT_EVENT_SELL : 0u);
-        if (lane == qn) { q_w = word; q_p = pl; }
-        ++qn;
+        const unsigned word = (unsigned)(N - 1) | B200BT_EVENT_EXIT | (m.pos > 0 ? B200BT_EVENT_SELL : 0u);
+        if (lane == 0) ws->evq[m.qhead & (SW_EVQ - 1)] = make_uint2(word, __float_as_uint(pl));
+        ++m.qhead;
     }
-    if (qn > 0) process_batch(qn, q_w, q_p, c, a, cfg, ev_out, ev_cap);
+    __syncwarp();
+    while (m.qhead != qtail) {
+        const int cnt = min(32u, m.qhead - qtail);
+        process_batch(ws, qtail, cnt, minute0, bar_minutes, ev_cap);
+        qtail += cnt;
+    }
 
     if (lane == 0) {
-        if (a.day_valid) day_complete(a, a.day_sum);
+        const WarpAcc a = ws->acc;
+        DayAcc da{a.pivot, a.s1, a.s2, a.n_days, a.pivot_set};
+        if (a.day_valid) day_complete(da, a.day_sum);
         b200bt_lane_stats o;
         const double n_rec = (double)a.n_events;
         o.n_records = n_rec;
@@ -315,7 +436,7 @@ sweep_kernel(const float* __restrict__ price, int64_t ld_price,
         o.total_loss = a.tot_loss;
         o.net_profit = a.tot_profit + a.tot_loss;
         o.max_drawdown = a.maxdd;
-        o.n_days = (double)a.n_days;
+        o.n_days = (double)da.n_days;
         o.largest_profit = a.largest_p;
         o.largest_loss = a.largest_l;
         o.sum_duration_bars = (double)a.sum_dur;
@@ -324,13 +445,13 @@ sweep_kernel(const float* __restrict__ price, int64_t ld_price,
         if (a.n_events >= 2) {
             win_rate = (double)a.n_win / n_rec;
             pf = (a.tot_loss != 0.0) ? fabs(a.tot_profit / a.tot_loss) : INFINITY;
-            if (a.n_days > 1) {
-                const double n = (double)a.n_days;
-                const double mean_y = a.s1 / n;
-                double var = a.s2 / n - mean_y * mean_y;
+            if (da.n_days > 1) {
+                const double nd = (double)da.n_days;
+                const double mean_y = da.s1 / nd;
+                double var = da.s2 / nd - mean_y * mean_y;
                 if (var < 0.0) var = 0.0;
                 const double sd = sqrt(var);
-                const double mean = a.pivot + mean_y;
+                const double mean = da.pivot + mean_y;
                 sharpe = sd > 0.0 ? (mean / sd) * sqrt(252.0) : 0.0;
             }
         }
@@ -379,10 +500,16 @@ extern "C" int b200bt_sweep(const float* price, int64_t ld_price, const float* r
     B200BT_REQUIRE(events == nullptr || event_cap > 0, B200BT_EINVAL, "sweep: event buffer without capacity");
     int rc = check_device();
     if (rc) return rc;
-    const int64_t lanes = (int64_t)pop * S;
-    const int64_t blocks = (lanes + SW_WARPS - 1) / SW_WARPS;
+    const int64_t blocks = (int64_t)((pop + SW_WARPS - 1) / SW_WARPS) * S;
     B200BT_REQUIRE(blocks < (1ll << 31), B200BT_ELIMIT, "sweep: too many lanes");
-    sweep_kernel<<<(unsigned)blocks, SW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    const size_t smem = sizeof(WarpShared) * SW_WARPS;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e, "sweep: cudaFuncSetAttribute");
+        attr_set = true;
+    }
+    sweep_kernel<<<(unsigned)blocks, SW_WARPS * 32, smem, (cudaStream_t)stream>>>(
         price, ld_price, rsi, ld_rsi, P, S, N, indiv, order, pop, *cfg_host, stats, events, event_cap);
     B200BT_LAUNCH_CHECK("sweep launch");
     return B200BT_OK;

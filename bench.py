@@ -211,7 +211,7 @@ def main():
     import torch
     import torch.distributed as dist
     from ai_crypto_trader_b200 import _lib, synth
-    from ai_crypto_trader_b200.sweep import MarketData, PopulationSweep, decode_population
+    from ai_crypto_trader_b200.sweep import MarketData, PopulationSweep, decode_population, evaluation_order
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -231,7 +231,7 @@ def main():
     population = synth.random_population(pop_global, seed=42)
     my_pop = population[rank * pop_local:(rank + 1) * pop_local]
     packed = decode_population(my_pop, sweep.period_row)
-    order = np.argsort(packed["rsi_row"], kind="stable").astype(np.int32)
+    order = evaluation_order(my_pop)
     indiv_dev = torch.from_numpy(packed.view(np.uint8)).to(dev)
     order_dev = torch.from_numpy(order).to(dev)
     fit_local = torch.empty(pop_local, dtype=torch.float64, device=dev)
