@@ -163,6 +163,46 @@ int b200bt_sweep(const float* price, int64_t ld_price,
 int b200bt_fitness_reduce(const b200bt_lane_stats* stats, int pop, int S,
                           double* fitness, b200bt_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Family 3: Monte-Carlo risk projection.
+ * Replaces the path generation and per-path loops of
+ *   MonteCarloService.run_monte_carlo_simulation  services/monte_carlo_service.py:197-394
+ * Randomness: Philox4x32-10, counter = (path index lo, hi, step/4, mode),
+ * key = seed; normals by Box-Muller on 24-bit uniforms.  A path's values depend
+ * only on (seed, path_offset + local index, step), never on sharding.
+ * Outputs: finals[n] = S_T, maxdd[n] = max_t (runmax_t - S_t)/runmax_t (:327-336),
+ * optional paths[(steps+1)][n] fp32 (the reference's `paths` array, shape (days, n)).
+ * ------------------------------------------------------------------------ */
+
+/* Geometric Brownian motion (:266-273): `steps` = days-1 multiplicative steps of
+ * exp((mu - sigma^2/2) dt + sigma sqrt(dt) Z). */
+int b200bt_mc_gbm(double s0, double mu, double sigma, double dt, int64_t n_paths, int steps,
+                  uint64_t seed, uint64_t path_offset, float* finals, float* maxdd,
+                  float* paths_or_null, b200bt_stream_t stream);
+
+/* 'historical' simulation (:277-298): bootstrap of the return sample with
+ * replacement.  block_len = 1 reproduces the reference (iid); block_len > 1 is a
+ * circular block bootstrap.  log_returns != 0: P_t = P_{t-1} exp(r); else
+ * P_t = P_{t-1} (1 + r).  `returns` is a device array of R <= 12288 fp32 values. */
+int b200bt_mc_bootstrap(const float* returns, int R, int block_len, int log_returns, double s0,
+                        int64_t n_paths, int steps, uint64_t seed, uint64_t path_offset,
+                        float* finals, float* maxdd, float* paths_or_null, b200bt_stream_t stream);
+
+/* Exact order statistics: out[r] = ranks[r]-th smallest (0-based) of x[0..n).
+ * ranks_dev: device int64[n_ranks], ASCENDING, n_ranks <= 64.  Two-level radix
+ * select; workspace of b200bt_select_workspace_bytes(n_ranks) device bytes.
+ * Feeds np.percentile's linear interpolation (:308-317) on the host side. */
+int64_t b200bt_select_workspace_bytes(int n_ranks);
+int b200bt_select(const float* x, int64_t n, const int64_t* ranks_dev, int n_ranks, float* out,
+                  void* workspace, int64_t workspace_bytes, b200bt_stream_t stream);
+
+/* Moments of the final prices (:305-336).  out7 (device, float64):
+ *  [0] sum S_T  [1] sum pct  [2] #(S_T > s0)  [3] sum maxdd  [4] max maxdd
+ *  [5] sum pct[pct <= var_threshold]  [6] #(pct <= var_threshold)
+ * with pct = (S_T/s0 - 1)*100 in float64; maxdd may be NULL. */
+int b200bt_mc_moments(const float* finals, const float* maxdd, int64_t n, double s0,
+                      double var_threshold, double* out7, b200bt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@ Writes (all small, committed):
     tests/golden/sim_cases.json   parameter sets + reference metrics / score
     tests/golden/sim_cases.npz    fp32 inputs + reference trade records
     tests/golden/ga_run.json      seeded GeneticAlgorithm trajectory
+    tests/golden/mc_reference.*   MonteCarloService results + its own paths (NumPy seed fixed)
 Inputs are the fp32 synthetic series of ai_crypto_trader_b200.synth; the RSI
 bank is oracle.indicators_ref.rsi_bank (float64 pandas, rounded to fp32).
 The reference functions executed are
@@ -136,6 +137,62 @@ def make_ga():
     (OUT / "ga_run.json").write_text(json.dumps({"runs": runs}, indent=1))
 
 
+
+
+def make_mc():
+    """Reference MonteCarloService.run_monte_carlo_simulation, NumPy global seed fixed,
+    `store_all_paths` on so the fixture holds the reference's own paths."""
+    import pandas as pd
+    out = {}
+    meta = []
+    rng = np.random.default_rng(7)
+    returns = rng.normal(5e-4, 0.02, 60)
+    for method, n, days, scenario in (("geometric_brownian_motion", 400, 30, "base"),
+                                      ("geometric_brownian_motion", 250, 12, "volatile"),
+                                      ("historical", 120, 20, "bear")):
+        params = {
+            "num_simulations": n, "time_horizon_days": days, "confidence_level": 0.95, "lookback_days": 60,
+            "return_method": "log", "simulation_method": method, "plot_chart": False, "store_all_paths": True,
+            "scenarios": {"base": {}, "bull": {"drift_factor": 1.5, "volatility_factor": 0.8},
+                          "bear": {"drift_factor": 0.5, "volatility_factor": 1.2},
+                          "volatile": {"drift_factor": 1.0, "volatility_factor": 2.0},
+                          "crab": {"drift_factor": 0.2, "volatility_factor": 0.5}}}
+        svc = ref_runner.monte_carlo_service(params)
+        svc.historical_data["SYNUSDC"] = pd.DataFrame({"returns": returns})
+        np.random.seed(20240921)
+        res = svc.run_monte_carlo_simulation("SYNUSDC", 100.0, scenario=scenario)      # REFERENCE
+        assert res, "reference simulation failed"
+        key = f"{method}_{scenario}"
+        out[f"paths_{key}"] = np.array(res["paths"], dtype=np.float64)
+        res = dict(res); res.pop("paths"); res.pop("timestamp")
+        meta.append({"key": key, "method": method, "scenario": scenario, "n": n, "days": days, "result": res})
+        print(f"MC {key}: VaR={res['risk_metrics']['var']:.4f} mdd_mean={res['risk_metrics']['max_drawdown']['mean']:.4f}")
+    out["returns"] = returns
+    # portfolio statistics (:577-659) on reference simulations
+    svc = ref_runner.monte_carlo_service(params)
+    svc.historical_data["AAAUSDC"] = pd.DataFrame({"returns": returns})
+    svc.historical_data["BBBUSDC"] = pd.DataFrame({"returns": returns * 1.5})
+    holdings = {"total_value": 15000.0, "assets": {"AAA": {"value_usdc": 6000.0, "current_price": 10.0},
+                                                    "BBB": {"value_usdc": 4000.0, "current_price": 2.5},
+                                                    "USDC": {"value_usdc": 5000.0, "current_price": 1.0}}}
+    np.random.seed(99)
+    sims = {}
+    for a in ("AAA", "BBB"):
+        for sc in params["scenarios"]:
+            r = svc.run_monte_carlo_simulation(f"{a}USDC", holdings["assets"][a]["current_price"], scenario=sc)
+            r = dict(r); r.pop("paths"); r.pop("timestamp")
+            sims[f"{a}USDC_{sc}"] = r
+    pstats = svc._calculate_portfolio_stats(holdings, sims)                             # REFERENCE
+    np.savez_compressed(OUT / "mc_reference.npz", **out)
+    (OUT / "mc_reference.json").write_text(json.dumps(
+        {"cases": meta, "portfolio": {"holdings": holdings, "simulations": sims, "stats": pstats}}, indent=1))
+
+
 if __name__ == "__main__":
-    make_sim()
-    make_ga()
+    which = sys.argv[1:] or ["sim", "ga", "mc"]
+    if "sim" in which:
+        make_sim()
+    if "ga" in which:
+        make_ga()
+    if "mc" in which:
+        make_mc()
