@@ -1,0 +1,175 @@
+"""StrategyEvaluationSystem / StrategyPerformanceMetrics call surface on the GPU engine.
+
+Reference: services/strategy_evaluation.py.
+  StrategyEvaluationSystem._simulate_trades(strategy_id, parameters, market_data)   :746-878
+  StrategyPerformanceMetrics.calculate_metrics(trades, initial_capital)             :32-228
+  StrategyEvaluationSystem._calculate_strategy_score(metrics)                       :579-633
+
+`_simulate_trades` keeps the reference's signature and returns the reference's trade
+records (one dict per entry and per exit, keys timestamp/symbol/side/price/quantity/
+fees/pnl); the bar-by-bar state machine runs in the sweep kernel (one lane), the host
+only formats the O(#trades) records.  `evaluate_population` is the batched form the GA
+uses.  Market data contract: price and rsi are fp32 (values are rounded to fp32 on
+upload; DESIGN.md "Data contract").
+"""
+from __future__ import annotations
+
+import json
+import logging
+from datetime import datetime
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .sweep import DEFAULT_GOALS, MarketData, PopulationSweep
+
+logger = logging.getLogger("b200bt.strategy_evaluation")
+
+
+class StrategyPerformanceMetrics:
+    """Host-side metrics over an arbitrary list of trade records (e.g. live trades handed in
+    by a caller).  The GA path never calls this: there the same quantities are reduced inside
+    the sweep kernel.  Restates calculate_metrics (:32-228) for the scalar fields."""
+
+    @staticmethod
+    def calculate_metrics(trades: List[Dict], initial_capital: float = 10000.0) -> Dict:
+        base = {"total_trades": 0, "win_rate": 0.0, "profit_factor": 0.0, "sharpe_ratio": 0.0, "max_drawdown": 0.0,
+                "average_profit": 0.0, "average_loss": 0.0, "largest_profit": 0.0, "largest_loss": 0.0,
+                "total_profit": 0.0, "total_loss": 0.0, "net_profit": 0.0, "return_pct": 0.0,
+                "avg_trade_duration": 0, "risk_reward_ratio": 0.0, "profitable_symbols": {},
+                "unprofitable_symbols": {}, "monthly_returns": {}, "daily_returns": {}}
+        if not trades:
+            return base
+        recs = sorted(trades, key=lambda t: t.get("timestamp", ""))
+        pnl = [t.get("pnl", 0) for t in recs]
+        if len(recs) < 2:
+            p = pnl[0]
+            base.update(total_trades=1, win_rate=1.0 if p > 0 else 0.0, net_profit=p,
+                        return_pct=(p / initial_capital) * 100)
+            for key, cond in (("average_profit", p > 0), ("largest_profit", p > 0), ("total_profit", p > 0),
+                              ("average_loss", p < 0), ("largest_loss", p < 0), ("total_loss", p < 0)):
+                base[key] = p if cond else 0.0
+            return base
+        wins = [p for p in pnl if p > 0]
+        losses = [p for p in pnl if p < 0]
+        tp, tl = sum(wins), sum(losses)
+        equity, peak, dds = [initial_capital], initial_capital, []
+        daily, monthly, by_symbol = {}, {}, {}
+        for t, p in zip(recs, pnl):
+            cur = equity[-1] + p
+            equity.append(cur)
+            if cur > peak:
+                peak = cur
+            else:
+                dds.append((peak - cur) / peak)
+            ts = t.get("timestamp", "")
+            if ts:
+                try:
+                    d = datetime.fromisoformat(ts.replace("Z", "+00:00"))
+                    for key, bucket in ((d.strftime("%Y-%m-%d"), daily), (d.strftime("%Y-%m"), monthly)):
+                        bucket[key] = bucket[key] + p if key in bucket else p
+                except ValueError:
+                    pass
+            sym = t.get("symbol", "UNKNOWN")
+            by_symbol[sym] = by_symbol.get(sym, 0) + p
+        durs = []
+        for i in range(0, len(recs) - 1, 2):
+            try:
+                a = datetime.fromisoformat(recs[i].get("timestamp", "").replace("Z", "+00:00"))
+                b = datetime.fromisoformat(recs[i + 1].get("timestamp", "").replace("Z", "+00:00"))
+                durs.append((b - a).total_seconds() / 60)
+            except ValueError:
+                pass
+        vals = list(daily.values())
+        sharpe = 0
+        if len(vals) > 1:
+            sd = np.std(vals)
+            sharpe = (np.mean(vals) / sd) * np.sqrt(252) if sd > 0 else 0
+        avg_p = tp / len(wins) if wins else 0
+        avg_l = tl / len(losses) if losses else 0
+        net = tp + tl
+        return {
+            "total_trades": len(recs), "win_rate": len(wins) / len(recs),
+            "profit_factor": abs(tp / tl) if tl != 0 else float("inf"), "sharpe_ratio": sharpe,
+            "max_drawdown": max(dds) if dds else 0, "average_profit": avg_p, "average_loss": avg_l,
+            "largest_profit": max(wins) if wins else 0, "largest_loss": min(losses) if losses else 0,
+            "total_profit": tp, "total_loss": tl, "net_profit": net, "return_pct": (net / initial_capital) * 100,
+            "avg_trade_duration": sum(durs) / len(durs) if durs else 0,
+            "risk_reward_ratio": abs(avg_p / avg_l) if avg_l != 0 else float("inf"),
+            "profitable_symbols": {s: v for s, v in by_symbol.items() if v > 0},
+            "unprofitable_symbols": {s: v for s, v in by_symbol.items() if v <= 0},
+            "monthly_returns": monthly, "daily_returns": daily, "equity_curve": equity,
+        }
+
+
+class StrategyEvaluationSystem:
+    def __init__(self, config_path: Optional[str] = "config.json", config: Optional[Dict] = None):
+        if config is None:
+            try:
+                with open(config_path, "r") as f:
+                    config = json.load(f)
+            except (OSError, TypeError):
+                config = {}
+        self.config = config
+        self.optimization_goals = self.config.get("evolution", {}).get("optimization_goals", {}) or dict(DEFAULT_GOALS)
+        self.performance_metrics = self.config.get("evolution", {}).get("performance_metrics", {})
+
+    # -- reference-compatible single-strategy call -----------------------------------
+    def _simulate_trades(self, strategy_id: str, parameters: Dict, market_data: List[Dict]) -> List[Dict]:
+        if not market_data:
+            return []
+        n = len(market_data)
+        price = np.array([d.get("price", 50000) for d in market_data], dtype=np.float32)
+        rsi = np.array([d.get("rsi", 50) for d in market_data], dtype=np.float32)
+        ohlcv = np.zeros((5, 1, n), dtype=np.float32)
+        ohlcv[3, 0] = price
+        market = MarketData(ohlcv)
+        period = int(parameters.get("rsi_period", 14))
+        sweep = PopulationSweep.from_bank(market, torch.from_numpy(rsi).to(market.device).view(1, 1, n), [period],
+                                          self.optimization_goals, event_cap=n + 1)
+        sweep.evaluate([dict(parameters)])
+        n_rec = int(sweep.lane_stats()["n_records"][0, 0])
+        ev = sweep.events()[0, 0, :n_rec]
+        size = 10000 * (min(parameters.get("max_position_size", 5), 20) / 100)     # :761-764
+        out, entry = [], 0.0
+        for w in ev.tolist():
+            bar, is_exit, sell = w & _lib.EVENT_BAR_MASK, bool(w & _lib.EVENT_EXIT), bool(w & _lib.EVENT_SELL)
+            d = market_data[bar]
+            px = float(price[bar])
+            if not is_exit:
+                entry = px
+                qty, pnl = size / px, -size * 0.001
+            else:
+                qty = size / entry
+                pnl = qty * ((px - entry) if sell else (entry - px)) - size * 0.002
+            out.append({"timestamp": d.get("timestamp", f"2023-01-{bar + 1:02d}T00:00:00Z"),
+                        "symbol": d.get("symbol", "BTCUSDT"), "side": "sell" if sell else "buy", "price": px,
+                        "quantity": qty, "fees": size * 0.001, "pnl": pnl})
+        return out
+
+    def _calculate_strategy_score(self, metrics: Dict) -> float:
+        goals = self.optimization_goals
+        score = metrics.get(goals.get("primary", "sharpe_ratio"), 0)
+        for name in goals.get("secondary", []):
+            if name == "max_drawdown":
+                score *= (1 - metrics.get("max_drawdown", 0))
+            elif name == "win_rate":
+                score *= (1 + metrics.get("win_rate", 0))
+            elif name == "profit_factor":
+                score *= (metrics.get("profit_factor", 1) / 2)
+            elif name == "expectancy":
+                score *= (1 + min(metrics.get("expectancy", 0) / 100, 1))
+        floor = goals.get("constraints", {}).get("min_trades_per_day", 0)
+        per_day = metrics.get("trades_per_day", floor)
+        if per_day < floor:
+            score *= per_day / floor
+        return score
+
+    # -- batched form -------------------------------------------------------------
+    def evaluate_population(self, population: List[Dict], market: MarketData,
+                            sweep: Optional[PopulationSweep] = None) -> np.ndarray:
+        """fitness[i] = mean over symbols of score(metrics(simulate(population[i], symbol)))."""
+        sweep = sweep or PopulationSweep(market, optimization_goals=self.optimization_goals)
+        return sweep.evaluate(population)

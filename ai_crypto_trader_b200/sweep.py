@@ -179,6 +179,28 @@ class PopulationSweep:
         self._pinned_in = None
         self._pinned_out = None
 
+    @classmethod
+    def from_bank(cls, market: MarketData, bank: torch.Tensor, periods, optimization_goals=None,
+                  initial_capital: float = 10000.0, event_cap: int = 0) -> "PopulationSweep":
+        """Sweep over a caller-supplied RSI bank [S][P][N] (e.g. the 'rsi' field of the reference's
+        market-data points) instead of one computed from the close prices."""
+        self = cls.__new__(cls)
+        self.market = market
+        self.periods = [int(p) for p in periods]
+        self.period_row = {p: i for i, p in enumerate(self.periods)}
+        goals = optimization_goals or DEFAULT_GOALS
+        self.cfg = _lib.SweepConfig(
+            initial_capital=float(initial_capital), minute0=market.minute0, bar_minutes=market.bar_minutes,
+            primary=_lib.PRIMARY[goals.get("primary", "sharpe_ratio")],
+            secondary_mask=sum(_lib.SECONDARY.get(m, 0) for m in goals.get("secondary", [])), variant=0)
+        self.event_cap = int(event_cap)
+        assert bank.is_cuda and bank.dtype == torch.float32 and tuple(bank.shape) == (market.S, len(self.periods), market.N)
+        self.bank = bank.contiguous()
+        self._stats = self._events = None
+        self._pop = 0
+        self._pinned_in = self._pinned_out = None
+        return self
+
     # -- device-side evaluation (inputs already resident) -------------------
     def evaluate_device(self, indiv_dev: torch.Tensor, order_dev: Optional[torch.Tensor], pop: int,
                         fitness_dev: torch.Tensor) -> None:

@@ -134,3 +134,45 @@ def test_sweep_vs_c_oracle_random_populations(torch_cuda, n_bars, pop, n_sym):
                 assert stats[f][i, s] == pytest.approx(float(want[f]), rel=1e-9, abs=1e-11), (i, s, f)
             scores[i, s] = want["score"]
     np.testing.assert_allclose(fitness, scores.mean(axis=1), rtol=1e-9, atol=1e-11)
+
+
+def test_simulate_trades_dropin_returns_reference_records(torch_cuda, sim_golden):
+    """StrategyEvaluationSystem._simulate_trades (reference signature) -> the reference's own records."""
+    from ai_crypto_trader_b200.strategy_evaluation import StrategyEvaluationSystem, StrategyPerformanceMetrics
+    from oracle import simulate_ref
+    meta, arrays = sim_golden
+    ses = StrategyEvaluationSystem(config={"evolution": {"optimization_goals": meta["goals"]}})
+    for c in meta["cases"][:6]:
+        period = c["params"].get("rsi_period", 14)
+        pts = simulate_ref.market_points(arrays[f"close_{c['symbol']}"], arrays[f"rsi_{c['symbol']}_{period}"],
+                                         f"SYN{c['symbol']:03d}USDT", meta["minute0"])
+        recs = ses._simulate_trades(c["name"], dict(c["params"]), pts)
+        key = c["key"]
+        assert len(recs) == c["n_records"]
+        assert [r["side"] == "sell" for r in recs] == arrays[f"sell_{key}"].tolist()
+        assert np.array_equal(np.array([r["pnl"] for r in recs]), arrays[f"pnl_{key}"])          # bit-identical float64
+        assert np.array_equal(np.array([r["quantity"] for r in recs]), arrays[f"qty_{key}"])
+        m = StrategyPerformanceMetrics.calculate_metrics(recs)
+        for name, want in c["metrics"].items():
+            assert float(m[name]) == unjson(want), (key, name)
+        assert float(ses._calculate_strategy_score(m)) == unjson(c["score"])
+    assert ses._simulate_trades("empty", {}, []) == []
+
+
+def test_evolution_service_runs_ga_on_gpu(torch_cuda):
+    import asyncio
+    from ai_crypto_trader_b200 import synth
+    from ai_crypto_trader_b200.evolution import StrategyEvolutionService
+    from ai_crypto_trader_b200.sweep import MarketData
+    market = MarketData(synth.synth_ohlcv(2, 30000))
+    svc = StrategyEvolutionService(market, random_seed=42)
+    svc.ga_population_size, svc.ga_generations = 24, 3
+    cur = synth.random_population(1, seed=9)[0]
+    best = asyncio.run(svc.optimize_with_genetic_algorithm(cur))
+    assert best is not None and set(best) == set(svc.param_ranges)
+    hist = svc.last_ga.get_generation_history()
+    assert len(hist) == 4 and hist[-1]["best_fitness"] >= hist[0]["best_fitness"]
+    # the GA's recorded fitness of the final population equals a fresh sweep of it
+    again = svc.sweep.evaluate(svc.last_ga.population)
+    np.testing.assert_array_equal(np.array(svc.last_ga.fitness_scores), again)
+    assert svc.evolution_records[-1]["new_params"] == best
