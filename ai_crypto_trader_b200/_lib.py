@@ -33,6 +33,14 @@ class Individual(C.Structure):
     ]
 
 
+class BtParams(C.Structure):
+    _fields_ = [
+        ("initial_balance", C.c_double), ("position_pct", C.c_double), ("stop_loss_pct", C.c_double),
+        ("take_profit_pct", C.c_double), ("volume_factor", C.c_double), ("max_risk_per_trade", C.c_double),
+        ("can_enter", C.c_int32), ("skip", C.c_int32),
+    ]
+
+
 class SweepConfig(C.Structure):
     _fields_ = [
         ("initial_capital", C.c_double),
@@ -64,9 +72,21 @@ _SIGNATURES = {
     "b200bt_last_error": (C.c_char_p, []),
     "b200bt_launch_count": (C.c_int64, []),
     "b200bt_rsi_bank": (C.c_int, [_vp, _i, _i64, _i64, C.POINTER(C.c_int), _i, _i, _vp, _vp]),
+    "b200bt_ema_bank": (C.c_int, [_vp, _i, _i64, _i64, C.POINTER(C.c_int), _i, _vp, _vp]),
+    "b200bt_sma_bank": (C.c_int, [_vp, _i, _i64, _i64, C.POINTER(C.c_int), _i, _vp, _vp]),
+    "b200bt_macd": (C.c_int, [_vp, _i, _i64, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "b200bt_bollinger": (C.c_int, [_vp, _i, _i64, _i64, _i, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200bt_stochastic": (C.c_int, [_vp, _vp, _vp, _i, _i64, _i64, _i, _i, _vp, _vp, _vp]),
+    "b200bt_williams_r": (C.c_int, [_vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _vp]),
+    "b200bt_ichimoku": (C.c_int, [_vp, _vp, _i, _i64, _i64, _i, _i, _i, _vp, _vp, _vp]),
+    "b200bt_atr_bank": (C.c_int, [_vp, _vp, _vp, _i, _i64, _i64, C.POINTER(C.c_int), _i, _vp, _vp]),
+    "b200bt_vwap": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _vp]),
+    "b200bt_nanfill_workspace_floats": (C.c_int64, [_i64, _i64]),
+    "b200bt_nanfill": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "b200bt_sweep": (C.c_int, [_vp, _i64, _vp, _i64, _i, _i, _i64, _vp, _vp, _i,
                                C.POINTER(SweepConfig), _vp, _vp, _i64, _vp]),
     "b200bt_fitness_reduce": (C.c_int, [_vp, _i, _i, _vp, _vp]),
+    "b200bt_backtest_ref": (C.c_int, [_vp, _i64, _i, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "b200bt_mc_gbm": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_double, _i64, _i, C.c_uint64, C.c_uint64,
                                 _vp, _vp, _vp, _vp]),
     "b200bt_mc_bootstrap": (C.c_int, [_vp, _i, _i, _i, C.c_double, _i64, _i, C.c_uint64, C.c_uint64,

@@ -1,0 +1,790 @@
+// Family 1 (continued): EMA / MACD / SMA / Bollinger / stochastic / Williams %R /
+// Ichimoku / ATR / VWAP over fp32 OHLCV, plus the TechnicalAnalyzer NaN policy (sm_100a).
+//
+// Reference call sites: binance_ml_strategy.py:63-182 (TechnicalAnalyzer, via the third-party
+// `ta` package, whose definitions are restated in oracle/indicators_ref.py) and
+// services/market_monitor_service.py:219-301.
+//
+// Common scheme: one CTA per (symbol, time tile).  The input tile plus a halo is staged in
+// shared memory once; arithmetic is fp64 so a float64 CPU evaluation rounds to the same
+// fp32 outputs; undefined leading values are written as NaN and, when the caller asks for
+// the reference's `_handle_nan_values` policy, resolved by the nanfill kernels
+// (ffill -> bfill -> 0).
+//   * exponential recurrences (EMA, MACD, ATR): time-parallel affine warp scan, tiles made
+//     independent by a warm-up halo that attenuates the unknown state below 2^-60;
+//   * window sums (SMA, Bollinger, VWAP, %D): fp64 prefix sums of tile-offset values in
+//     shared memory, window sum = difference of two prefixes;
+//   * window extrema (stochastic, Williams, Ichimoku): direct scan of the window in shared
+//     memory (exact: min/max do not round).
+#include <math.h>
+#include "common.cuh"
+
+namespace b200bt {
+
+constexpr int IND_TILE = 2048;
+constexpr int IND_THREADS = 256;
+constexpr int IND_MAX_WINDOW = 1024;
+constexpr int IND_MAX_P = 64;
+__device__ __forceinline__ float nanf32() { return __int_as_float(0x7fc00000); }
+
+struct BankParams {
+    int window[IND_MAX_P];
+    int halo[IND_MAX_P];
+};
+
+// ---------------------------------------------------------------------------------
+// Affine warp scan: y_t = om*y_{t-1} + b_t over 32 lanes x K consecutive bars per lane.
+// In: b[K] per lane (already scaled), carry = state before the block's first bar.
+// Out: y[K] = states after each of the lane's bars; carry updated to the state after the
+// block's last bar.  apow[i] = (om^K)^(2^i), alane = (om^K)^(lane+1).
+// ---------------------------------------------------------------------------------
+template <int K>
+struct AffineScan {
+    double om, apow[5], alane;
+    __device__ void init(double om_, int lane) {
+        om = om_;
+        double a = 1.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) a *= om;
+        apow[0] = a;
+#pragma unroll
+        for (int i = 1; i < 5; ++i) apow[i] = apow[i - 1] * apow[i - 1];
+        alane = 1.0;
+        int e = lane + 1;
+        double b = a;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            if (e & 1) alane *= b;
+            b *= b;
+            e >>= 1;
+        }
+    }
+    __device__ void run(const double (&b)[K], double& carry, double (&y)[K], int lane) const {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc = acc * om + b[j];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const double up = shfl_up_d(acc, 1 << i);
+            if (lane >= (1 << i)) acc += apow[i] * up;
+        }
+        const double end = acc + alane * carry;
+        double st = shfl_up_d(end, 1);
+        if (lane == 0) st = carry;
+        carry = shfl_d(end, 31);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            st = st * om + b[j];
+            y[j] = st;
+        }
+    }
+};
+
+__device__ __forceinline__ void stage_row(const float* __restrict__ row, int64_t N, int64_t s0, int n_stage,
+                                          float* __restrict__ dst) {
+    for (int i = threadIdx.x; i < n_stage; i += blockDim.x) {
+        int64_t t = s0 + i;
+        t = t < 0 ? 0 : (t >= N ? N - 1 : t);
+        dst[i] = __ldg(row + t);
+    }
+}
+
+static int halo_for(double om) {
+    // om^L <= 2^-60
+    if (!(om > 0.0)) return 4;
+    double L = ceil(60.0 * log(2.0) / -log(om));
+    if (!(L < 1e9)) L = 1e9;
+    return ((int)L + 3) & ~3;
+}
+
+// ---------------------------------------------------------------------------------
+// EMA bank: ta.trend.EMAIndicator = close.ewm(span=w, min_periods=w, adjust=False).mean()
+// (binance_ml_strategy.py:79-83): y_0 = x_0, alpha = 2/(w+1), defined for t >= w-1.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(IND_THREADS)
+ema_bank_kernel(const float* __restrict__ x, int64_t N, int64_t ld, const __grid_constant__ BankParams prm, int P,
+                int halo_max, float* __restrict__ out) {
+    extern __shared__ float s_x[];  // s_x[i] = x[s0 + i]
+    const int sym = blockIdx.y;
+    const int64_t tile_start = (int64_t)blockIdx.x * IND_TILE;
+    const int64_t tile_end = min(tile_start + (int64_t)IND_TILE, N);
+    const int64_t s0 = max((int64_t)0, tile_start - halo_max);
+    const int n_stage = (int)(tile_start + IND_TILE - s0);
+    stage_row(x + (int64_t)sym * ld, N, s0, n_stage, s_x);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    constexpr int K = 4;
+    for (int pi = warp; pi < P; pi += nwarp) {
+        const int w = prm.window[pi];
+        float* orow = out + ((int64_t)sym * P + pi) * N;
+        const double alpha = 2.0 / ((double)w + 1.0), om = 1.0 - alpha;
+        AffineScan<K> sc;
+        sc.init(om, lane);
+        int64_t start = max(s0, tile_start - prm.halo[pi]) & ~(int64_t)3;
+        double carry = (start == 0) ? (double)s_x[(int)(0 - s0)] : 0.0;  // y_{-1} := x_0 gives y_0 = x_0
+        for (int64_t base = start; base < tile_end; base += 32 * K) {
+            const int64_t t = base + lane * K;
+            double b[K], y[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) b[j] = alpha * (double)s_x[min((int)(t + j - s0), n_stage - 1)];
+            sc.run(b, carry, y, lane);
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                if (t + j >= tile_start && t + j < tile_end) orow[t + j] = (t + j >= w - 1) ? (float)y[j] : nanf32();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// MACD (ta.trend.MACD, binance_ml_strategy.py:91-94): line = EMA_fast - EMA_slow (defined where
+// both are), signal = ewm(span=sign, min_periods=sign, adjust=False) of the line seeded with its
+// first defined value, diff = line - signal.  One warp per CTA does the three scans in sequence.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+macd_kernel(const float* __restrict__ x, int64_t N, int64_t ld, int fast, int slow, int sign, int halo_ema, int halo_sig,
+            float* __restrict__ o_line, float* __restrict__ o_sig, float* __restrict__ o_diff) {
+    extern __shared__ double s_line[];  // line over [s0, tile_end)
+    const int sym = blockIdx.y, lane = threadIdx.x;
+    const int64_t tile_start = (int64_t)blockIdx.x * IND_TILE;
+    const int64_t tile_end = min(tile_start + (int64_t)IND_TILE, N);
+    const int64_t s1 = max((int64_t)0, tile_start - halo_sig) & ~(int64_t)3;   // first bar whose line is needed
+    const int64_t s0 = max((int64_t)0, s1 - halo_ema) & ~(int64_t)3;           // first bar the EMAs start from
+    const float* row = x + (int64_t)sym * ld;
+    constexpr int K = 4;
+    const double af = 2.0 / ((double)fast + 1.0), as = 2.0 / ((double)slow + 1.0), ag = 2.0 / ((double)sign + 1.0);
+    AffineScan<K> sf, ss, sg;
+    sf.init(1.0 - af, lane);
+    ss.init(1.0 - as, lane);
+    sg.init(1.0 - ag, lane);
+    const int first_line = max(fast, slow) - 1;            // first defined line value
+    const int first_sig = first_line + sign - 1;           // first defined signal value
+    const double x0 = (double)__ldg(row);
+    double cf = (s0 == 0) ? x0 : 0.0, cs = cf;
+    for (int64_t base = s0; base < tile_end; base += 32 * K) {
+        const int64_t t = base + lane * K;
+        double bf[K], bs[K], yf[K], ys[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int64_t tt = min(t + j, N - 1);
+            const double v = (double)__ldg(row + tt);
+            bf[j] = af * v;
+            bs[j] = as * v;
+        }
+        sf.run(bf, cf, yf, lane);
+        ss.run(bs, cs, ys, lane);
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            if (t + j >= s1 && t + j < tile_end) s_line[t + j - s1] = yf[j] - ys[j];
+    }
+    __syncwarp();
+    // signal: starts at max(s1, first_line); seeded with the line itself at first_line
+    int64_t g0 = max(s1, (int64_t)first_line) & ~(int64_t)3;
+    if (g0 < s1) g0 = s1;
+    double cg = 0.0;
+    const bool seeded = (g0 <= first_line);  // this tile contains the seed bar
+    for (int64_t base = g0; base < tile_end; base += 32 * K) {
+        const int64_t t = base + lane * K;
+        double b[K], y[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int64_t tt = t + j;
+            double v = (tt >= s1 && tt < tile_end) ? s_line[tt - s1] : 0.0;
+            if (seeded && tt < first_line) v = 0.0;
+            // seed bar: y = line  <=>  b = line with zero incoming state (scale 1 instead of alpha)
+            b[j] = (seeded && tt == first_line) ? v : ag * v;
+            if (tt >= tile_end) b[j] = 0.0;
+        }
+        sg.run(b, cg, y, lane);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int64_t tt = t + j;
+            if (tt >= tile_start && tt < tile_end) {
+                const double line = s_line[tt - s1];
+                const int64_t o = (int64_t)sym * N + tt;
+                o_line[o] = tt >= first_line ? (float)line : nanf32();
+                o_sig[o] = tt >= first_sig ? (float)y[j] : nanf32();
+                o_diff[o] = tt >= first_sig ? (float)(line - y[j]) : nanf32();
+            }
+        }
+    }
+    // bars of this tile before the first signal bar that the loop above did not visit
+    for (int64_t tt = tile_start + lane; tt < min(tile_end, g0); tt += 32) {
+        const int64_t o = (int64_t)sym * N + tt;
+        o_line[o] = tt >= first_line ? (float)s_line[tt - s1] : nanf32();
+        o_sig[o] = nanf32();
+        o_diff[o] = nanf32();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Block-wide inclusive prefix sum of n doubles in shared memory (n <= IND_THREADS * 16).
+// ---------------------------------------------------------------------------------
+__device__ void block_prefix_sum(double* __restrict__ s, int n, double* __restrict__ s_warp) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    const int lo = min(tid * per, n), hi = min(lo + per, n);
+    double run = 0.0;
+    for (int i = lo; i < hi; ++i) { run += s[i]; s[i] = run; }
+    double inc = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double up = shfl_up_d(inc, d);
+        if (lane >= d) inc += up;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        double v = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0.0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double up = shfl_up_d(v, d);
+            if (lane >= d) v += up;
+        }
+        if (lane < (int)(blockDim.x >> 5)) s_warp[lane] = v;
+    }
+    __syncthreads();
+    const double off = (inc - run) + (warp > 0 ? s_warp[warp - 1] : 0.0);
+    for (int i = lo; i < hi; ++i) s[i] += off;
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------
+// SMA bank (ta.trend.SMAIndicator = rolling(w, min_periods=w).mean(); :67-76).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(IND_THREADS)
+sma_bank_kernel(const float* __restrict__ x, int64_t N, int64_t ld, const __grid_constant__ BankParams prm, int P,
+                int halo_max, float* __restrict__ out) {
+    extern __shared__ double s_pre[];  // s_pre[i+1] = sum_{k<=i} (x[s0+k] - c), s_pre[0] = 0
+    __shared__ double s_warp[32];
+    const int sym = blockIdx.y;
+    const int64_t tile_start = (int64_t)blockIdx.x * IND_TILE;
+    const int64_t tile_end = min(tile_start + (int64_t)IND_TILE, N);
+    const int64_t s0 = max((int64_t)0, tile_start - halo_max);
+    const int n_stage = (int)(tile_end - s0);
+    const float* row = x + (int64_t)sym * ld;
+    const double c = (double)__ldg(row + tile_start);  // tile offset keeps the prefix small
+    if (threadIdx.x == 0) s_pre[0] = 0.0;
+    for (int i = threadIdx.x; i < n_stage; i += blockDim.x) s_pre[i + 1] = (double)__ldg(row + s0 + i) - c;
+    __syncthreads();
+    block_prefix_sum(s_pre + 1, n_stage, s_warp);
+    for (int pi = 0; pi < P; ++pi) {
+        const int w = prm.window[pi];
+        float* orow = out + ((int64_t)sym * P + pi) * N;
+        for (int64_t t = tile_start + threadIdx.x; t < tile_end; t += blockDim.x) {
+            float v = nanf32();
+            if (t >= w - 1) {
+                const int i = (int)(t - s0);
+                v = (float)((s_pre[i + 1] - s_pre[i + 1 - w]) / (double)w + c);
+            }
+            orow[t] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Bollinger bands (ta.volatility.BollingerBands(close, 20, 2); :148-156):
+// mid = rolling mean, std = rolling std(ddof=0), high/low = mid +- k*std,
+// width = (high-low)/mid, position = (close-low)/(high-low) with NaN where the range is 0.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(IND_THREADS)
+bollinger_kernel(const float* __restrict__ x, int64_t N, int64_t ld, int w, double kdev, float* __restrict__ o_high,
+                 float* __restrict__ o_mid, float* __restrict__ o_low, float* __restrict__ o_width,
+                 float* __restrict__ o_pos) {
+    extern __shared__ double s_buf[];  // [0, n+1): prefix of d, [n+1, 2n+2): prefix of d^2
+    __shared__ double s_warp[32];
+    const int sym = blockIdx.y;
+    const int64_t tile_start = (int64_t)blockIdx.x * IND_TILE;
+    const int64_t tile_end = min(tile_start + (int64_t)IND_TILE, N);
+    const int64_t s0 = max((int64_t)0, tile_start - (w - 1));
+    const int n = (int)(tile_end - s0);
+    double* p1 = s_buf;
+    double* p2 = s_buf + (IND_TILE + IND_MAX_WINDOW + 1);
+    const float* row = x + (int64_t)sym * ld;
+    const double c = (double)__ldg(row + tile_start);
+    if (threadIdx.x == 0) { p1[0] = 0.0; p2[0] = 0.0; }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double d = (double)__ldg(row + s0 + i) - c;
+        p1[i + 1] = d;
+        p2[i + 1] = d * d;
+    }
+    __syncthreads();
+    block_prefix_sum(p1 + 1, n, s_warp);
+    block_prefix_sum(p2 + 1, n, s_warp);
+    for (int64_t t = tile_start + threadIdx.x; t < tile_end; t += blockDim.x) {
+        const int64_t o = (int64_t)sym * N + t;
+        if (t < w - 1) {
+            o_high[o] = o_mid[o] = o_low[o] = o_width[o] = o_pos[o] = nanf32();
+            continue;
+        }
+        const int i = (int)(t - s0);
+        const double m1 = (p1[i + 1] - p1[i + 1 - w]) / (double)w;   // mean of d
+        const double m2 = (p2[i + 1] - p2[i + 1 - w]) / (double)w;   // mean of d^2
+        double var = m2 - m1 * m1;
+        if (var < 0.0) var = 0.0;
+        const double sd = sqrt(var), mid = m1 + c;
+        const double hi = mid + kdev * sd, lo = mid - kdev * sd;
+        const double rng = hi - lo;
+        const double close = (double)__ldg(row + t);
+        o_high[o] = (float)hi;
+        o_mid[o] = (float)mid;
+        o_low[o] = (float)lo;
+        o_width[o] = (float)(rng / mid);
+        o_pos[o] = rng == 0.0 ? nanf32() : (float)((close - lo) / rng);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Rolling extrema helpers + stochastic / Williams %R / Ichimoku.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float window_max(const float* __restrict__ s, int i, int w) {
+    float m = s[i];
+    for (int k = 1; k < w; ++k) m = fmaxf(m, s[i - k]);
+    return m;
+}
+__device__ __forceinline__ float window_min(const float* __restrict__ s, int i, int w) {
+    float m = s[i];
+    for (int k = 1; k < w; ++k) m = fminf(m, s[i - k]);
+    return m;
+}
+
+// mode 0: stochastic (%K into o_a, %D = rolling mean(smooth) of %K into o_b)   :121-127
+// mode 1: Williams %R into o_a                                                 :135-140
+// mode 2: Ichimoku a, b (w1 conversion, w2 base, w3 span b)                    :102-104
+__global__ void __launch_bounds__(IND_THREADS)
+extrema_kernel(const float* __restrict__ high, const float* __restrict__ low, const float* __restrict__ close,
+               int64_t N, int64_t ld, int mode, int w1, int w2, int w3, float* __restrict__ o_a, float* __restrict__ o_b) {
+    extern __shared__ float s_hl[];  // [halo + tile] highs, then lows, then %K scratch
+    const int sym = blockIdx.y;
+    const int64_t tile_start = (int64_t)blockIdx.x * IND_TILE;
+    const int64_t tile_end = min(tile_start + (int64_t)IND_TILE, N);
+    const int wmax = max(w1, max(w2, w3));
+    const int extra = (mode == 0) ? (w2 - 1) : 0;  // %D needs %K of the previous smooth-1 bars
+    const int64_t s0 = max((int64_t)0, tile_start - (wmax - 1) - extra);
+    const int n = (int)(tile_end - s0);
+    float* sh = s_hl;
+    float* sl = s_hl + (IND_TILE + 2 * IND_MAX_WINDOW);
+    float* sk = sl + (IND_TILE + 2 * IND_MAX_WINDOW);
+    stage_row(high + (int64_t)sym * ld, N, s0, n, sh);
+    stage_row(low + (int64_t)sym * ld, N, s0, n, sl);
+    __syncthreads();
+    const float* crow = close ? close + (int64_t)sym * ld : nullptr;
+    if (mode == 0) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int64_t t = s0 + i;
+            float k = nanf32();
+            if (i >= w1 - 1) {  // (s0 == 0: same as t >= w1-1; s0 > 0: the window must lie inside the staged halo)
+                const double lo = (double)window_min(sl, i, w1), hi = (double)window_max(sh, i, w1);
+                k = (float)(100.0 * ((double)__ldg(crow + t) - lo) / (hi - lo));   // 0/0 -> NaN as in pandas
+            }
+            sk[i] = k;
+        }
+        __syncthreads();
+        for (int64_t t = tile_start + threadIdx.x; t < tile_end; t += blockDim.x) {
+            const int i = (int)(t - s0);
+            const int64_t o = (int64_t)sym * N + t;
+            o_a[o] = sk[i];
+            float d = nanf32();
+            if (t >= w1 - 1 + w2 - 1) {
+                // %D over the float64 %K values (recomputed: the reference averages float64 %K)
+                double acc = 0.0;
+                for (int k = 0; k < w2; ++k) {
+                    const int ii = i - k;
+                    const double lo = (double)window_min(sl, ii, w1), hi = (double)window_max(sh, ii, w1);
+                    acc += 100.0 * ((double)__ldg(crow + s0 + ii) - lo) / (hi - lo);
+                }
+                d = (float)(acc / (double)w2);
+            }
+            o_b[o] = d;
+        }
+    } else if (mode == 1) {
+        for (int64_t t = tile_start + threadIdx.x; t < tile_end; t += blockDim.x) {
+            const int i = (int)(t - s0);
+            float v = nanf32();
+            if (t >= w1 - 1) {
+                const double hi = (double)window_max(sh, i, w1), lo = (double)window_min(sl, i, w1);
+                v = (float)(-100.0 * (hi - (double)__ldg(crow + t)) / (hi - lo));
+            }
+            o_a[(int64_t)sym * N + t] = v;
+        }
+    } else {
+        for (int64_t t = tile_start + threadIdx.x; t < tile_end; t += blockDim.x) {
+            const int i = (int)(t - s0);
+            const int64_t o = (int64_t)sym * N + t;
+            float a = nanf32(), b = nanf32();
+            if (t >= max(w1, w2) - 1) {
+                const double conv = 0.5 * ((double)window_max(sh, i, w1) + (double)window_min(sl, i, w1));
+                const double base = 0.5 * ((double)window_max(sh, i, w2) + (double)window_min(sl, i, w2));
+                a = (float)(0.5 * (conv + base));
+            }
+            if (t >= w3 - 1) b = (float)(0.5 * ((double)window_max(sh, i, w3) + (double)window_min(sl, i, w3)));
+            o_a[o] = a;
+            o_b[o] = b;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// ATR bank (ta.volatility.AverageTrueRange; :164): TR_t = max(h-l, |h-c_{t-1}|, |l-c_{t-1}|),
+// TR_0 = h_0-l_0; atr[t<w-1] = 0, atr[w-1] = mean(TR[0:w]), atr[i] = (atr[i-1](w-1)+TR[i])/w.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(IND_THREADS)
+atr_bank_kernel(const float* __restrict__ high, const float* __restrict__ low, const float* __restrict__ close,
+                int64_t N, int64_t ld, const __grid_constant__ BankParams prm, int P, int halo_max,
+                float* __restrict__ out) {
+    extern __shared__ float s_tr[];  // true range over [s0, tile_end) as fp32-exact differences kept in double? -> store double
+    double* tr = reinterpret_cast<double*>(s_tr);
+    const int sym = blockIdx.y;
+    const int64_t tile_start = (int64_t)blockIdx.x * IND_TILE;
+    const int64_t tile_end = min(tile_start + (int64_t)IND_TILE, N);
+    int64_t s0 = max((int64_t)0, tile_start - halo_max) & ~(int64_t)3;
+    if (s0 < IND_MAX_WINDOW) s0 = 0;  // a pass that crosses a seed bar t = w-1 needs TR from bar 0
+    const int n_stage = (int)(tile_start + IND_TILE - s0);
+    const float* hr = high + (int64_t)sym * ld;
+    const float* lr = low + (int64_t)sym * ld;
+    const float* cr = close + (int64_t)sym * ld;
+    for (int i = threadIdx.x; i < n_stage; i += blockDim.x) {
+        const int64_t t = s0 + i;
+        double v = 0.0;
+        if (t < N) {
+            const double h = (double)__ldg(hr + t), l = (double)__ldg(lr + t);
+            v = h - l;
+            if (t > 0) {
+                const double pc = (double)__ldg(cr + t - 1);
+                v = fmax(v, fmax(fabs(h - pc), fabs(l - pc)));
+            }
+        }
+        tr[i] = v;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    constexpr int K = 4;
+    for (int pi = warp; pi < P; pi += nwarp) {
+        const int w = prm.window[pi];
+        float* orow = out + ((int64_t)sym * P + pi) * N;
+        const double alpha = 1.0 / (double)w, om = ((double)w - 1.0) / (double)w;
+        AffineScan<K> sc;
+        sc.init(om, lane);
+        int64_t start = max(s0, tile_start - prm.halo[pi]) & ~(int64_t)3;
+        const bool has_seed = (start <= w - 1);     // this pass crosses the seed bar t = w-1
+        double seed = 0.0;
+        if (has_seed && w - 1 < N) {
+            for (int k = 0; k < w; ++k) seed += tr[(int)(k - s0)];   // s0 == 0 whenever has_seed
+            seed /= (double)w;
+        }
+        if (has_seed) start = 0;
+        double carry = 0.0;
+        for (int64_t base = start; base < tile_end; base += 32 * K) {
+            const int64_t t = base + lane * K;
+            double b[K], y[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int64_t tt = t + j;
+                double v = alpha * tr[min((int)(tt - s0), n_stage - 1)];
+                if (has_seed) v = tt < w - 1 ? 0.0 : (tt == w - 1 ? seed : v);   // zeros, then the seed, then the recurrence
+                b[j] = v;
+            }
+            sc.run(b, carry, y, lane);
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                if (t + j >= tile_start && t + j < tile_end) orow[t + j] = (t + j >= w - 1) ? (float)y[j] : 0.0f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// VWAP (ta.volume.VolumeWeightedAveragePrice, window 14; :173-179):
+// sum_w(tp*v)/sum_w(v), tp = (h+l+c)/3.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(IND_THREADS)
+vwap_kernel(const float* __restrict__ high, const float* __restrict__ low, const float* __restrict__ close,
+            const float* __restrict__ volume, int64_t N, int64_t ld, int w, float* __restrict__ out) {
+    extern __shared__ double s_buf[];
+    __shared__ double s_warp[32];
+    const int sym = blockIdx.y;
+    const int64_t tile_start = (int64_t)blockIdx.x * IND_TILE;
+    const int64_t tile_end = min(tile_start + (int64_t)IND_TILE, N);
+    const int64_t s0 = max((int64_t)0, tile_start - (w - 1));
+    const int n = (int)(tile_end - s0);
+    double* p1 = s_buf;
+    double* p2 = s_buf + (IND_TILE + IND_MAX_WINDOW + 1);
+    const int64_t ro = (int64_t)sym * ld;
+    if (threadIdx.x == 0) { p1[0] = 0.0; p2[0] = 0.0; }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int64_t t = s0 + i;
+        const double tp = ((double)__ldg(high + ro + t) + (double)__ldg(low + ro + t) + (double)__ldg(close + ro + t)) / 3.0;
+        const double v = (double)__ldg(volume + ro + t);
+        p1[i + 1] = tp * v;
+        p2[i + 1] = v;
+    }
+    __syncthreads();
+    block_prefix_sum(p1 + 1, n, s_warp);
+    block_prefix_sum(p2 + 1, n, s_warp);
+    for (int64_t t = tile_start + threadIdx.x; t < tile_end; t += blockDim.x) {
+        float v = nanf32();
+        if (t >= w - 1) {
+            const int i = (int)(t - s0);
+            v = (float)((p1[i + 1] - p1[i + 1 - w]) / (p2[i + 1] - p2[i + 1 - w]));
+        }
+        out[(int64_t)sym * N + t] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// NaN policy of TechnicalAnalyzer._handle_nan_values (:28-38): ffill, then bfill, then 0.
+// Pass 1: per (row, tile) last / first non-NaN value.  Pass 2: fill inside each tile with the
+// carry from the nearest earlier tile (or, before the first valid value, the first valid value).
+// ---------------------------------------------------------------------------------
+constexpr int NF_TILE = 4096;
+
+__global__ void __launch_bounds__(256)
+nanfill_scan_kernel(const float* __restrict__ x, int64_t N, int tiles, float* __restrict__ t_last, float* __restrict__ t_first) {
+    const int row = blockIdx.y, tile = blockIdx.x;
+    const int64_t lo = (int64_t)tile * NF_TILE, hi = min(lo + (int64_t)NF_TILE, N);
+    const float* r = x + (int64_t)row * N;
+    int last = -1, first = 0x7fffffff;
+    for (int64_t t = lo + threadIdx.x; t < hi; t += blockDim.x)
+        if (!isnan(r[t])) { last = max(last, (int)(t - lo)); first = min(first, (int)(t - lo)); }
+    __shared__ int s_last[8], s_first[8];
+    last = __reduce_max_sync(FULL, last);
+    first = __reduce_min_sync(FULL, first);
+    if ((threadIdx.x & 31) == 0) { s_last[threadIdx.x >> 5] = last; s_first[threadIdx.x >> 5] = first; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) { last = max(last, s_last[i]); first = min(first, s_first[i]); }
+        last = max(last, s_last[0]);
+        first = min(first, s_first[0]);
+        t_last[(int64_t)row * tiles + tile] = last >= 0 ? r[lo + last] : nanf32();
+        t_first[(int64_t)row * tiles + tile] = first != 0x7fffffff ? r[lo + first] : nanf32();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+nanfill_apply_kernel(float* __restrict__ x, int64_t N, int tiles, const float* __restrict__ t_last,
+                     const float* __restrict__ t_first) {
+    const int row = blockIdx.y, tile = blockIdx.x;
+    const int64_t lo = (int64_t)tile * NF_TILE, hi = min(lo + (int64_t)NF_TILE, N);
+    float* r = x + (int64_t)row * N;
+    __shared__ float s_carry, s_firstvalid;
+    __shared__ int s_idx[NF_TILE];
+    if (threadIdx.x == 0) {
+        float c = nanf32();
+        for (int k = tile - 1; k >= 0 && isnan(c); --k) c = t_last[(int64_t)row * tiles + k];
+        float f = nanf32();
+        for (int k = 0; k < tiles && isnan(f); ++k) f = t_first[(int64_t)row * tiles + k];
+        s_carry = c;
+        s_firstvalid = f;
+    }
+    // index of the last valid element at or before each position (block-level max-scan, done per warp chunk)
+    const int n = (int)(hi - lo);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_idx[i] = isnan(r[lo + i]) ? -1 : i;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        // 32 lanes x 128 contiguous positions: serial running max per lane, then a warp scan of lane totals
+        const int per = NF_TILE / 32, a = threadIdx.x * per, b = min(a + per, n);
+        int run = -1;
+        for (int i = a; i < b; ++i) { run = max(run, s_idx[i]); s_idx[i] = run; }
+        int inc = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(FULL, inc, d);
+            if ((int)threadIdx.x >= d) inc = max(inc, up);
+        }
+        const int before = __shfl_up_sync(FULL, inc, 1);
+        if (threadIdx.x > 0 && before >= 0)
+            for (int i = a; i < b; ++i) s_idx[i] = max(s_idx[i], before);
+    }
+    __syncthreads();
+    const float carry = s_carry, fv = s_firstvalid;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float v = r[lo + i];
+        if (isnan(v)) {
+            const int j = s_idx[i];
+            if (j >= 0) v = r[lo + j];            // ffill inside the tile (source is a valid element, never rewritten)
+            else if (!isnan(carry)) v = carry;    // ffill across tiles
+            else if (!isnan(fv)) v = fv;          // bfill before the first valid value
+            else v = 0.0f;                        // all-NaN column
+            r[lo + i] = v;
+        }
+    }
+}
+
+}  // namespace b200bt
+
+using namespace b200bt;
+
+#define IND_COMMON_CHECKS(name)                                                                         \
+    B200BT_REQUIRE(S > 0 && N > 0 && ld >= N, B200BT_EINVAL, name ": bad sizes S=%d N=%lld", S, (long long)N); \
+    {                                                                                                   \
+        int rc__ = check_device();                                                                      \
+        if (rc__) return rc__;                                                                          \
+    }
+
+static dim3 ind_grid(int64_t N, int S) { return dim3((unsigned)((N + IND_TILE - 1) / IND_TILE), (unsigned)S); }
+
+extern "C" int b200bt_nanfill(float* x, int64_t rows, int64_t N, float* workspace, b200bt_stream_t stream) {
+    B200BT_REQUIRE(x && workspace && rows > 0 && N > 0, B200BT_EINVAL, "nanfill: bad argument");
+    int rc = check_device();
+    if (rc) return rc;
+    const int tiles = (int)((N + NF_TILE - 1) / NF_TILE);
+    float* t_last = workspace;
+    float* t_first = workspace + rows * tiles;
+    dim3 grid((unsigned)tiles, (unsigned)rows);
+    nanfill_scan_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, N, tiles, t_last, t_first);
+    B200BT_LAUNCH_CHECK("nanfill scan");
+    nanfill_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, N, tiles, t_last, t_first);
+    B200BT_LAUNCH_CHECK("nanfill apply");
+    return B200BT_OK;
+}
+
+extern "C" int64_t b200bt_nanfill_workspace_floats(int64_t rows, int64_t N) {
+    return 2 * rows * ((N + NF_TILE - 1) / NF_TILE);
+}
+
+static int fill_bank_params(const int* w_host, int P, bool wilder, BankParams& prm, int& halo_max, const char* name) {
+    B200BT_REQUIRE(w_host && P > 0 && P <= IND_MAX_P, B200BT_ELIMIT, "%s: 1..%d windows per call", name, IND_MAX_P);
+    halo_max = 0;
+    for (int i = 0; i < P; ++i) {
+        const int w = w_host[i];
+        B200BT_REQUIRE(w >= 1 && w <= IND_MAX_WINDOW, B200BT_ELIMIT, "%s: window %d outside [1,%d]", name, w, IND_MAX_WINDOW);
+        prm.window[i] = w;
+        const double om = wilder ? ((double)w - 1.0) / (double)w : 1.0 - 2.0 / ((double)w + 1.0);
+        prm.halo[i] = halo_for(om);
+        if (prm.halo[i] > halo_max) halo_max = prm.halo[i];
+    }
+    return B200BT_OK;
+}
+
+extern "C" int b200bt_ema_bank(const float* x, int S, int64_t N, int64_t ld, const int* spans_host, int P, float* out,
+                               b200bt_stream_t stream) {
+    B200BT_REQUIRE(x && out, B200BT_EINVAL, "ema_bank: null pointer");
+    IND_COMMON_CHECKS("ema_bank");
+    BankParams prm;
+    int halo_max;
+    int rc = fill_bank_params(spans_host, P, false, prm, halo_max, "ema_bank");
+    if (rc) return rc;
+    const size_t smem = (size_t)(halo_max + IND_TILE + 8) * sizeof(float);
+    B200BT_REQUIRE(smem <= 200 * 1024, B200BT_ELIMIT, "ema_bank: span too long for the shared-memory tile");
+    cudaError_t e = cudaFuncSetAttribute(ema_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "ema_bank: cudaFuncSetAttribute");
+    ema_bank_kernel<<<ind_grid(N, S), IND_THREADS, smem, (cudaStream_t)stream>>>(x, N, ld, prm, P, halo_max, out);
+    B200BT_LAUNCH_CHECK("ema_bank launch");
+    return B200BT_OK;
+}
+
+extern "C" int b200bt_macd(const float* x, int S, int64_t N, int64_t ld, int fast, int slow, int sign, float* line,
+                           float* signal, float* diff, b200bt_stream_t stream) {
+    B200BT_REQUIRE(x && line && signal && diff, B200BT_EINVAL, "macd: null pointer");
+    IND_COMMON_CHECKS("macd");
+    B200BT_REQUIRE(fast >= 1 && slow >= 1 && sign >= 1 && fast <= 512 && slow <= 512 && sign <= 512, B200BT_ELIMIT,
+                   "macd: spans must be in [1,512]");
+    const int halo_ema = halo_for(1.0 - 2.0 / ((double)(fast > slow ? fast : slow) + 1.0));
+    const int halo_sig = halo_for(1.0 - 2.0 / ((double)sign + 1.0));
+    const size_t smem = (size_t)(halo_sig + IND_TILE + 8) * sizeof(double);
+    B200BT_REQUIRE(smem <= 200 * 1024, B200BT_ELIMIT, "macd: signal span too long for the shared-memory tile");
+    cudaError_t e = cudaFuncSetAttribute(macd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "macd: cudaFuncSetAttribute");
+    macd_kernel<<<ind_grid(N, S), 32, smem, (cudaStream_t)stream>>>(x, N, ld, fast, slow, sign, halo_ema, halo_sig, line,
+                                                                     signal, diff);
+    B200BT_LAUNCH_CHECK("macd launch");
+    return B200BT_OK;
+}
+
+extern "C" int b200bt_sma_bank(const float* x, int S, int64_t N, int64_t ld, const int* windows_host, int P, float* out,
+                               b200bt_stream_t stream) {
+    B200BT_REQUIRE(x && out, B200BT_EINVAL, "sma_bank: null pointer");
+    IND_COMMON_CHECKS("sma_bank");
+    BankParams prm;
+    int halo_max = 0;
+    B200BT_REQUIRE(windows_host && P > 0 && P <= IND_MAX_P, B200BT_ELIMIT, "sma_bank: 1..%d windows per call", IND_MAX_P);
+    for (int i = 0; i < P; ++i) {
+        B200BT_REQUIRE(windows_host[i] >= 1 && windows_host[i] <= IND_MAX_WINDOW, B200BT_ELIMIT, "sma_bank: window %d outside [1,%d]",
+                       windows_host[i], IND_MAX_WINDOW);
+        prm.window[i] = windows_host[i];
+        prm.halo[i] = windows_host[i] - 1;
+        if (prm.halo[i] > halo_max) halo_max = prm.halo[i];
+    }
+    const size_t smem = (size_t)(halo_max + IND_TILE + 2) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(sma_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "sma_bank: cudaFuncSetAttribute");
+    sma_bank_kernel<<<ind_grid(N, S), IND_THREADS, smem, (cudaStream_t)stream>>>(x, N, ld, prm, P, halo_max, out);
+    B200BT_LAUNCH_CHECK("sma_bank launch");
+    return B200BT_OK;
+}
+
+extern "C" int b200bt_bollinger(const float* x, int S, int64_t N, int64_t ld, int window, double k, float* high,
+                                float* mid, float* low, float* width, float* pos, b200bt_stream_t stream) {
+    B200BT_REQUIRE(x && high && mid && low && width && pos, B200BT_EINVAL, "bollinger: null pointer");
+    IND_COMMON_CHECKS("bollinger");
+    B200BT_REQUIRE(window >= 1 && window <= IND_MAX_WINDOW, B200BT_ELIMIT, "bollinger: window outside [1,%d]", IND_MAX_WINDOW);
+    const size_t smem = (size_t)2 * (IND_TILE + IND_MAX_WINDOW + 1) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(bollinger_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "bollinger: cudaFuncSetAttribute");
+    bollinger_kernel<<<ind_grid(N, S), IND_THREADS, smem, (cudaStream_t)stream>>>(x, N, ld, window, k, high, mid, low, width, pos);
+    B200BT_LAUNCH_CHECK("bollinger launch");
+    return B200BT_OK;
+}
+
+static int launch_extrema(const float* high, const float* low, const float* close, int S, int64_t N, int64_t ld, int mode,
+                          int w1, int w2, int w3, float* a, float* b, b200bt_stream_t stream, const char* name) {
+    B200BT_REQUIRE(high && low && a, B200BT_EINVAL, "%s: null pointer", name);
+    B200BT_REQUIRE(S > 0 && N > 0 && ld >= N, B200BT_EINVAL, "%s: bad sizes", name);
+    B200BT_REQUIRE(w1 >= 1 && w2 >= 1 && w3 >= 1 && w1 <= IND_MAX_WINDOW && w2 <= IND_MAX_WINDOW && w3 <= IND_MAX_WINDOW,
+                   B200BT_ELIMIT, "%s: window outside [1,%d]", name, IND_MAX_WINDOW);
+    int rc = check_device();
+    if (rc) return rc;
+    const size_t smem = (size_t)3 * (IND_TILE + 2 * IND_MAX_WINDOW) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(extrema_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "extrema: cudaFuncSetAttribute");
+    extrema_kernel<<<ind_grid(N, S), IND_THREADS, smem, (cudaStream_t)stream>>>(high, low, close, N, ld, mode, w1, w2, w3, a, b);
+    B200BT_LAUNCH_CHECK("extrema launch");
+    return B200BT_OK;
+}
+
+extern "C" int b200bt_stochastic(const float* high, const float* low, const float* close, int S, int64_t N, int64_t ld,
+                                 int window, int smooth, float* k, float* d, b200bt_stream_t stream) {
+    B200BT_REQUIRE(close && d, B200BT_EINVAL, "stochastic: null pointer");
+    return launch_extrema(high, low, close, S, N, ld, 0, window, smooth, 1, k, d, stream, "stochastic");
+}
+
+extern "C" int b200bt_williams_r(const float* high, const float* low, const float* close, int S, int64_t N, int64_t ld,
+                                 int lbp, float* out, b200bt_stream_t stream) {
+    B200BT_REQUIRE(close, B200BT_EINVAL, "williams_r: null pointer");
+    return launch_extrema(high, low, close, S, N, ld, 1, lbp, 1, 1, out, nullptr, stream, "williams_r");
+}
+
+extern "C" int b200bt_ichimoku(const float* high, const float* low, int S, int64_t N, int64_t ld, int w1, int w2, int w3,
+                               float* a, float* b, b200bt_stream_t stream) {
+    B200BT_REQUIRE(b, B200BT_EINVAL, "ichimoku: null pointer");
+    return launch_extrema(high, low, nullptr, S, N, ld, 2, w1, w2, w3, a, b, stream, "ichimoku");
+}
+
+extern "C" int b200bt_atr_bank(const float* high, const float* low, const float* close, int S, int64_t N, int64_t ld,
+                               const int* windows_host, int P, float* out, b200bt_stream_t stream) {
+    B200BT_REQUIRE(high && low && close && out, B200BT_EINVAL, "atr_bank: null pointer");
+    IND_COMMON_CHECKS("atr_bank");
+    BankParams prm;
+    int halo_max;
+    int rc = fill_bank_params(windows_host, P, true, prm, halo_max, "atr_bank");
+    if (rc) return rc;
+    for (int i = 0; i < P; ++i) B200BT_REQUIRE(prm.window[i] <= IND_TILE / 2, B200BT_ELIMIT, "atr_bank: window too long");
+    const size_t smem = (size_t)(halo_max + IND_TILE + IND_MAX_WINDOW + 8) * sizeof(double);
+    B200BT_REQUIRE(smem <= 200 * 1024, B200BT_ELIMIT, "atr_bank: window too long for the shared-memory tile");
+    cudaError_t e = cudaFuncSetAttribute(atr_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "atr_bank: cudaFuncSetAttribute");
+    atr_bank_kernel<<<ind_grid(N, S), IND_THREADS, smem, (cudaStream_t)stream>>>(high, low, close, N, ld, prm, P, halo_max, out);
+    B200BT_LAUNCH_CHECK("atr_bank launch");
+    return B200BT_OK;
+}
+
+extern "C" int b200bt_vwap(const float* high, const float* low, const float* close, const float* volume, int S, int64_t N,
+                           int64_t ld, int window, float* out, b200bt_stream_t stream) {
+    B200BT_REQUIRE(high && low && close && volume && out, B200BT_EINVAL, "vwap: null pointer");
+    IND_COMMON_CHECKS("vwap");
+    B200BT_REQUIRE(window >= 1 && window <= IND_MAX_WINDOW, B200BT_ELIMIT, "vwap: window outside [1,%d]", IND_MAX_WINDOW);
+    const size_t smem = (size_t)2 * (IND_TILE + IND_MAX_WINDOW + 1) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(vwap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "vwap: cudaFuncSetAttribute");
+    vwap_kernel<<<ind_grid(N, S), IND_THREADS, smem, (cudaStream_t)stream>>>(high, low, close, volume, N, ld, window, out);
+    B200BT_LAUNCH_CHECK("vwap launch");
+    return B200BT_OK;
+}

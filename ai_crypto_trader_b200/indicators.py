@@ -1,0 +1,192 @@
+"""Rolling indicators on the GPU (host side of Family 1, include/b200bt.h).
+
+Each function takes fp32 CUDA tensors shaped [S][N] (one row per symbol) and returns fp32
+tensors; arithmetic is fp64 inside the kernels.  `fill=True` applies the reference's
+TechnicalAnalyzer._handle_nan_values policy (binance_ml_strategy.py:28-38: ffill, bfill, 0);
+`fill=False` leaves `ta`'s leading NaNs in place.  TechnicalAnalyzer below mirrors the
+reference class of the same name (binance_ml_strategy.py:14-249) for a whole batch of symbols.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .sweep import rsi_bank  # noqa: F401  (re-export: RSI lives with the sweep that consumes it)
+
+
+def _check(*ts):
+    S, N = ts[0].shape
+    for t in ts:
+        assert t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and tuple(t.shape) == (S, N) and t.stride(1) == 1
+    return S, N
+
+
+def _ints(v: Sequence[int]):
+    return (C.c_int * len(v))(*[int(x) for x in v])
+
+
+def nanfill_(x: torch.Tensor) -> torch.Tensor:
+    """In-place ffill -> bfill -> 0 along the last axis of a contiguous fp32 CUDA tensor."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    N = x.shape[-1]
+    rows = x.numel() // N
+    ws = torch.empty(int(_lib.load().b200bt_nanfill_workspace_floats(rows, N)), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("b200bt_nanfill", x.data_ptr(), rows, N, ws.data_ptr(), _lib.current_stream())
+    return x
+
+
+def _bank(fn: str, x: torch.Tensor, windows: Sequence[int], fill: bool, extra=()):
+    S, N = _check(x)
+    out = torch.empty((S, len(windows), N), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call(fn, *extra, x.data_ptr(), S, N, x.stride(0), _ints(windows), len(windows), out.data_ptr(),
+                  _lib.current_stream())
+    return nanfill_(out) if fill else out
+
+
+def ema_bank(close: torch.Tensor, spans: Sequence[int], fill: bool = True) -> torch.Tensor:
+    return _bank("b200bt_ema_bank", close, spans, fill)
+
+
+def sma_bank(close: torch.Tensor, windows: Sequence[int], fill: bool = True) -> torch.Tensor:
+    return _bank("b200bt_sma_bank", close, windows, fill)
+
+
+def atr_bank(high, low, close, windows: Sequence[int]) -> torch.Tensor:
+    S, N = _check(high, low, close)
+    out = torch.empty((S, len(windows), N), dtype=torch.float32, device=close.device)
+    with torch.cuda.device(close.device):
+        _lib.call("b200bt_atr_bank", high.data_ptr(), low.data_ptr(), close.data_ptr(), S, N, close.stride(0),
+                  _ints(windows), len(windows), out.data_ptr(), _lib.current_stream())
+    return out
+
+
+def _outs(n, like):
+    return [torch.empty_like(like) for _ in range(n)]
+
+
+def _maybe_fill(ts, fill):
+    if fill:
+        for t in ts:
+            nanfill_(t)
+    return ts
+
+
+def macd(close, fast: int = 12, slow: int = 26, sign: int = 9, fill: bool = True):
+    S, N = _check(close)
+    line, signal, diff = _outs(3, close.contiguous())
+    with torch.cuda.device(close.device):
+        _lib.call("b200bt_macd", close.data_ptr(), S, N, close.stride(0), fast, slow, sign, line.data_ptr(),
+                  signal.data_ptr(), diff.data_ptr(), _lib.current_stream())
+    return tuple(_maybe_fill([line, signal, diff], fill))
+
+
+def bollinger(close, window: int = 20, dev: float = 2.0, fill: bool = True):
+    """-> (high, mid, low, width, position)."""
+    S, N = _check(close)
+    outs = _outs(5, close.contiguous())
+    with torch.cuda.device(close.device):
+        _lib.call("b200bt_bollinger", close.data_ptr(), S, N, close.stride(0), window, float(dev),
+                  *[o.data_ptr() for o in outs], _lib.current_stream())
+    return tuple(_maybe_fill(outs, fill))
+
+
+def stochastic(high, low, close, window: int = 14, smooth: int = 3, fill: bool = True):
+    S, N = _check(high, low, close)
+    k, d = _outs(2, close.contiguous())
+    with torch.cuda.device(close.device):
+        _lib.call("b200bt_stochastic", high.data_ptr(), low.data_ptr(), close.data_ptr(), S, N, close.stride(0),
+                  window, smooth, k.data_ptr(), d.data_ptr(), _lib.current_stream())
+    return tuple(_maybe_fill([k, d], fill))
+
+
+def williams_r(high, low, close, lbp: int = 14, fill: bool = True):
+    S, N = _check(high, low, close)
+    (out,) = _outs(1, close.contiguous())
+    with torch.cuda.device(close.device):
+        _lib.call("b200bt_williams_r", high.data_ptr(), low.data_ptr(), close.data_ptr(), S, N, close.stride(0), lbp,
+                  out.data_ptr(), _lib.current_stream())
+    return _maybe_fill([out], fill)[0]
+
+
+def ichimoku(high, low, w1: int = 9, w2: int = 26, w3: int = 52, fill: bool = True):
+    S, N = _check(high, low)
+    a, b = _outs(2, high.contiguous())
+    with torch.cuda.device(high.device):
+        _lib.call("b200bt_ichimoku", high.data_ptr(), low.data_ptr(), S, N, high.stride(0), w1, w2, w3, a.data_ptr(),
+                  b.data_ptr(), _lib.current_stream())
+    return tuple(_maybe_fill([a, b], fill))
+
+
+def vwap(high, low, close, volume, window: int = 14, fill: bool = True):
+    S, N = _check(high, low, close, volume)
+    (out,) = _outs(1, close.contiguous())
+    with torch.cuda.device(close.device):
+        _lib.call("b200bt_vwap", high.data_ptr(), low.data_ptr(), close.data_ptr(), volume.data_ptr(), S, N,
+                  close.stride(0), window, out.data_ptr(), _lib.current_stream())
+    return _maybe_fill([out], fill)[0]
+
+
+class TechnicalAnalyzer:
+    """binance_ml_strategy.py:14-249 for S symbols at once: the 18 indicator columns as device
+    tensors in `self.data`, and the last-bar scalars `get_all_indicators(symbol_index)` reads."""
+
+    COLUMNS = ("sma_20", "sma_50", "sma_200", "ema_12", "ema_26", "macd", "macd_signal", "macd_diff", "ichimoku_a",
+               "ichimoku_b", "rsi", "stoch_k", "stoch_d", "williams_r", "bb_high", "bb_mid", "bb_low", "bb_width",
+               "bb_position", "atr", "vwap")
+
+    def __init__(self, market):
+        from .sweep import MarketData
+        assert isinstance(market, MarketData)
+        self.market = market
+        o, h, l, c, v = market.open, market.high, market.low, market.close, market.volume
+        d: Dict[str, torch.Tensor] = {}
+        sma = sma_bank(c, [20, 50, 200])                                   # :67-76
+        d["sma_20"], d["sma_50"], d["sma_200"] = sma[:, 0], sma[:, 1], sma[:, 2]
+        ema = ema_bank(c, [12, 26])                                        # :79-83
+        d["ema_12"], d["ema_26"] = ema[:, 0], ema[:, 1]
+        d["macd"], d["macd_signal"], d["macd_diff"] = macd(c)              # :91-94
+        d["ichimoku_a"], d["ichimoku_b"] = ichimoku(h, l)                  # :102-104
+        d["rsi"] = rsi_bank(c, [14])[:, 0]                                 # :112
+        d["stoch_k"], d["stoch_d"] = stochastic(h, l, c)                   # :121-127
+        d["williams_r"] = williams_r(h, l, c)                              # :135-140
+        d["bb_high"], d["bb_mid"], d["bb_low"], d["bb_width"], d["bb_position"] = bollinger(c)   # :148-156
+        d["atr"] = atr_bank(h, l, c, [14])[:, 0]                           # :164
+        d["vwap"] = vwap(h, l, c, v)                                       # :173-179
+        self.data = d
+        last = torch.stack([d[k][:, -1] for k in self.COLUMNS] + [c[:, -1], h[:, -1], l[:, -1]], dim=1)
+        self._last = last.double().cpu().numpy()                           # [S][len(COLUMNS)+3]
+
+    def _get(self, s: int, name: str) -> float:
+        extra = {"close": len(self.COLUMNS), "high": len(self.COLUMNS) + 1, "low": len(self.COLUMNS) + 2}
+        idx = extra[name] if name in extra else self.COLUMNS.index(name)
+        return float(self._last[s, idx])
+
+    def get_trend(self, s: int = 0) -> Tuple[str, float]:
+        last_close, sma20, sma50 = self._get(s, "close"), self._get(s, "sma_20"), self._get(s, "sma_50")
+        strength = ((last_close - sma20) / sma20 * 100 + (last_close - sma50) / sma50 * 100) / 2      # :191-192
+        if last_close > sma20 and sma20 > sma50:
+            return "uptrend", abs(strength)
+        if last_close < sma20 and sma20 < sma50:
+            return "downtrend", abs(strength)
+        return "sideways", abs(strength)
+
+    def get_volatility(self, s: int = 0) -> float:
+        return self._get(s, "atr") / self._get(s, "close")                 # :208
+
+    def get_support_resistance(self, s: int = 0) -> Dict[str, float]:
+        h, l, c = self._get(s, "high"), self._get(s, "low"), self._get(s, "close")
+        pivot = (h + l + c) / 3
+        return {"support1": 2 * pivot - h, "support2": pivot - (h - l), "resistance1": 2 * pivot - l,
+                "resistance2": pivot + (h - l)}
+
+    def get_all_indicators(self, s: int = 0) -> Dict:
+        trend, strength = self.get_trend(s)
+        return {"rsi": self._get(s, "rsi"), "stoch_k": self._get(s, "stoch_k"), "stoch_d": self._get(s, "stoch_d"),
+                "macd": self._get(s, "macd"), "macd_signal": self._get(s, "macd_signal"),
+                "williams_r": self._get(s, "williams_r"), "bb_position": self._get(s, "bb_position"),
+                "volatility": self.get_volatility(s), "trend": trend, "trend_strength": strength}

@@ -60,6 +60,52 @@ int b200bt_rsi_bank(const float* close, int S, int64_t N, int64_t ld,
                     const int* periods_host, int P, int fill,
                     float* out, b200bt_stream_t stream);
 
+/* EMA bank: ta.trend.EMAIndicator(close, window=w) = ewm(span=w, min_periods=w, adjust=False)
+ * (binance_ml_strategy.py:79-83).  out [S][P][N]; undefined leading values are NaN. */
+int b200bt_ema_bank(const float* x, int S, int64_t N, int64_t ld, const int* spans_host, int P,
+                    float* out, b200bt_stream_t stream);
+
+/* SMA bank: ta.trend.SMAIndicator = rolling(w, min_periods=w).mean() (:67-76). out [S][P][N]. */
+int b200bt_sma_bank(const float* x, int S, int64_t N, int64_t ld, const int* windows_host, int P,
+                    float* out, b200bt_stream_t stream);
+
+/* MACD: ta.trend.MACD(close, slow, fast, sign) (:91-94).  line/signal/diff each [S][N]. */
+int b200bt_macd(const float* x, int S, int64_t N, int64_t ld, int fast, int slow, int sign,
+                float* line, float* signal, float* diff, b200bt_stream_t stream);
+
+/* Bollinger bands: ta.volatility.BollingerBands(close, window, k) plus the analyzer's
+ * bb_width and bb_position (zero range -> NaN) (:148-156).  Five outputs, each [S][N]. */
+int b200bt_bollinger(const float* x, int S, int64_t N, int64_t ld, int window, double k,
+                     float* high, float* mid, float* low, float* width, float* position,
+                     b200bt_stream_t stream);
+
+/* Stochastic oscillator %K / %D: ta.momentum.StochasticOscillator(high, low, close, window,
+ * smooth_window) (:121-127). */
+int b200bt_stochastic(const float* high, const float* low, const float* close, int S, int64_t N,
+                      int64_t ld, int window, int smooth, float* k, float* d, b200bt_stream_t stream);
+
+/* Williams %R: ta.momentum.WilliamsRIndicator(high, low, close, lbp) (:135-140). */
+int b200bt_williams_r(const float* high, const float* low, const float* close, int S, int64_t N,
+                      int64_t ld, int lbp, float* out, b200bt_stream_t stream);
+
+/* Ichimoku a / b: ta.trend.IchimokuIndicator(high, low, w1, w2, w3, visual=False) (:102-104). */
+int b200bt_ichimoku(const float* high, const float* low, int S, int64_t N, int64_t ld, int w1, int w2,
+                    int w3, float* a, float* b, b200bt_stream_t stream);
+
+/* ATR bank: ta.volatility.AverageTrueRange(high, low, close, window=w) (:164); zeros before
+ * bar w-1 (ta writes 0, not NaN).  out [S][P][N]. */
+int b200bt_atr_bank(const float* high, const float* low, const float* close, int S, int64_t N,
+                    int64_t ld, const int* windows_host, int P, float* out, b200bt_stream_t stream);
+
+/* VWAP: ta.volume.VolumeWeightedAveragePrice(high, low, close, volume, window) (:173-179). */
+int b200bt_vwap(const float* high, const float* low, const float* close, const float* volume, int S,
+                int64_t N, int64_t ld, int window, float* out, b200bt_stream_t stream);
+
+/* TechnicalAnalyzer._handle_nan_values (:28-38) on `rows` contiguous rows of length N, in place:
+ * forward-fill, then back-fill, then 0.  workspace: b200bt_nanfill_workspace_floats(rows, N) floats. */
+int64_t b200bt_nanfill_workspace_floats(int64_t rows, int64_t N);
+int b200bt_nanfill(float* x, int64_t rows, int64_t N, float* workspace, b200bt_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Family 2: the per-bar entry/exit/stop/PnL state machine over
  * (GA-individual x symbol) lanes.
@@ -162,6 +208,36 @@ int b200bt_sweep(const float* price, int64_t ld_price,
 /* fitness[i] = mean over symbols of stats[i][s].score  (float64, device). */
 int b200bt_fitness_reduce(const b200bt_lane_stats* stats, int pop, int S,
                           double* fitness, b200bt_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * The reference's own single-symbol bar loop (BASELINE configs[0]):
+ *   StrategyTester.backtest_strategy   backtesting/strategy_tester.py:156-312
+ *   open_position / close_position     :314-369
+ *   PositionSizer.calculate_position_size  binance_ml_strategy.py:251-291
+ * One warp per symbol; the entry gate (technical signal x AI decision, constant per
+ * symbol in the reference) is decided on the host and passed as can_enter.
+ * ------------------------------------------------------------------------ */
+typedef struct b200bt_bt_params {
+    double initial_balance;
+    double position_pct;       /* 0.25 / 0.20 / 0.15 by volatility class (:256-264)      */
+    double stop_loss_pct;      /* 0.02 / 0.015 / 0.01 -- a FRACTION compared with a PERCENT
+                                  pnl (strategy_tester.py:206-215), quirk kept            */
+    double take_profit_pct;    /* 2 x stop_loss_pct (:287)                                */
+    double volume_factor;      /* min(avg_volume/50000, 1) (:267)                         */
+    double max_risk_per_trade; /* 0.15                                                    */
+    int32_t can_enter;         /* technical BUY x strength>=70 x AI gate (:371-401)       */
+    int32_t skip;              /* 10 (:192)                                               */
+} b200bt_bt_params; /* 56 bytes */
+
+/* stats  [S][16] float64: final_balance, total_trades, winning, losing, total_profit,
+ *                         total_loss(positive), max_drawdown, max_drawdown_pct, n_equity_points, open_at_end
+ * trades [S][trade_cap][8] float64: entry_bar, exit_bar, reason(1 SL,2 TP,3 end), entry_price,
+ *                         quantity, position_size, pnl, pnl_pct
+ * equity [S][equity_cap][2] float64: bar, cash balance at that (flat or entry) bar */
+int b200bt_backtest_ref(const float* price, int64_t ld, int S, int64_t N,
+                        const b200bt_bt_params* params, double* stats, double* trades,
+                        int64_t trade_cap, double* equity, int64_t equity_cap,
+                        b200bt_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Family 3: Monte-Carlo risk projection.

@@ -117,3 +117,37 @@ def rsi_bank(close32: np.ndarray, periods, fill: bool = True) -> np.ndarray:
             r = handle_nan(r)
         rows.append(r.to_numpy().astype(np.float32))
     return np.stack(rows)
+
+
+def analyzer_columns(open_, high, low, close, volume) -> dict:
+    """All TechnicalAnalyzer columns (binance_ml_strategy.py:40-182) after _handle_nan_values."""
+    cols = {}
+    cols["sma_20"], cols["sma_50"], cols["sma_200"] = sma(close, 20), sma(close, 50), sma(close, 200)
+    cols["ema_12"], cols["ema_26"] = ema(close, 12), ema(close, 26)
+    cols["macd"], cols["macd_signal"], cols["macd_diff"] = macd(close)
+    cols["ichimoku_a"], cols["ichimoku_b"] = ichimoku(high, low)
+    cols["rsi"] = rsi(close)
+    cols["stoch_k"], cols["stoch_d"] = stochastic(high, low, close)
+    cols["williams_r"] = williams_r(high, low, close)
+    cols["bb_high"], cols["bb_mid"], cols["bb_low"] = bollinger(close)
+    cols["bb_width"], cols["bb_position"] = bollinger_width_position(close, cols["bb_high"], cols["bb_mid"], cols["bb_low"])
+    cols["atr"] = atr(high, low, close)
+    cols["vwap"] = vwap(high, low, close, volume)
+    return {k: handle_nan(v) for k, v in cols.items()}
+
+
+def analyzer_scalars(open_, high, low, close, volume) -> dict:
+    """get_all_indicators / get_trend / get_volatility (binance_ml_strategy.py:184-249)."""
+    c = analyzer_columns(open_, high, low, close, volume)
+    last = lambda s: float(s.iloc[-1])
+    last_close, sma20, sma50 = last(close), last(c["sma_20"]), last(c["sma_50"])
+    strength = ((last_close - sma20) / sma20 * 100 + (last_close - sma50) / sma50 * 100) / 2
+    if last_close > sma20 and sma20 > sma50:
+        trend = "uptrend"
+    elif last_close < sma20 and sma20 < sma50:
+        trend = "downtrend"
+    else:
+        trend = "sideways"
+    return {"rsi": last(c["rsi"]), "stoch_k": last(c["stoch_k"]), "stoch_d": last(c["stoch_d"]), "macd": last(c["macd"]),
+            "macd_signal": last(c["macd_signal"]), "williams_r": last(c["williams_r"]), "bb_position": last(c["bb_position"]),
+            "volatility": last(c["atr"]) / last_close, "trend": trend, "trend_strength": abs(strength)}

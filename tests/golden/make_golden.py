@@ -9,6 +9,7 @@ Writes (all small, committed):
     tests/golden/sim_cases.npz    fp32 inputs + reference trade records
     tests/golden/ga_run.json      seeded GeneticAlgorithm trajectory
     tests/golden/mc_reference.*   MonteCarloService results + its own paths (NumPy seed fixed)
+    tests/golden/bt_reference.*   StrategyTester.backtest_strategy runs (LLM stubbed, `ta` shimmed)
 Inputs are the fp32 synthetic series of ai_crypto_trader_b200.synth; the RSI
 bank is oracle.indicators_ref.rsi_bank (float64 pandas, rounded to fp32).
 The reference functions executed are
@@ -188,11 +189,67 @@ def make_mc():
         {"cases": meta, "portfolio": {"holdings": holdings, "simulations": sims, "stats": pstats}}, indent=1))
 
 
+def bt_frame(n, crash, vol_scale, sym=0):
+    """OHLCV DataFrame for the configs[0] fixtures: the synthetic series, optionally ending in a
+    10 % sell-off over the last 60 bars (drives the constant technical signal to BUY/strength>=70)."""
+    import pandas as pd
+    d = synth.synth_symbol(sym, n)
+    cols = {k: d[k].astype(np.float64).copy() for k in synth.FIELDS}
+    if crash:
+        f = np.ones(n)
+        f[-60:] = np.linspace(1.0, 0.90, 60)
+        for k in ("open", "high", "low", "close"):
+            cols[k] *= f
+    cols["volume"] *= vol_scale
+    idx = pd.date_range("2024-01-01", periods=n, freq="min")
+    return pd.DataFrame({k: v.astype(np.float32).astype(np.float64) for k, v in cols.items()}, index=idx)  # fp32 market data, widened (CSV-loaded frames are float64)
+
+
+BT_CASES = [("crash_trading", 3000, True, 1000.0, 0), ("quiet_no_entry", 2500, False, 1.0, 1),
+            ("crash_lowvolume", 1200, True, 1.0, 2)]
+
+
+def make_bt():
+    """Reference StrategyTester.backtest_strategy (LLM stubbed, `ta` shimmed; oracle/ref_runner.py)."""
+    arrays, meta = {}, []
+    for name, n, crash, vs, sym in BT_CASES:
+        df = bt_frame(n, crash, vs, sym)
+        stats, tester, bms = ref_runner.run_reference_backtest(df)                    # REFERENCE
+        bar = {t.isoformat(): i for i, t in enumerate(df.index)}
+        tr = stats["trades"]
+        arrays[f"entry_bar_{name}"] = np.array([bar[t["entry_time"]] for t in tr], dtype=np.int64)
+        arrays[f"exit_bar_{name}"] = np.array([bar[t["exit_time"]] for t in tr], dtype=np.int64)
+        arrays[f"reason_{name}"] = np.array([{"Stop Loss": 1, "Take Profit": 2, "End of Test": 3}[t["exit_reason"]] for t in tr], dtype=np.int64)
+        for k in ("entry_price", "quantity", "position_size", "pnl", "pnl_pct"):
+            arrays[f"{k}_{name}"] = np.array([t[k] for t in tr], dtype=np.float64)
+        arrays[f"eq_bar_{name}"] = np.array([bar[p["timestamp"]] for p in stats["equity_curve"]], dtype=np.int64)
+        arrays[f"eq_{name}"] = np.array([p["equity"] for p in stats["equity_curve"]], dtype=np.float64)
+        arrays[f"dd_{name}"] = np.array([[p["drawdown"], p["drawdown_pct"]] for p in stats["drawdown_curve"]], dtype=np.float64).reshape(-1, 2)
+        # the per-bar constants the reference feeds its signal (one market update is enough: they are frame constants)
+        upd = tester.prepare_market_data(df.iloc[:], "SYNUSDC")[-1]
+        sig = bms.TradingSignal(symbol="SYNUSDC", price=upd["current_price"], rsi=upd["rsi"], stoch_k=upd["stoch_k"],
+                                macd=upd["macd"], volume=upd["avg_volume"], volatility=upd["volatility"],
+                                williams_r=upd["williams_r"], trend=upd["trend"], trend_strength=upd["trend_strength"],
+                                bb_position=upd["bb_position"])
+        consts = {k: upd[k] for k in ("rsi", "stoch_k", "macd", "williams_r", "bb_position", "trend", "trend_strength",
+                                      "volatility", "avg_volume", "price_change_1m", "price_change_3m",
+                                      "price_change_5m", "price_change_15m")}
+        scal = {k: jsonable(v) if not isinstance(v, str) else v for k, v in stats.items() if not isinstance(v, list)}
+        meta.append({"name": name, "n": n, "crash": crash, "vol_scale": vs, "symbol": sym, "stats": scal,
+                     "constants": {k: (v if isinstance(v, str) else jsonable(v)) for k, v in consts.items()},
+                     "signal": sig.signal, "strength": jsonable(sig.strength), "n_trades": len(tr)})
+        print(f"BT {name}: trades={len(tr)} final={stats['final_balance']:.4f} signal={sig.signal} strength={sig.strength:.2f}")
+    np.savez_compressed(OUT / "bt_reference.npz", **arrays)
+    (OUT / "bt_reference.json").write_text(json.dumps({"cases": meta}, indent=1))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sim", "ga", "mc"]
+    which = sys.argv[1:] or ["sim", "ga", "mc", "bt"]
     if "sim" in which:
         make_sim()
     if "ga" in which:
         make_ga()
     if "mc" in which:
         make_mc()
+    if "bt" in which:
+        make_bt()

@@ -1,0 +1,130 @@
+"""GPU indicator kernels vs the float64 pandas restatement of `ta` (oracle/indicators_ref.py)."""
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 2e-6   # fp64 evaluation rounded once to fp32 vs float64 pandas (tolerance stated per north star: 1e-5)
+
+
+@pytest.fixture(scope="module")
+def gpu(native_lib):
+    import torch
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    return torch
+
+
+def _series(ohlcv, s):
+    return [pd.Series(ohlcv[f, s].astype(np.float64)) for f in range(5)]
+
+
+def _cmp(got, want, name, rtol=RTOL, atol=0.0):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, name
+    assert np.array_equal(np.isnan(got), np.isnan(want)), (name, np.flatnonzero(np.isnan(got) != np.isnan(want))[:5])
+    m = ~np.isnan(want)
+    np.testing.assert_allclose(got[m], want[m], rtol=rtol, atol=atol, err_msg=name)
+
+
+@pytest.mark.parametrize("n_bars", [1, 5, 19, 20, 60, 255, 2048, 2049, 5000, 70001])
+def test_all_indicators_no_fill(gpu, n_bars):
+    torch = gpu
+    from ai_crypto_trader_b200 import indicators as ind, synth
+    from oracle import indicators_ref as ref
+    S = 2
+    ohlcv = synth.synth_ohlcv(S, n_bars, first_symbol=2)
+    o, h, l, c, v = [torch.from_numpy(ohlcv[f]).cuda() for f in range(5)]
+    ema = ind.ema_bank(c, [3, 12, 26, 100], fill=False).cpu().numpy()
+    sma = ind.sma_bank(c, [5, 20, 50, 200], fill=False).cpu().numpy()
+    line, sig, diff = [t.cpu().numpy() for t in ind.macd(c, fill=False)]
+    bb = [t.cpu().numpy() for t in ind.bollinger(c, fill=False)]
+    sk, sd = [t.cpu().numpy() for t in ind.stochastic(h, l, c, fill=False)]
+    wr = ind.williams_r(h, l, c, fill=False).cpu().numpy()
+    ia, ib = [t.cpu().numpy() for t in ind.ichimoku(h, l, fill=False)]
+    atr = ind.atr_bank(h, l, c, [7, 14, 25]).cpu().numpy()
+    vw = ind.vwap(h, l, c, v, fill=False).cpu().numpy()
+    for s in range(S):
+        so, sh, sl, sc, sv = _series(ohlcv, s)
+        for i, w in enumerate([3, 12, 26, 100]):
+            _cmp(ema[s, i], ref.ema(sc, w), f"ema{w}")
+        for i, w in enumerate([5, 20, 50, 200]):
+            _cmp(sma[s, i], ref.sma(sc, w), f"sma{w}")
+        rl, rs, rd = ref.macd(sc)
+        _cmp(line[s], rl, "macd", atol=1e-9)
+        _cmp(sig[s], rs, "macd_signal", atol=1e-9)
+        _cmp(diff[s], rd, "macd_diff", rtol=1e-4, atol=2e-7)   # difference of two nearly equal fp32-rounded numbers
+        rh, rm, rlo = ref.bollinger(sc)
+        rw, rp = ref.bollinger_width_position(sc, rh, rm, rlo)
+        for got, want, nm, tol in zip(bb, (rh, rm, rlo, rw, rp), ("bb_high", "bb_mid", "bb_low", "bb_width", "bb_pos"),
+                                      (RTOL, RTOL, RTOL, 2e-5, 2e-5)):
+            _cmp(got[s], want, nm, rtol=tol, atol=1e-7)
+        rk, rdd = ref.stochastic(sh, sl, sc)
+        _cmp(sk[s], rk, "stoch_k", atol=1e-5)
+        _cmp(sd[s], rdd, "stoch_d", atol=1e-5)
+        _cmp(wr[s], ref.williams_r(sh, sl, sc), "williams", atol=1e-5)
+        ra, rb = ref.ichimoku(sh, sl)
+        _cmp(ia[s], ra, "ichimoku_a")
+        _cmp(ib[s], rb, "ichimoku_b")
+        for i, w in enumerate([7, 14, 25]):
+            _cmp(atr[s, i], ref.atr(sh, sl, sc, w), f"atr{w}", atol=1e-12)
+        _cmp(vw[s], ref.vwap(sh, sl, sc, sv), "vwap")
+
+
+def test_nanfill_matches_handle_nan_values(gpu):
+    torch = gpu
+    from ai_crypto_trader_b200.indicators import nanfill_
+    from oracle.indicators_ref import handle_nan
+    rng = np.random.default_rng(0)
+    n = 20000
+    x = rng.normal(size=(6, n)).astype(np.float32)
+    x[0, :37] = np.nan                      # leading run
+    x[1, 100:9000] = np.nan                 # run spanning two 4096-tiles
+    x[2, :] = np.nan                        # all-NaN column -> 0
+    x[3, rng.random(n) < 0.3] = np.nan      # scattered
+    x[4, -5:] = np.nan                      # trailing
+    x[5, :4096] = np.nan                    # exactly one leading tile
+    got = nanfill_(torch.from_numpy(x.copy()).cuda()).cpu().numpy()
+    for r in range(6):
+        want = handle_nan(pd.Series(x[r].astype(np.float64))).to_numpy().astype(np.float32)
+        assert np.array_equal(got[r], want), r
+
+
+def test_flat_series_edge_cases(gpu):
+    torch = gpu
+    from ai_crypto_trader_b200 import indicators as ind
+    from oracle import indicators_ref as ref
+    n = 300
+    c = np.full((1, n), 50.0, dtype=np.float32)
+    c[0, 150:] += np.arange(150, dtype=np.float32) * 0.25
+    h, l = c.copy(), c.copy()               # high == low == close: zero ranges
+    v = np.ones_like(c)
+    tc, th, tl, tv = [torch.from_numpy(a).cuda() for a in (c, h, l, v)]
+    sc = pd.Series(c[0].astype(np.float64))
+    bb = [t.cpu().numpy()[0] for t in ind.bollinger(tc, fill=True)]
+    rh, rm, rlo = ref.bollinger(sc)
+    rw, rp = ref.bollinger_width_position(sc, rh, rm, rlo)
+    _cmp(bb[4], ref.handle_nan(rp), "bb_position filled", atol=1e-6)          # zero range -> NaN -> filled
+    k, d = [t.cpu().numpy()[0] for t in ind.stochastic(th, tl, tc, fill=True)]
+    rk, rd = ref.stochastic(sc, sc, sc)
+    _cmp(k, ref.handle_nan(rk), "stoch_k filled", atol=1e-5)
+    _cmp(d, ref.handle_nan(rd), "stoch_d filled", atol=1e-5)
+
+
+def test_technical_analyzer_last_bar_scalars(gpu):
+    """TechnicalAnalyzer.get_all_indicators vs the same scalars from the float64 oracle columns."""
+    from ai_crypto_trader_b200 import synth
+    from ai_crypto_trader_b200.indicators import TechnicalAnalyzer
+    from ai_crypto_trader_b200.sweep import MarketData
+    from oracle import indicators_ref as ref
+    ohlcv = synth.synth_ohlcv(3, 10000)
+    ta = TechnicalAnalyzer(MarketData(ohlcv))
+    for s in range(3):
+        so, sh, sl, sc, sv = _series(ohlcv, s)
+        want = ref.analyzer_scalars(so, sh, sl, sc, sv)
+        got = ta.get_all_indicators(s)
+        assert got["trend"] == want["trend"]
+        for k in ("rsi", "stoch_k", "stoch_d", "macd", "macd_signal", "williams_r", "bb_position", "volatility", "trend_strength"):
+            assert got[k] == pytest.approx(want[k], rel=2e-5, abs=2e-6), (s, k)
