@@ -140,6 +140,11 @@ def ptr(t) -> int:
     return None if t is None else t.data_ptr()
 
 
+def ld(t) -> int:
+    """Row stride (in elements) of the last-but-one axis; a size-1 axis may carry any stride."""
+    return int(t.stride(-2)) if t.shape[-2] > 1 else int(t.shape[-1])
+
+
 def current_stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream

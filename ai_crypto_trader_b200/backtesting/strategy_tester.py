@@ -166,7 +166,7 @@ class StrategyTester:
         trades_dev = torch.zeros((n + 1, 8), dtype=torch.float64, device=dev)
         equity_dev = torch.zeros((n + 1, 2), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
-            _lib.call("b200bt_backtest_ref", market.close.data_ptr(), market.close.stride(0), 1, n, prm_dev.data_ptr(),
+            _lib.call("b200bt_backtest_ref", market.close.data_ptr(), _lib.ld(market.close), 1, n, prm_dev.data_ptr(),
                       stats_dev.data_ptr(), trades_dev.data_ptr(), n + 1, equity_dev.data_ptr(), n + 1, _lib.current_stream())
         s = stats_dev.cpu().numpy()
         n_tr, n_eq = int(s[1]), int(s[8])

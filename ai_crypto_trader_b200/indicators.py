@@ -43,7 +43,7 @@ def _bank(fn: str, x: torch.Tensor, windows: Sequence[int], fill: bool, extra=()
     S, N = _check(x)
     out = torch.empty((S, len(windows), N), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.call(fn, *extra, x.data_ptr(), S, N, x.stride(0), _ints(windows), len(windows), out.data_ptr(),
+        _lib.call(fn, *extra, x.data_ptr(), S, N, _lib.ld(x), _ints(windows), len(windows), out.data_ptr(),
                   _lib.current_stream())
     return nanfill_(out) if fill else out
 
@@ -60,7 +60,7 @@ def atr_bank(high, low, close, windows: Sequence[int]) -> torch.Tensor:
     S, N = _check(high, low, close)
     out = torch.empty((S, len(windows), N), dtype=torch.float32, device=close.device)
     with torch.cuda.device(close.device):
-        _lib.call("b200bt_atr_bank", high.data_ptr(), low.data_ptr(), close.data_ptr(), S, N, close.stride(0),
+        _lib.call("b200bt_atr_bank", high.data_ptr(), low.data_ptr(), close.data_ptr(), S, N, _lib.ld(close),
                   _ints(windows), len(windows), out.data_ptr(), _lib.current_stream())
     return out
 
@@ -80,7 +80,7 @@ def macd(close, fast: int = 12, slow: int = 26, sign: int = 9, fill: bool = True
     S, N = _check(close)
     line, signal, diff = _outs(3, close.contiguous())
     with torch.cuda.device(close.device):
-        _lib.call("b200bt_macd", close.data_ptr(), S, N, close.stride(0), fast, slow, sign, line.data_ptr(),
+        _lib.call("b200bt_macd", close.data_ptr(), S, N, _lib.ld(close), fast, slow, sign, line.data_ptr(),
                   signal.data_ptr(), diff.data_ptr(), _lib.current_stream())
     return tuple(_maybe_fill([line, signal, diff], fill))
 
@@ -90,7 +90,7 @@ def bollinger(close, window: int = 20, dev: float = 2.0, fill: bool = True):
     S, N = _check(close)
     outs = _outs(5, close.contiguous())
     with torch.cuda.device(close.device):
-        _lib.call("b200bt_bollinger", close.data_ptr(), S, N, close.stride(0), window, float(dev),
+        _lib.call("b200bt_bollinger", close.data_ptr(), S, N, _lib.ld(close), window, float(dev),
                   *[o.data_ptr() for o in outs], _lib.current_stream())
     return tuple(_maybe_fill(outs, fill))
 
@@ -99,7 +99,7 @@ def stochastic(high, low, close, window: int = 14, smooth: int = 3, fill: bool =
     S, N = _check(high, low, close)
     k, d = _outs(2, close.contiguous())
     with torch.cuda.device(close.device):
-        _lib.call("b200bt_stochastic", high.data_ptr(), low.data_ptr(), close.data_ptr(), S, N, close.stride(0),
+        _lib.call("b200bt_stochastic", high.data_ptr(), low.data_ptr(), close.data_ptr(), S, N, _lib.ld(close),
                   window, smooth, k.data_ptr(), d.data_ptr(), _lib.current_stream())
     return tuple(_maybe_fill([k, d], fill))
 
@@ -108,7 +108,7 @@ def williams_r(high, low, close, lbp: int = 14, fill: bool = True):
     S, N = _check(high, low, close)
     (out,) = _outs(1, close.contiguous())
     with torch.cuda.device(close.device):
-        _lib.call("b200bt_williams_r", high.data_ptr(), low.data_ptr(), close.data_ptr(), S, N, close.stride(0), lbp,
+        _lib.call("b200bt_williams_r", high.data_ptr(), low.data_ptr(), close.data_ptr(), S, N, _lib.ld(close), lbp,
                   out.data_ptr(), _lib.current_stream())
     return _maybe_fill([out], fill)[0]
 
@@ -117,7 +117,7 @@ def ichimoku(high, low, w1: int = 9, w2: int = 26, w3: int = 52, fill: bool = Tr
     S, N = _check(high, low)
     a, b = _outs(2, high.contiguous())
     with torch.cuda.device(high.device):
-        _lib.call("b200bt_ichimoku", high.data_ptr(), low.data_ptr(), S, N, high.stride(0), w1, w2, w3, a.data_ptr(),
+        _lib.call("b200bt_ichimoku", high.data_ptr(), low.data_ptr(), S, N, _lib.ld(high), w1, w2, w3, a.data_ptr(),
                   b.data_ptr(), _lib.current_stream())
     return tuple(_maybe_fill([a, b], fill))
 
@@ -127,7 +127,7 @@ def vwap(high, low, close, volume, window: int = 14, fill: bool = True):
     (out,) = _outs(1, close.contiguous())
     with torch.cuda.device(close.device):
         _lib.call("b200bt_vwap", high.data_ptr(), low.data_ptr(), close.data_ptr(), volume.data_ptr(), S, N,
-                  close.stride(0), window, out.data_ptr(), _lib.current_stream())
+                  _lib.ld(close), window, out.data_ptr(), _lib.current_stream())
     return _maybe_fill([out], fill)[0]
 
 

@@ -104,7 +104,7 @@ def rsi_bank(close: torch.Tensor, periods: Sequence[int], fill: bool = True,
         out = torch.empty((S, P, N), dtype=torch.float32, device=close.device)
     arr = (C.c_int * P)(*[int(p) for p in periods])
     with torch.cuda.device(close.device):
-        _lib.call("b200bt_rsi_bank", close.data_ptr(), S, N, close.stride(0), arr, P, 1 if fill else 0,
+        _lib.call("b200bt_rsi_bank", close.data_ptr(), S, N, _lib.ld(close), arr, P, 1 if fill else 0,
                   out.data_ptr(), _lib.current_stream())
     return out
 
@@ -212,8 +212,8 @@ class PopulationSweep:
             self._pop = pop
         with torch.cuda.device(m.device):
             st = _lib.current_stream()
-            _lib.call("b200bt_sweep", m.close.data_ptr(), m.close.stride(0), self.bank.data_ptr(),
-                      self.bank.stride(1), len(self.periods), m.S, m.N, indiv_dev.data_ptr(),
+            _lib.call("b200bt_sweep", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(),
+                      _lib.ld(self.bank), len(self.periods), m.S, m.N, indiv_dev.data_ptr(),
                       _lib.ptr(order_dev), pop, C.byref(self.cfg), self._stats.data_ptr(),
                       _lib.ptr(self._events), self.event_cap, st)
             _lib.call("b200bt_fitness_reduce", self._stats.data_ptr(), pop, m.S, fitness_dev.data_ptr(), st)

@@ -265,7 +265,7 @@ def main():
         # the dominant kernel (b200bt_sweep) is bracketed by its own events inside the timed region
         k_ev[i][0].record()
         m = sweep.market
-        _lib.call("b200bt_sweep", m.close.data_ptr(), m.close.stride(0), sweep.bank.data_ptr(), sweep.bank.stride(1),
+        _lib.call("b200bt_sweep", m.close.data_ptr(), _lib.ld(m.close), sweep.bank.data_ptr(), _lib.ld(sweep.bank),
                   len(sweep.periods), m.S, m.N, indiv_dev.data_ptr(), order_dev.data_ptr(), pop_local,
                   __import__("ctypes").byref(sweep.cfg), sweep._stats.data_ptr(), None, 0, _lib.current_stream())
         k_ev[i][1].record()
