@@ -81,6 +81,9 @@ _SIGNATURES = {
     "b200bt_ichimoku": (C.c_int, [_vp, _vp, _i, _i64, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "b200bt_atr_bank": (C.c_int, [_vp, _vp, _vp, _i, _i64, _i64, C.POINTER(C.c_int), _i, _vp, _vp]),
     "b200bt_vwap": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _vp]),
+    "b200bt_resample_bars": (C.c_int64, [_i64, _i64, _i, _i]),
+    "b200bt_resample": (C.c_int, [_vp, _i, _i64, _i64, _i, _i, _vp, _i64, _vp]),
+    "b200bt_align": (C.c_int, [_vp, _i, _i64, _i64, _i64, _i, _i, _vp, _vp]),
     "b200bt_nanfill_workspace_floats": (C.c_int64, [_i64, _i64]),
     "b200bt_nanfill": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "b200bt_sweep": (C.c_int, [_vp, _i64, _vp, _i64, _i, _i, _i64, _vp, _vp, _i,

@@ -190,3 +190,63 @@ class TechnicalAnalyzer:
                 "macd": self._get(s, "macd"), "macd_signal": self._get(s, "macd_signal"),
                 "williams_r": self._get(s, "williams_r"), "bb_position": self._get(s, "bb_position"),
                 "volatility": self.get_volatility(s), "trend": trend, "trend_strength": strength}
+
+
+# ---------------------------------------------------------------------------------------
+# Multi-timeframe (BASELINE configs[3]); recipe: services/market_monitor_service.py:219-301
+# ---------------------------------------------------------------------------------------
+def resample(market, k: int):
+    """Clock-aligned k-minute bars derived on the device from `market` (a MarketData)."""
+    from .sweep import MarketData
+    M = int(_lib.load().b200bt_resample_bars(market.N, market.minute0, market.bar_minutes, k))
+    out = torch.empty((5, market.S, M), dtype=torch.float32, device=market.device)
+    with torch.cuda.device(market.device):
+        _lib.call("b200bt_resample", market.ohlcv.data_ptr(), market.S, market.N, market.minute0, market.bar_minutes, k,
+                  out.data_ptr(), M, _lib.current_stream())
+    first_bucket_minute = (market.minute0 // k) * k
+    return MarketData(out, symbols=market.symbols, minute0=first_bucket_minute, bar_minutes=k, device=market.device)
+
+
+def align_to_base(series: torch.Tensor, base, k: int) -> torch.Tensor:
+    """Higher-timeframe series [S][M] -> base clock [S][N]: value of the last COMPLETED k-minute bar."""
+    S, M = series.shape
+    out = torch.empty((S, base.N), dtype=torch.float32, device=series.device)
+    series = series.contiguous()
+    with torch.cuda.device(series.device):
+        _lib.call("b200bt_align", series.data_ptr(), S, M, base.N, base.minute0, base.bar_minutes, k, out.data_ptr(),
+                  _lib.current_stream())
+    return out
+
+
+def multi_timeframe_indicators(market, s: int = 0) -> Dict:
+    """calculate_technical_indicators (market_monitor_service.py:219-301) for symbol `s`: RSI/MACD on
+    1m, 3m, 5m; stochastic, Williams, Bollinger position, SMA20/50 on 1m; SMA20 on 5m; trend from 1m;
+    trend_strength = |0.6*s_1m + 0.4*s_5m|; price changes against the open of each timeframe's last bar."""
+    tf = {1: market, 3: resample(market, 3), 5: resample(market, 5), 15: resample(market, 15)}
+    last = lambda t: float(t[s, -1].item())
+    out = {}
+    for k, name in ((1, ""), (3, "_3m"), (5, "_5m")):
+        m = tf[k]
+        out["rsi" + name] = last(rsi_bank(m.close, [14], fill=False)[:, 0])
+        out["macd" + name] = last(macd(m.close, fill=False)[0])
+    m1 = tf[1]
+    out["stoch_k"] = last(stochastic(m1.high, m1.low, m1.close, fill=False)[0])
+    out["williams_r"] = last(williams_r(m1.high, m1.low, m1.close, fill=False))
+    out["bb_position"] = last(bollinger(m1.close, fill=False)[4])
+    sma1 = sma_bank(m1.close, [20, 50], fill=False)
+    sma20_1m, sma50_1m = last(sma1[:, 0]), last(sma1[:, 1])
+    sma20_5m = last(sma_bank(tf[5].close, [20], fill=False)[:, 0])
+    last_close = last(m1.close)
+    strength_1m = (last_close - sma20_1m) / sma20_1m * 100
+    strength_5m = (last_close - sma20_5m) / sma20_5m * 100
+    out["trend_strength"] = abs(strength_1m * 0.6 + strength_5m * 0.4)
+    if last_close > sma20_1m and sma20_1m > sma50_1m:
+        out["trend"] = "uptrend"
+    elif last_close < sma20_1m and sma20_1m < sma50_1m:
+        out["trend"] = "downtrend"
+    else:
+        out["trend"] = "sideways"
+    for k in (1, 3, 5, 15):
+        o = last(tf[k].open)
+        out[f"price_change_{k}m"] = ((last_close - o) / o) * 100
+    return out

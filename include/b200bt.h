@@ -101,6 +101,17 @@ int b200bt_atr_bank(const float* high, const float* low, const float* close, int
 int b200bt_vwap(const float* high, const float* low, const float* close, const float* volume, int S,
                 int64_t N, int64_t ld, int window, float* out, b200bt_stream_t stream);
 
+/* Multi-timeframe (BASELINE configs[3]; recipe: services/market_monitor_service.py:219-301, where
+ * each timeframe is its own kline series, :168-171).  b200bt_resample derives clock-aligned k-minute
+ * OHLCV [5][S][M] from 1-minute (or bar_minutes) OHLCV [5][S][N]; M = b200bt_resample_bars(...).
+ * b200bt_align maps a higher-timeframe series [S][M] back onto the base clock [S][N] using the last
+ * COMPLETED higher-timeframe bar (NaN before the first one). */
+int64_t b200bt_resample_bars(int64_t N, int64_t minute0, int bar_minutes, int k);
+int b200bt_resample(const float* ohlcv, int S, int64_t N, int64_t minute0, int bar_minutes, int k,
+                    float* out, int64_t M, b200bt_stream_t stream);
+int b200bt_align(const float* src, int S, int64_t M, int64_t N, int64_t minute0, int bar_minutes, int k,
+                 float* out, b200bt_stream_t stream);
+
 /* TechnicalAnalyzer._handle_nan_values (:28-38) on `rows` contiguous rows of length N, in place:
  * forward-fill, then back-fill, then 0.  workspace: b200bt_nanfill_workspace_floats(rows, N) floats. */
 int64_t b200bt_nanfill_workspace_floats(int64_t rows, int64_t N);

@@ -128,3 +128,61 @@ def test_technical_analyzer_last_bar_scalars(gpu):
         assert got["trend"] == want["trend"]
         for k in ("rsi", "stoch_k", "stoch_d", "macd", "macd_signal", "williams_r", "bb_position", "volatility", "trend_strength"):
             assert got[k] == pytest.approx(want[k], rel=2e-5, abs=2e-6), (s, k)
+
+
+@pytest.mark.parametrize("k,offset", [(5, 0), (15, 7), (3, 2)])
+def test_resample_and_align(gpu, k, offset):
+    """Derived k-minute bars equal pandas' clock-aligned resample; alignment uses completed bars only."""
+    torch = gpu
+    from ai_crypto_trader_b200 import indicators as ind, synth
+    from ai_crypto_trader_b200.sweep import MarketData
+    n = 5003
+    ohlcv = synth.synth_ohlcv(2, n)
+    minute0 = synth.EPOCH_2024_MINUTES + offset
+    base = MarketData(ohlcv, minute0=minute0)
+    hi = ind.resample(base, k)
+    got = hi.ohlcv.cpu().numpy()
+    idx = pd.to_datetime((minute0 + np.arange(n)) * 60, unit="s")
+    for s in range(2):
+        df = pd.DataFrame({f: ohlcv[i, s].astype(np.float64) for i, f in enumerate(synth.FIELDS)}, index=idx)
+        r = df.resample(f"{k}min").agg({"open": "first", "high": "max", "low": "min", "close": "last", "volume": "sum"})
+        assert got.shape[2] == len(r)
+        for i, f in enumerate(("open", "high", "low", "close")):
+            assert np.array_equal(got[i, s], r[f].to_numpy().astype(np.float32)), f
+        np.testing.assert_allclose(got[4, s], r["volume"].to_numpy(), rtol=1e-6)
+        # alignment: at base bar t, the last k-minute bar whose final minute is <= t
+        al = ind.align_to_base(hi.close, base, k).cpu().numpy()[s]
+        ends = (r.index.astype("datetime64[s]").astype(np.int64) // 60).to_numpy() + k - 1     # last minute of each bucket
+        mins = minute0 + np.arange(n)
+        j = np.searchsorted(ends, mins, side="right") - 1
+        want = np.where(j >= 0, r["close"].to_numpy().astype(np.float32)[np.maximum(j, 0)], np.nan)
+        assert np.array_equal(np.isnan(al), np.isnan(want)) and np.array_equal(al[~np.isnan(want)], want[~np.isnan(want)].astype(np.float32))
+
+
+def test_multi_timeframe_recipe(gpu):
+    from ai_crypto_trader_b200 import indicators as ind, synth
+    from ai_crypto_trader_b200.sweep import MarketData
+    from oracle import indicators_ref as ref
+    n = 3000
+    ohlcv = synth.synth_ohlcv(1, n)
+    base = MarketData(ohlcv)
+    got = ind.multi_timeframe_indicators(base, 0)
+    idx = pd.to_datetime((synth.EPOCH_2024_MINUTES + np.arange(n)) * 60, unit="s")
+    df = pd.DataFrame({f: ohlcv[i, 0].astype(np.float64) for i, f in enumerate(synth.FIELDS)}, index=idx)
+    agg = {"open": "first", "high": "max", "low": "min", "close": "last", "volume": "sum"}
+    d3, d5, d15 = (df.resample(f"{k}min").agg(agg) for k in (3, 5, 15))
+    # resampled bars hold fp32 values on the device
+    for d in (d3, d5, d15):
+        for c in d.columns:
+            d[c] = d[c].astype(np.float32).astype(np.float64)
+    last = lambda s: float(s.iloc[-1])
+    want = {"rsi": last(ref.rsi(df["close"])), "rsi_3m": last(ref.rsi(d3["close"])), "rsi_5m": last(ref.rsi(d5["close"])),
+            "macd": last(ref.macd(df["close"])[0]), "macd_3m": last(ref.macd(d3["close"])[0]), "macd_5m": last(ref.macd(d5["close"])[0]),
+            "stoch_k": last(ref.stochastic(df["high"], df["low"], df["close"])[0]),
+            "williams_r": last(ref.williams_r(df["high"], df["low"], df["close"]))}
+    s1 = (last(df["close"]) - last(ref.sma(df["close"], 20))) / last(ref.sma(df["close"], 20)) * 100
+    s5 = (last(df["close"]) - last(ref.sma(d5["close"], 20))) / last(ref.sma(d5["close"], 20)) * 100
+    want["trend_strength"] = abs(0.6 * s1 + 0.4 * s5)
+    for k, v in want.items():
+        assert got[k] == pytest.approx(v, rel=3e-5, abs=3e-6), k
+    assert got["price_change_15m"] == pytest.approx((last(df["close"]) - last(d15["open"])) / last(d15["open"]) * 100, rel=1e-5)
