@@ -30,11 +30,11 @@ namespace b200bt {
 
 constexpr int SW_WARPS = 8;         // warps (lanes of the sweep) per CTA
 #ifndef B200BT_SW_MIN_BLOCKS
-#define B200BT_SW_MIN_BLOCKS 3
+#define B200BT_SW_MIN_BLOCKS 2
 #endif
 constexpr int SW_MIN_BLOCKS = B200BT_SW_MIN_BLOCKS;    // CTAs per SM the register budget is held to (<= 64 regs/thread)
-constexpr int SW_GROUP = 128;       // bars per cp.async group (per stream)
-constexpr int SW_STAGES = 4;        // shared-memory ring depth per warp
+constexpr int SW_GROUP = 256;       // bars per cp.async group (per stream)
+constexpr int SW_STAGES = 3;        // shared-memory ring depth per warp
 constexpr int SW_EVQ = 128;         // event queue entries per warp (>= 32 + 64 new events per window pair)
 constexpr float SW_MARGIN = 1e-6f;  // relative width of the fp32 screening band
 
@@ -90,6 +90,11 @@ __device__ __noinline__ void process_batch(WarpShared* __restrict__ ws, unsigned
                                            long long minute0, int bar_minutes, int64_t ev_cap) {
     const int lane = threadIdx.x & 31;
     WarpAcc* __restrict__ acc = &ws->acc;
+#ifdef B200BT_SW_NOBATCH   // timing experiment only: skip the batch arithmetic
+    if (lane == 0) acc->n_events += cnt;
+    __syncwarp();
+    return;
+#endif
     const bool active = lane < cnt;
     const uint2 evt = ws->evq[(qtail + lane) & (SW_EVQ - 1)];
     const unsigned w = evt.x;
@@ -230,62 +235,81 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 struct Machine {
     int pos;                                   // 0 flat, +1 long, -1 short
     float e;                                   // entry price
-    float rlo, rhi, plo, phi;                  // event thresholds of the current state (screening bounds)
+    float plo, phi;                            // price bounds of the open position: exit CANDIDATE when crossed
+    float plo_d, phi_d;                        // ... DEFINITE exit when crossed (fp32 screening band in between)
     unsigned qhead;                            // events pushed so far (queue head)
 };
 
-__device__ __forceinline__ bool fires(const Machine& m, float p, float r) {
-    return (r < m.rlo) | (r > m.rhi) | (p <= m.plo) | (p >= m.phi);
+// Per-window hit masks (bit l = bar t0+l).  `os`/`ob` depend only on the lane's RSI thresholds,
+// never on the machine state; `cand`/`defi` depend on the open position's price bounds.
+struct WindowHits {
+    unsigned os, ob;      // rsi < oversold, rsi > overbought
+    unsigned cand, defi;  // price exit candidate / definite (valid while price_valid)
+    bool price_valid;
+};
+
+__device__ __forceinline__ void price_hits(const Machine& m, float p, WindowHits& h) {
+    h.cand = __ballot_sync(FULL, (p <= m.plo) | (p >= m.phi));
+    h.defi = __ballot_sync(FULL, (p <= m.plo_d) | (p >= m.phi_d));
+    h.price_valid = true;
+}
+
+__device__ __forceinline__ void push_event(WarpShared* ws, Machine& m, int lane, unsigned word, float pk) {
+    if (lane == 0) ws->evq[m.qhead & (SW_EVQ - 1)] = make_uint2(word, __float_as_uint(pk));
+    ++m.qhead;
 }
 
 // Advance the machine through every event of one 32-bar window (lane l holds bar t0+l).
-__device__ __forceinline__ void scan_window(const float p, const float r, const int t0, const int lane,
-                                            WarpShared* __restrict__ ws, Machine& m) {
+// Flat-state hits are the precomputed RSI masks, so an exit is followed by the next entry without
+// any new compare; only an entry (new price bounds) costs a compare + ballot round.
+__device__ __forceinline__ void scan_window(const float p, const int t0, const int lane, WindowHits& h,
+                                            WarpShared* __restrict__ ws, const ScanConst& c, Machine& m) {
     unsigned live = FULL;  // bars of the window not yet consumed
     while (true) {
-        const unsigned hit = __ballot_sync(FULL, fires(m, p, r)) & live;
-        if (hit == 0) break;
-        const int kk = __ffs(hit) - 1;
-        const float pk = __shfl_sync(FULL, p, kk);
-        const float rk = __shfl_sync(FULL, r, kk);
-        live = (kk == 31) ? 0u : (FULL << (kk + 1));
-        const ScanConst& c = ws->sc;
-        unsigned word;
         if (m.pos == 0) {
-            // entry (strategy_evaluation.py:784-813): long has priority over short
+            // entry (strategy_evaluation.py:784-813): long (rsi < oversold) has priority over short
+            const unsigned hit = (h.os | h.ob) & live;
+            if (hit == 0) break;
+            const int kk = __ffs(hit) - 1;
+            live = (kk == 31) ? 0u : (FULL << (kk + 1));
+            const float pk = __shfl_sync(FULL, p, kk);
             m.e = pk;
-            if (rk < c.os_f) {
+            unsigned word;
+            if ((h.os >> kk) & 1u) {
                 m.pos = 1;
-                m.rlo = -INFINITY; m.rhi = c.ob_f;
                 m.phi = pk * c.hiL_c; m.plo = pk * c.loL_c;
+                m.phi_d = pk * c.hiL_d; m.plo_d = pk * c.loL_d;
                 word = (unsigned)(t0 + kk);
             } else {
                 m.pos = -1;
-                m.rlo = c.os_f; m.rhi = INFINITY;
                 m.phi = pk * c.hiS_c; m.plo = pk * c.loS_c;
+                m.phi_d = pk * c.hiS_d; m.plo_d = pk * c.loS_d;
                 word = (unsigned)(t0 + kk) | B200BT_EVENT_SELL;
             }
+            price_hits(m, p, h);
+            push_event(ws, m, lane, word, pk);
         } else {
-            // exit candidate (:815-847)
-            const float phi_d = m.e * (m.pos > 0 ? c.hiL_d : c.hiS_d);
-            const float plo_d = m.e * (m.pos > 0 ? c.loL_d : c.loS_d);
-            const bool definite = (rk < m.rlo) || (rk > m.rhi) || (pk >= phi_d) || (pk <= plo_d);
-            if (!definite) {
+            // exit (:815-847): take-profit / stop-loss on price, or RSI reversal
+            if (!h.price_valid) price_hits(m, p, h);
+            const unsigned rsi_exit = m.pos > 0 ? h.ob : h.os;
+            const unsigned hit = (h.cand | rsi_exit) & live;
+            if (hit == 0) break;
+            const int kk = __ffs(hit) - 1;
+            live = (kk == 31) ? 0u : (FULL << (kk + 1));
+            const float pk = __shfl_sync(FULL, p, kk);
+            if ((((h.defi | rsi_exit) >> kk) & 1u) == 0) {
                 // inside the fp32 screening band: decide with the reference's float64 expression
                 const double ed = (double)m.e, pd = (double)pk;
                 const double q = (m.pos > 0) ? __ddiv_rn(__dsub_rn(pd, ed), ed) : __ddiv_rn(__dsub_rn(ed, pd), ed);
                 if (!(q >= ws->acc.tp || q <= -ws->acc.sl)) continue;
             }
-            word = (unsigned)(t0 + kk) | B200BT_EVENT_EXIT | (m.pos > 0 ? B200BT_EVENT_SELL : 0u);
+            push_event(ws, m, lane, (unsigned)(t0 + kk) | B200BT_EVENT_EXIT | (m.pos > 0 ? B200BT_EVENT_SELL : 0u), pk);
             m.pos = 0;
-            m.rlo = c.os_f; m.rhi = c.ob_f;
-            m.plo = -INFINITY; m.phi = INFINITY;
         }
-        if (lane == 0) ws->evq[m.qhead & (SW_EVQ - 1)] = make_uint2(word, __float_as_uint(pk));
-        ++m.qhead;
     }
 }
 
+template <bool VEC16>
 __global__ void __launch_bounds__(SW_WARPS * 32, SW_MIN_BLOCKS)
 sweep_kernel(const float* __restrict__ price, int64_t ld_price,
              const float* __restrict__ rsi, int64_t ld_rsi, int P, int S, int64_t N,
@@ -339,66 +363,87 @@ sweep_kernel(const float* __restrict__ price, int64_t ld_price,
 
     Machine m;
     m.pos = 0; m.e = 0.f;
-    m.rlo = iv.rsi_lo; m.rhi = iv.rsi_hi; m.plo = -INFINITY; m.phi = INFINITY;
+    m.plo = m.plo_d = -INFINITY; m.phi = m.phi_d = INFINITY;
     m.qhead = 0;
+    const ScanConst c = ws->sc;                // warp-uniform constants of the scan, kept in registers
     unsigned qtail = 0;
 
     // Streams are staged through a per-warp shared-memory ring filled with cp.async
     // (16 B per thread = 128 bars per instruction when the rows are 16-byte aligned):
     // SW_STAGES-1 groups are always in flight, no registers are tied up by prefetch.
     constexpr int G = SW_GROUP;               // bars per group
-    float* sp = &ws->ring[0][0][0];
+    float* const sp = &ws->ring[0][0][0];
     const int n = (int)N;
     const int n_full = n / G;                 // groups copied without bounds checks
     const int n_groups = (n + G - 1) / G;
-    const bool vec16 = ((((uintptr_t)pr) | ((uintptr_t)rr)) & 15) == 0;
-    auto issue = [&](int g) {
-        float* dst = sp + (g % SW_STAGES) * (2 * G);
-        if (g < n_full) {
-            const float* gp = pr + (int64_t)g * G;
-            const float* gr = rr + (int64_t)g * G;
-            if (vec16) {
+    // running producer state: next group to issue, its ring slot, its source pointers
+    int issued = 0;
+    float* idst = sp + (VEC16 ? lane * 4 : lane);
+    const float* ip = pr + (VEC16 ? lane * 4 : lane);
+    const float* ir = rr + (VEC16 ? lane * 4 : lane);
+    auto issue = [&]() {
+        if (issued < n_full) {
+            if (VEC16) {
 #pragma unroll
                 for (int i = 0; i < G / 128; ++i) {
-                    cp_async16(dst + i * 128 + lane * 4, gp + i * 128 + lane * 4);
-                    cp_async16(dst + G + i * 128 + lane * 4, gr + i * 128 + lane * 4);
+                    cp_async16(idst + i * 128, ip + i * 128);
+                    cp_async16(idst + G + i * 128, ir + i * 128);
                 }
             } else {
 #pragma unroll
                 for (int i = 0; i < G / 32; ++i) {
-                    cp_async4(dst + i * 32 + lane, gp + i * 32 + lane);
-                    cp_async4(dst + G + i * 32 + lane, gr + i * 32 + lane);
+                    cp_async4(idst + i * 32, ip + i * 32);
+                    cp_async4(idst + G + i * 32, ir + i * 32);
                 }
             }
-        } else if (g < n_groups) {
+        } else if (issued < n_groups) {
             // ragged last group: guarded loads, NaN beyond the series (NaN never fires an event)
             const float qnan = __int_as_float(0x7fc00000);
+            float* dst = sp + (issued % SW_STAGES) * (2 * G);
             for (int i = lane; i < G; i += 32) {
-                const int t = g * G + i;
+                const int t = issued * G + i;
                 dst[i] = t < n ? __ldg(pr + t) : qnan;
                 dst[G + i] = t < n ? __ldg(rr + t) : qnan;
             }
         }
         cp_async_commit();  // always commit (possibly empty) so the group accounting stays uniform
+        ++issued;
+        ip += G; ir += G;
+        idst = (issued % SW_STAGES == 0) ? idst - (SW_STAGES - 1) * (2 * G) : idst + 2 * G;
     };
 #pragma unroll
-    for (int g = 0; g < SW_STAGES - 1; ++g) issue(g);
+    for (int g = 0; g < SW_STAGES - 1; ++g) issue();
+    const float* cur = sp + lane;
+    int cstage = 0;
     for (int g = 0; g < n_groups; ++g) {
-        issue(g + SW_STAGES - 1);
+        issue();
         cp_async_wait<SW_STAGES - 1>();       // group g has landed
         __syncwarp();
-        const float* cur = sp + (g % SW_STAGES) * (2 * G) + lane;
+        const float* w = cur;
+        int t0 = g * G;
 #pragma unroll 1
-        for (int v = 0; v < G / 32; v += 2) {
-            // two windows per step: both ballots are issued before either is needed
-            const float p0 = cur[v * 32], r0 = cur[G + v * 32];
-            const float p1 = cur[v * 32 + 32], r1 = cur[G + v * 32 + 32];
-            const unsigned h0 = __ballot_sync(FULL, fires(m, p0, r0));
-            const unsigned h1 = __ballot_sync(FULL, fires(m, p1, r1));
-            if (h0 | h1) {
-                const int t0 = g * G + v * 32;
-                if (h0) scan_window(p0, r0, t0, lane, ws, m);
-                scan_window(p1, r1, t0 + 32, lane, ws, m);
+        for (int v = 0; v < G / 64; ++v, w += 64, t0 += 64) {
+            // two windows per step: all state-independent ballots are issued before any is needed
+            const float p0 = w[0], r0 = w[G];
+            const float p1 = w[32], r1 = w[G + 32];
+            WindowHits h0, h1;
+            h0.os = __ballot_sync(FULL, r0 < c.os_f); h0.ob = __ballot_sync(FULL, r0 > c.ob_f);
+            h1.os = __ballot_sync(FULL, r1 < c.os_f); h1.ob = __ballot_sync(FULL, r1 > c.ob_f);
+            h0.price_valid = h1.price_valid = false;
+            unsigned any;
+            if (m.pos == 0) {
+                any = h0.os | h0.ob | h1.os | h1.ob;
+            } else {
+                price_hits(m, p0, h0);
+                price_hits(m, p1, h1);
+                const unsigned x0 = m.pos > 0 ? h0.ob : h0.os, x1 = m.pos > 0 ? h1.ob : h1.os;
+                any = h0.cand | x0 | h1.cand | x1;
+            }
+            if (any) {
+                const unsigned before = m.qhead;
+                scan_window(p0, t0, lane, h0, ws, c, m);
+                if (m.qhead != before) h1.price_valid = false;   // price bounds changed in window 0
+                scan_window(p1, t0 + 32, lane, h1, ws, c, m);
                 while (m.qhead - qtail >= 32) {
                     __syncwarp();
                     process_batch(ws, qtail, 32, minute0, bar_minutes, ev_cap);
@@ -407,14 +452,14 @@ sweep_kernel(const float* __restrict__ price, int64_t ld_price,
             }
         }
         __syncwarp();                         // stage is refilled by the next iteration's issue
+        if (++cstage == SW_STAGES) { cstage = 0; cur -= (SW_STAGES - 1) * (2 * G); } else cur += 2 * G;
     }
     cp_async_wait<0>();
     if (m.pos != 0) {
         // force-close at the last bar (:849-876)
         const float pl = __ldg(pr + (N - 1));
         const unsigned word = (unsigned)(N - 1) | B200BT_EVENT_EXIT | (m.pos > 0 ? B200BT_EVENT_SELL : 0u);
-        if (lane == 0) ws->evq[m.qhead & (SW_EVQ - 1)] = make_uint2(word, __float_as_uint(pl));
-        ++m.qhead;
+        push_event(ws, m, lane, word, pl);
     }
     __syncwarp();
     while (m.qhead != qtail) {
@@ -503,13 +548,12 @@ extern "C" int b200bt_sweep(const float* price, int64_t ld_price, const float* r
     const int64_t blocks = (int64_t)((pop + SW_WARPS - 1) / SW_WARPS) * S;
     B200BT_REQUIRE(blocks < (1ll << 31), B200BT_ELIMIT, "sweep: too many lanes");
     const size_t smem = sizeof(WarpShared) * SW_WARPS;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_status(e, "sweep: cudaFuncSetAttribute");
-        attr_set = true;
-    }
-    sweep_kernel<<<(unsigned)blocks, SW_WARPS * 32, smem, (cudaStream_t)stream>>>(
+    // 16-byte cp.async needs every (symbol, period) row to start on a 16-byte boundary
+    const bool vec16 = (((uintptr_t)price | (uintptr_t)rsi) & 15) == 0 && ld_price % 4 == 0 && ld_rsi % 4 == 0;
+    auto kern = vec16 ? sweep_kernel<true> : sweep_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "sweep: cudaFuncSetAttribute");
+    kern<<<(unsigned)blocks, SW_WARPS * 32, smem, (cudaStream_t)stream>>>(
         price, ld_price, rsi, ld_rsi, P, S, N, indiv, order, pop, *cfg_host, stats, events, event_cap);
     B200BT_LAUNCH_CHECK("sweep launch");
     return B200BT_OK;
