@@ -69,4 +69,16 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
+// Trade-hash contribution of one event (event index, event word): two 32-bit multiply-xorshift
+// mixes; the lane hash is the xor over all events (oracle/sim_oracle.c computes the same).
+__host__ __device__ __forceinline__ uint64_t event_hash(uint32_t index, uint32_t word) {
+    uint32_t a = (index * 0x9E3779B1u) ^ word;
+    a *= 0x85EBCA77u;
+    a ^= a >> 15;
+    uint32_t b = (word * 0xC2B2AE3Du) ^ ((index << 13) | (index >> 19));
+    b *= 0x27D4EB2Fu;
+    b ^= b >> 16;
+    return ((uint64_t)b << 32) | a;
+}
+
 }  // namespace b200bt

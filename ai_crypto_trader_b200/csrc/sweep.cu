@@ -121,8 +121,6 @@ __device__ __noinline__ void process_batch(WarpShared* __restrict__ ws, unsigned
     const bool win = active && pnl > 0.0, loss = active && pnl < 0.0;
     const unsigned n_win = acc->n_win + __popc(__ballot_sync(FULL, win));
     const unsigned n_loss = acc->n_loss + __popc(__ballot_sync(FULL, loss));
-    const double tot_profit = acc->tot_profit + warp_sum_d(win ? pnl : 0.0);
-    const double tot_loss = acc->tot_loss + warp_sum_d(loss ? pnl : 0.0);
     double largest_p = acc->largest_p, largest_l = acc->largest_l;
     if (__any_sync(FULL, pnl > largest_p)) largest_p = fmax(largest_p, warp_max_d(win ? pnl : 0.0));   // rare after warm-up
     if (__any_sync(FULL, pnl < largest_l)) largest_l = fmin(largest_l, warp_min_d(loss ? pnl : 0.0));
@@ -135,14 +133,22 @@ __device__ __noinline__ void process_batch(WarpShared* __restrict__ ws, unsigned
         double up = shfl_up_d(cs, d);
         if (lane >= d) cs += up;
     }
+    // gains by one butterfly; losses = batch total - gains (the total comes free from the scan)
+    const double gains = warp_sum_d(win ? pnl : 0.0);
+    const double tot_profit = acc->tot_profit + gains;
+    const double tot_loss = __any_sync(FULL, loss) ? acc->tot_loss + (__shfl_sync(FULL, cs, 31) - gains) : acc->tot_loss;
     const double eq = acc->equity + cs;
-    double pk = active ? eq : -INFINITY;
+    const double peak_in = acc->peak;
+    double pk = peak_in;
+    if (__any_sync(FULL, active && eq > peak_in)) {   // a new equity peak inside the batch (uncommon for most lanes)
+        pk = active ? eq : -INFINITY;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        double up = shfl_up_d(pk, d);
-        if (lane >= d) pk = fmax(pk, up);
+        for (int d = 1; d < 32; d <<= 1) {
+            double up = shfl_up_d(pk, d);
+            if (lane >= d) pk = fmax(pk, up);
+        }
+        pk = fmax(pk, peak_in);
     }
-    pk = fmax(pk, acc->peak);
     double maxdd = acc->maxdd;
     {
         // dd_j = (pk-eq)/pk; a new maximum needs (pk-eq) > maxdd*pk (screen with a safety factor, then divide)
@@ -155,19 +161,20 @@ __device__ __noinline__ void process_batch(WarpShared* __restrict__ ws, unsigned
     const double peak_out = shfl_d(pk, cnt - 1);
 
     // daily buckets: segmented sum by calendar day over the batch, merged with the carry day
-    const long long day = active ? (minute0 + (long long)bar * bar_minutes) / 1440 : 0;
+    // calendar day of a record, relative to bar 0's day (32-bit: the host checks N*bar_minutes < 2^31 - 1440)
+    const int day = active ? (int)(((unsigned)minute0 + bar * (unsigned)bar_minutes) / 1440u) : 0;
     DayAcc da{acc->pivot, acc->s1, acc->s2, acc->n_days, acc->pivot_set};
     const int day_valid = acc->day_valid;
-    const long long day_cur = acc->day_cur;
+    const int day_cur = (int)acc->day_cur;
     double day_sum = acc->day_sum;
-    const long long first_day = __shfl_sync(FULL, day, 0);
-    const long long last_day = __shfl_sync(FULL, day, cnt - 1);
+    const int first_day = __shfl_sync(FULL, day, 0);
+    const int last_day = __shfl_sync(FULL, day, cnt - 1);
     if (first_day == last_day && (!day_valid || first_day == day_cur)) {
         // common case: the whole batch falls into the open day
         day_sum = (day_valid ? day_sum : 0.0) + batch_sum;
     } else {
-        const long long day_prev = __shfl_up_sync(FULL, day, 1);
-        const long long day_next = __shfl_down_sync(FULL, day, 1);
+        const int day_prev = __shfl_up_sync(FULL, day, 1);
+        const int day_next = __shfl_down_sync(FULL, day, 1);
         const bool head = active && (lane == 0 || day != day_prev);
         const bool tail = active && (lane == cnt - 1 || day != day_next);
         double seg = pnl;
@@ -198,7 +205,7 @@ __device__ __noinline__ void process_batch(WarpShared* __restrict__ ws, unsigned
 
     // trade hash + optional event buffer
     const unsigned n_events = acc->n_events;
-    const unsigned long long h = active ? mix64(((unsigned long long)(n_events + lane) << 32) | w) : 0ull;
+    const unsigned long long h = active ? event_hash(n_events + lane, w) : 0ull;
     const unsigned hlo = __reduce_xor_sync(FULL, (unsigned)h);
     const unsigned hhi = __reduce_xor_sync(FULL, (unsigned)(h >> 32));
     uint32_t* ev_out = acc->ev_out;
@@ -235,77 +242,59 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 struct Machine {
     int pos;                                   // 0 flat, +1 long, -1 short
     float e;                                   // entry price
-    float plo, phi;                            // price bounds of the open position: exit CANDIDATE when crossed
-    float plo_d, phi_d;                        // ... DEFINITE exit when crossed (fp32 screening band in between)
+    float rlo, rhi, plo, phi;                  // event thresholds of the current state (screening bounds)
+    float plo_d, phi_d;                        // "definite exit" price bounds of the open position
     unsigned qhead;                            // events pushed so far (queue head)
 };
 
-// Per-window hit masks (bit l = bar t0+l).  `os`/`ob` depend only on the lane's RSI thresholds,
-// never on the machine state; `cand`/`defi` depend on the open position's price bounds.
-struct WindowHits {
-    unsigned os, ob;      // rsi < oversold, rsi > overbought
-    unsigned cand, defi;  // price exit candidate / definite (valid while price_valid)
-    bool price_valid;
-};
-
-__device__ __forceinline__ void price_hits(const Machine& m, float p, WindowHits& h) {
-    h.cand = __ballot_sync(FULL, (p <= m.plo) | (p >= m.phi));
-    h.defi = __ballot_sync(FULL, (p <= m.plo_d) | (p >= m.phi_d));
-    h.price_valid = true;
-}
-
-__device__ __forceinline__ void push_event(WarpShared* ws, Machine& m, int lane, unsigned word, float pk) {
-    if (lane == 0) ws->evq[m.qhead & (SW_EVQ - 1)] = make_uint2(word, __float_as_uint(pk));
-    ++m.qhead;
+__device__ __forceinline__ bool fires(const Machine& m, float p, float r) {
+    return (r < m.rlo) | (r > m.rhi) | (p <= m.plo) | (p >= m.phi);
 }
 
 // Advance the machine through every event of one 32-bar window (lane l holds bar t0+l).
-// Flat-state hits are the precomputed RSI masks, so an exit is followed by the next entry without
-// any new compare; only an entry (new price bounds) costs a compare + ballot round.
-__device__ __forceinline__ void scan_window(const float p, const int t0, const int lane, WindowHits& h,
+__device__ __forceinline__ void scan_window(const float p, const float r, const int t0, const int lane,
                                             WarpShared* __restrict__ ws, const ScanConst& c, Machine& m) {
     unsigned live = FULL;  // bars of the window not yet consumed
     while (true) {
+        const unsigned hit = __ballot_sync(FULL, fires(m, p, r)) & live;
+        if (hit == 0) break;
+        const int kk = __ffs(hit) - 1;
+        const float pk = __shfl_sync(FULL, p, kk);
+        const float rk = __shfl_sync(FULL, r, kk);
+        live = (kk == 31) ? 0u : (FULL << (kk + 1));
+        unsigned word;
         if (m.pos == 0) {
-            // entry (strategy_evaluation.py:784-813): long (rsi < oversold) has priority over short
-            const unsigned hit = (h.os | h.ob) & live;
-            if (hit == 0) break;
-            const int kk = __ffs(hit) - 1;
-            live = (kk == 31) ? 0u : (FULL << (kk + 1));
-            const float pk = __shfl_sync(FULL, p, kk);
+            // entry (strategy_evaluation.py:784-813): long has priority over short
             m.e = pk;
-            unsigned word;
-            if ((h.os >> kk) & 1u) {
+            if (rk < c.os_f) {
                 m.pos = 1;
+                m.rlo = -INFINITY; m.rhi = c.ob_f;
                 m.phi = pk * c.hiL_c; m.plo = pk * c.loL_c;
                 m.phi_d = pk * c.hiL_d; m.plo_d = pk * c.loL_d;
                 word = (unsigned)(t0 + kk);
             } else {
                 m.pos = -1;
+                m.rlo = c.os_f; m.rhi = INFINITY;
                 m.phi = pk * c.hiS_c; m.plo = pk * c.loS_c;
                 m.phi_d = pk * c.hiS_d; m.plo_d = pk * c.loS_d;
                 word = (unsigned)(t0 + kk) | B200BT_EVENT_SELL;
             }
-            price_hits(m, p, h);
-            push_event(ws, m, lane, word, pk);
         } else {
-            // exit (:815-847): take-profit / stop-loss on price, or RSI reversal
-            if (!h.price_valid) price_hits(m, p, h);
-            const unsigned rsi_exit = m.pos > 0 ? h.ob : h.os;
-            const unsigned hit = (h.cand | rsi_exit) & live;
-            if (hit == 0) break;
-            const int kk = __ffs(hit) - 1;
-            live = (kk == 31) ? 0u : (FULL << (kk + 1));
-            const float pk = __shfl_sync(FULL, p, kk);
-            if ((((h.defi | rsi_exit) >> kk) & 1u) == 0) {
+            // exit candidate (:815-847)
+            const bool definite = (rk < m.rlo) || (rk > m.rhi) || (pk >= m.phi_d) || (pk <= m.plo_d);
+            if (!definite) {
                 // inside the fp32 screening band: decide with the reference's float64 expression
                 const double ed = (double)m.e, pd = (double)pk;
                 const double q = (m.pos > 0) ? __ddiv_rn(__dsub_rn(pd, ed), ed) : __ddiv_rn(__dsub_rn(ed, pd), ed);
                 if (!(q >= ws->acc.tp || q <= -ws->acc.sl)) continue;
             }
-            push_event(ws, m, lane, (unsigned)(t0 + kk) | B200BT_EVENT_EXIT | (m.pos > 0 ? B200BT_EVENT_SELL : 0u), pk);
+            word = (unsigned)(t0 + kk) | B200BT_EVENT_EXIT | (m.pos > 0 ? B200BT_EVENT_SELL : 0u);
             m.pos = 0;
+            m.rlo = c.os_f; m.rhi = c.ob_f;
+            m.plo = -INFINITY; m.phi = INFINITY;
         }
+        if (lane == 0) ws->evq[m.qhead & (SW_EVQ - 1)] = make_uint2(word, __float_as_uint(pk));
+        ++m.qhead;
     }
 }
 
@@ -363,7 +352,7 @@ sweep_kernel(const float* __restrict__ price, int64_t ld_price,
 
     Machine m;
     m.pos = 0; m.e = 0.f;
-    m.plo = m.plo_d = -INFINITY; m.phi = m.phi_d = INFINITY;
+    m.rlo = iv.rsi_lo; m.rhi = iv.rsi_hi; m.plo = m.plo_d = -INFINITY; m.phi = m.phi_d = INFINITY;
     m.qhead = 0;
     const ScanConst c = ws->sc;                // warp-uniform constants of the scan, kept in registers
     unsigned qtail = 0;
@@ -423,27 +412,14 @@ sweep_kernel(const float* __restrict__ price, int64_t ld_price,
         int t0 = g * G;
 #pragma unroll 1
         for (int v = 0; v < G / 64; ++v, w += 64, t0 += 64) {
-            // two windows per step: all state-independent ballots are issued before any is needed
+            // two windows per step: both ballots are issued before either is needed
             const float p0 = w[0], r0 = w[G];
             const float p1 = w[32], r1 = w[G + 32];
-            WindowHits h0, h1;
-            h0.os = __ballot_sync(FULL, r0 < c.os_f); h0.ob = __ballot_sync(FULL, r0 > c.ob_f);
-            h1.os = __ballot_sync(FULL, r1 < c.os_f); h1.ob = __ballot_sync(FULL, r1 > c.ob_f);
-            h0.price_valid = h1.price_valid = false;
-            unsigned any;
-            if (m.pos == 0) {
-                any = h0.os | h0.ob | h1.os | h1.ob;
-            } else {
-                price_hits(m, p0, h0);
-                price_hits(m, p1, h1);
-                const unsigned x0 = m.pos > 0 ? h0.ob : h0.os, x1 = m.pos > 0 ? h1.ob : h1.os;
-                any = h0.cand | x0 | h1.cand | x1;
-            }
-            if (any) {
-                const unsigned before = m.qhead;
-                scan_window(p0, t0, lane, h0, ws, c, m);
-                if (m.qhead != before) h1.price_valid = false;   // price bounds changed in window 0
-                scan_window(p1, t0 + 32, lane, h1, ws, c, m);
+            const unsigned h0 = __ballot_sync(FULL, fires(m, p0, r0));
+            const unsigned h1 = __ballot_sync(FULL, fires(m, p1, r1));
+            if (h0 | h1) {
+                if (h0) scan_window(p0, r0, t0, lane, ws, c, m);
+                scan_window(p1, r1, t0 + 32, lane, ws, c, m);
                 while (m.qhead - qtail >= 32) {
                     __syncwarp();
                     process_batch(ws, qtail, 32, minute0, bar_minutes, ev_cap);
@@ -459,7 +435,8 @@ sweep_kernel(const float* __restrict__ price, int64_t ld_price,
         // force-close at the last bar (:849-876)
         const float pl = __ldg(pr + (N - 1));
         const unsigned word = (unsigned)(N - 1) | B200BT_EVENT_EXIT | (m.pos > 0 ? B200BT_EVENT_SELL : 0u);
-        push_event(ws, m, lane, word, pl);
+        if (lane == 0) ws->evq[m.qhead & (SW_EVQ - 1)] = make_uint2(word, __float_as_uint(pl));
+        ++m.qhead;
     }
     __syncwarp();
     while (m.qhead != qtail) {
@@ -542,6 +519,8 @@ extern "C" int b200bt_sweep(const float* price, int64_t ld_price, const float* r
     B200BT_REQUIRE(ld_price >= N && ld_rsi >= N, B200BT_EINVAL, "sweep: row stride shorter than N");
     B200BT_REQUIRE(N < (1ll << 30), B200BT_ELIMIT, "sweep: N must be < 2^30 bars");
     B200BT_REQUIRE(cfg_host->bar_minutes > 0, B200BT_EINVAL, "sweep: bar_minutes must be > 0");
+    B200BT_REQUIRE(cfg_host->minute0 >= 0 && cfg_host->minute0 + N * (int64_t)cfg_host->bar_minutes < (1ll << 32) - 1440,
+                   B200BT_ELIMIT, "sweep: minute0 + N*bar_minutes must stay below 2^32 minutes");
     B200BT_REQUIRE(events == nullptr || event_cap > 0, B200BT_EINVAL, "sweep: event buffer without capacity");
     int rc = check_device();
     if (rc) return rc;

@@ -47,11 +47,15 @@ typedef struct {
 #define EV_EXIT 0x40000000u
 #define EV_SELL 0x80000000u
 
-static uint64_t mix64(uint64_t x) {
-    x += 0x9E3779B97F4A7C15ull;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
+/* same mixer as csrc/common.cuh event_hash */
+static uint64_t event_hash(uint32_t index, uint32_t word) {
+    uint32_t a = (index * 0x9E3779B1u) ^ word;
+    a *= 0x85EBCA77u;
+    a ^= a >> 15;
+    uint32_t b = (word * 0xC2B2AE3Du) ^ ((index << 13) | (index >> 19));
+    b *= 0x27D4EB2Fu;
+    b ^= b >> 16;
+    return ((uint64_t)b << 32) | a;
 }
 
 typedef struct {
@@ -87,7 +91,7 @@ static void record(acc_t* a, int64_t bar, uint32_t flags, double pnl) {
         a->ev[a->n_rec] = w;
         if (a->ev_pnl) a->ev_pnl[a->n_rec] = pnl;
     }
-    a->hash ^= mix64(((uint64_t)a->n_rec << 32) | w);
+    a->hash ^= event_hash((uint32_t)a->n_rec, w);
     a->n_rec++;
     if (pnl > 0) {
         a->n_win++;
