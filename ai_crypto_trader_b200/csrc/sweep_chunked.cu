@@ -1,0 +1,396 @@
+// Family 2, time-parallel form: the population sweep with every expensive lane split into
+// TIME CHUNKS that are scanned concurrently (sm_100a).
+//
+// The trade state machine (strategy_evaluation.py:746-878) is serial in time, and the lanes of a
+// GA population differ by two to three orders of magnitude in trade count, so at moderate
+// population sizes the fused kernel (sweep.cu) is bounded by the serial event chain of its few
+// heaviest lanes.  The machine, however, forgets: whenever it is flat, its future does not depend
+// on its past.  A chunk [T_c, T_{c+1}) is therefore scanned by its own warp, which starts `warm`
+// bars early in the flat state without recording, and records from T_c on.  Two trajectories that
+// are ever flat at the same bar coincide from then on, so after the warm-up the chunk's assumed
+// state (position side + entry bar) is almost always the true one.  It is VERIFIED, not trusted:
+//   scan kernel     one warp per (individual, symbol, chunk): events -> blocks of a global pool
+//                   (bump allocator, singly linked per chunk), assumed state at T_c and end state.
+//   metrics kernel  one warp per (individual, symbol): checks end state of chunk c-1 == assumed
+//                   state of chunk c for every boundary, then folds the chunks' events in time
+//                   order through the same float64 batch arithmetic as the fused kernel.
+// A lane with any mismatching boundary is flagged; the host re-evaluates flagged lanes with the
+// fused (serial) kernel, so results never depend on the speculation being right.
+#include "sweep_dev.cuh"
+
+namespace b200bt {
+
+constexpr int CK_BLOCK = 256;   // events per pool block
+
+struct ChunkScanArgs {
+    const float* price; int64_t ld_price;
+    const float* rsi; int64_t ld_rsi;
+    int P, S; int64_t N;
+    const b200bt_individual* indiv;
+    const b200bt_chunk_item* items; int n_items; int n_seg;   // n_seg = segments per symbol
+    int warm;
+    uint2* pool; int pool_blocks; int* next; unsigned* alloc;
+    int* seg_first; unsigned* seg_count; int2* seg_in; int2* seg_out; int* overflow;
+    const int4* repair;   // REPAIR launches: (individual, chunk, segment, symbol) per work item
+    const int32_t* n_chunks;
+};
+
+__device__ __forceinline__ int64_t chunk_begin(int64_t N, int c, int K) {
+    if (c >= K) return N;
+    return ((N * c) / K) & ~(int64_t)(SW_GROUP - 1);   // group aligned
+}
+
+// REPAIR = false: speculative pass over every (work item, symbol), warm-up from the flat state.
+// REPAIR = true : re-scan of chunks whose assumed state was wrong, started AT T_c from the now known
+//                 true state (end state of the preceding chunk); one work item per listed chunk.
+template <bool VEC16, bool REPAIR>
+__global__ void __launch_bounds__(SW_WARPS * 32, 3)
+chunk_scan_kernel(const ChunkScanArgs A) {   // by value, not __grid_constant__ (see sweep.cu)
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int lane = threadIdx.x & 31;
+    int sym, it;
+    b200bt_chunk_item item;
+    if (REPAIR) {
+        it = (int)blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
+        if (it >= A.n_items) return;
+        const int4 r = A.repair[it];
+        item.individual = r.x; item.chunk = r.y; item.segment = r.z; item.n_chunks = A.n_chunks[r.x];
+        sym = r.w;
+    } else {
+        sym = (int)(blockIdx.x % (unsigned)A.S);
+        it = (int)(blockIdx.x / (unsigned)A.S) * SW_WARPS + (threadIdx.x >> 5);
+        if (it >= A.n_items) return;
+        item = A.items[it];
+    }
+    const b200bt_individual iv = A.indiv[item.individual];
+    WarpShared* ws = reinterpret_cast<WarpShared*>(s_raw) + (threadIdx.x >> 5);
+    if (lane == 0) {
+        ScanConst sc0;
+        init_scan_const(sc0, iv);
+        ws->sc = sc0;
+        ws->acc.tp = iv.take_profit;   // only the screening-band decision reads these here
+        ws->acc.sl = iv.stop_loss;
+    }
+    __syncwarp();
+    const ScanConst c = ws->sc;
+    const float* __restrict__ pr = A.price + (int64_t)sym * A.ld_price;
+    const float* __restrict__ rr = A.rsi + ((int64_t)sym * A.P + iv.rsi_row) * A.ld_rsi;
+
+    const int n = (int)A.N;
+    const int T0 = (int)chunk_begin(A.N, item.chunk, item.n_chunks);       // first recorded bar
+    const int T1 = (int)chunk_begin(A.N, item.chunk + 1, item.n_chunks);   // end (exclusive)
+    int s0 = REPAIR ? T0 : T0 - A.warm;
+    if (s0 < 0 || item.chunk == 0) s0 = 0;
+    s0 &= ~(SW_GROUP - 1);
+    const int seg = sym * A.n_seg + item.segment;
+
+    Machine m;
+    m.pos = 0; m.e = 0.f; m.entry_bar = 0;
+    m.rlo = iv.rsi_lo; m.rhi = iv.rsi_hi; m.plo = m.plo_d = -INFINITY; m.phi = m.phi_d = INFINITY;
+    m.qhead = 0;
+    unsigned qtail = 0;
+    if (REPAIR) {
+        // true state at T0 = end state of the preceding chunk (position side, entry bar -> entry price)
+        const int2 z = A.seg_out[seg - 1];
+        if (z.x != 0) {
+            const float e = __ldg(pr + z.y);
+            m.pos = z.x; m.e = e; m.entry_bar = z.y;
+            if (z.x > 0) {
+                m.rlo = -INFINITY; m.rhi = c.ob_f;
+                m.phi = e * c.hiL_c; m.plo = e * c.loL_c; m.phi_d = e * c.hiL_d; m.plo_d = e * c.loL_d;
+            } else {
+                m.rlo = c.os_f; m.rhi = INFINITY;
+                m.phi = e * c.hiS_c; m.plo = e * c.loS_c; m.phi_d = e * c.hiS_d; m.plo_d = e * c.loS_d;
+            }
+        }
+    }
+
+    // event sink: 32 queued events -> one coalesced 256-byte store into the chunk's current pool block
+    int cur_block = -1, fill = CK_BLOCK, dead = 0;
+    auto flush = [&](int cnt) {
+        if (fill == CK_BLOCK && !dead) {
+            int b = 0;
+            if (lane == 0) {
+                b = (int)atomicAdd(A.alloc, 1u);
+                if (b >= A.pool_blocks) { atomicExch(A.overflow, 1); b = -1; }
+                else {
+                    A.next[b] = -1;
+                    if (cur_block < 0) A.seg_first[seg] = b; else A.next[cur_block] = b;
+                }
+            }
+            b = __shfl_sync(FULL, b, 0);
+            if (b < 0) dead = 1; else { cur_block = b; fill = 0; }
+        }
+        if (!dead) {
+            if (lane < cnt) A.pool[(int64_t)cur_block * CK_BLOCK + fill + lane] = ws->evq[(qtail + lane) & (SW_EVQ - 1)];
+            fill += 32;   // only the last flush of a chunk is partial
+        }
+        qtail += cnt;
+    };
+
+    constexpr int G = SW_GROUP;
+    float* const sp = &ws->ring[0][0][0];
+    const int n_full = n / G;
+    const int g_begin = s0 / G, g_end = (T1 + G - 1) / G;
+    int issued = g_begin;
+    float* idst = sp + (g_begin % SW_STAGES) * (2 * G) + (VEC16 ? lane * 4 : lane);
+    const float* ip = pr + (int64_t)g_begin * G + (VEC16 ? lane * 4 : lane);
+    const float* ir = rr + (int64_t)g_begin * G + (VEC16 ? lane * 4 : lane);
+    auto issue = [&]() {
+        if (issued < n_full && issued < g_end) {
+            if (VEC16) {
+#pragma unroll
+                for (int i = 0; i < G / 128; ++i) {
+                    cp_async16(idst + i * 128, ip + i * 128);
+                    cp_async16(idst + G + i * 128, ir + i * 128);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < G / 32; ++i) {
+                    cp_async4(idst + i * 32, ip + i * 32);
+                    cp_async4(idst + G + i * 32, ir + i * 32);
+                }
+            }
+        } else if (issued < g_end) {
+            const float qnan = __int_as_float(0x7fc00000);   // ragged last group of the series
+            float* dst = sp + (issued % SW_STAGES) * (2 * G);
+            for (int i = lane; i < G; i += 32) {
+                const int t = issued * G + i;
+                dst[i] = t < n ? __ldg(pr + t) : qnan;
+                dst[G + i] = t < n ? __ldg(rr + t) : qnan;
+            }
+        }
+        cp_async_commit();
+        ++issued;
+        ip += G; ir += G;
+        idst = (issued % SW_STAGES == 0) ? idst - (SW_STAGES - 1) * (2 * G) : idst + 2 * G;
+    };
+#pragma unroll
+    for (int g = 0; g < SW_STAGES - 1; ++g) issue();
+    int cstage = g_begin % SW_STAGES;
+    const float* cur = sp + cstage * (2 * G) + lane;
+    for (int g = g_begin; g < g_end; ++g) {
+        issue();
+        cp_async_wait<SW_STAGES - 1>();
+        __syncwarp();
+        const bool emit = g * G >= T0;
+        if (g * G == T0 && lane == 0) A.seg_in[seg] = make_int2(m.pos, m.pos != 0 ? m.entry_bar : -1);
+        const float* w = cur;
+        int t0 = g * G;
+#pragma unroll 1
+        for (int v = 0; v < G / 64; ++v, w += 64, t0 += 64) {
+            const float p0 = w[0], r0 = w[G];
+            const float p1 = w[32], r1 = w[G + 32];
+            const unsigned h0 = __ballot_sync(FULL, fires(m, p0, r0));
+            const unsigned h1 = __ballot_sync(FULL, fires(m, p1, r1));
+            if (h0 | h1) {
+                if (h0) scan_window(p0, r0, t0, lane, ws, c, m, emit);
+                scan_window(p1, r1, t0 + 32, lane, ws, c, m, emit);
+                while (m.qhead - qtail >= 32) {
+                    __syncwarp();
+                    flush(32);
+                }
+            }
+        }
+        __syncwarp();
+        if (++cstage == SW_STAGES) { cstage = 0; cur -= (SW_STAGES - 1) * (2 * G); } else cur += 2 * G;
+    }
+    cp_async_wait<0>();
+    if (lane == 0) {
+        const int2 st = make_int2(m.pos, m.pos != 0 ? m.entry_bar : -1);
+        A.seg_out[seg] = st;
+        if (T0 >= T1) A.seg_in[seg] = st;   // empty chunk: its assumed state is the state after the warm-up
+    }
+    if (item.chunk == item.n_chunks - 1 && m.pos != 0) {
+        // force-close at the last bar (:849-876)
+        const float pl = __ldg(pr + (A.N - 1));
+        const unsigned word = (unsigned)(A.N - 1) | B200BT_EVENT_EXIT | (m.pos > 0 ? B200BT_EVENT_SELL : 0u);
+        if (lane == 0) ws->evq[m.qhead & (SW_EVQ - 1)] = make_uint2(word, __float_as_uint(pl));
+        ++m.qhead;
+    }
+    __syncwarp();
+    while (m.qhead != qtail) flush((int)min(32u, m.qhead - qtail));
+    if (lane == 0) A.seg_count[seg] = dead ? 0xffffffffu : m.qhead;
+}
+
+// One thread per (individual, symbol): list every chunk whose assumed state differs from the end state
+// of its predecessor while that predecessor is itself consistent (so its end state is the truth).
+__global__ void chunk_verify_kernel(int pop, int S, const int32_t* __restrict__ seg_base,
+                                    const int32_t* __restrict__ n_chunks, int n_seg, const unsigned* __restrict__ seg_count,
+                                    const int2* __restrict__ seg_in, const int2* __restrict__ seg_out,
+                                    int4* __restrict__ repair, unsigned* __restrict__ n_repair) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)pop * S) return;
+    const int ind = (int)(t / S), sym = (int)(t % S);
+    const int K = n_chunks[ind];
+    const int base = sym * n_seg + seg_base[ind];
+    bool prev_bad = false;
+    for (int c = 1; c < K; ++c) {
+        const int2 a = seg_in[base + c], z = seg_out[base + c - 1];
+        const bool bad = (a.x != z.x) || (a.y != z.y);
+        const bool usable = seg_count[base + c - 1] != 0xffffffffu;   // predecessor did not lose events to a full pool
+        if (bad && !prev_bad && usable) repair[atomicAdd(n_repair, 1u)] = make_int4(ind, c, seg_base[ind] + c, sym);
+        prev_bad = bad;
+    }
+}
+
+// One warp per (individual, symbol): verify the chunk boundaries, then fold the chunks' events.
+__global__ void __launch_bounds__(128)
+chunk_metrics_kernel(const b200bt_individual* __restrict__ indiv, const int32_t* __restrict__ order, int pop, int S,
+                     const int32_t* __restrict__ seg_base, const int32_t* __restrict__ n_chunks, int n_seg,
+                     const uint2* __restrict__ pool, const int* __restrict__ next, const int* __restrict__ seg_first,
+                     const unsigned* __restrict__ seg_count, const int2* __restrict__ seg_in,
+                     const int2* __restrict__ seg_out, const b200bt_sweep_config cfg,
+                     b200bt_lane_stats* __restrict__ stats, uint32_t* __restrict__ events, int64_t ev_cap,
+                     unsigned char* __restrict__ invalid) {
+    __shared__ WarpAcc s_acc[4];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int sym = (int)(blockIdx.x % (unsigned)S);
+    const int k = (int)(blockIdx.x / (unsigned)S) * 4 + wid;
+    if (k >= pop) return;
+    const int ind = order ? order[k] : k;
+    const b200bt_individual iv = indiv[ind];
+    WarpAcc* acc = &s_acc[wid];
+    if (lane == 0) {
+        WarpAcc a0;
+        init_acc(a0, iv, cfg.initial_capital, events ? events + ((int64_t)ind * S + sym) * ev_cap : nullptr);
+        *acc = a0;
+    }
+    __syncwarp();
+    const int K = n_chunks[ind];
+    const int base = sym * n_seg + seg_base[ind];
+    bool ok = true;
+    for (int c = 0; c < K; ++c) {
+        const int2 a = seg_in[base + c];
+        if (c == 0) ok = ok && (a.x == 0);
+        else {
+            const int2 z = seg_out[base + c - 1];
+            ok = ok && (a.x == z.x) && (a.y == z.y);
+        }
+        ok = ok && (seg_count[base + c] != 0xffffffffu);
+    }
+    if (ok) {
+        unsigned w_carry = 0u;
+        float p_carry = 0.f;
+        for (int c = 0; c < K; ++c) {
+            unsigned left = seg_count[base + c];
+            int b = left ? seg_first[base + c] : -1;
+            int off = 0;
+            while (left) {
+                const int cnt = (int)min(32u, left);
+                const uint2 ev = lane < cnt ? pool[(int64_t)b * CK_BLOCK + off + lane] : make_uint2(0u, 0u);
+                batch_core(acc, cnt, ev.x, __uint_as_float(ev.y), w_carry, p_carry, cfg.minute0, cfg.bar_minutes, ev_cap);
+                w_carry = __shfl_sync(FULL, ev.x, cnt - 1);
+                p_carry = __shfl_sync(FULL, __uint_as_float(ev.y), cnt - 1);
+                left -= cnt;
+                off += 32;
+                if (off == CK_BLOCK && left) { b = next[b]; off = 0; }
+            }
+        }
+    }
+    if (lane == 0) {
+        invalid[(int64_t)ind * S + sym] = ok ? 0 : 1;
+        if (ok) {
+            b200bt_lane_stats o;
+            finalize_lane(*acc, cfg, o);
+            stats[(int64_t)ind * S + sym] = o;
+        }
+    }
+}
+
+}  // namespace b200bt
+
+using namespace b200bt;
+
+extern "C" int64_t b200bt_sweep_chunked_workspace_bytes(int pool_blocks, int S, int n_seg) {
+    const int64_t segs = (int64_t)S * n_seg;
+    // pool[pool_blocks][256] uint2 | seg_in[segs] int2 | seg_out[segs] int2 | seg_first[segs] | seg_count[segs] |
+    // alloc, overflow, n_repair, pad | repair[segs] int4 | next[pool_blocks]   (wide types first: base 256-byte aligned)
+    return (int64_t)pool_blocks * CK_BLOCK * 8 + segs * 16 + (segs * 2 + 4) * 4 + segs * 16 + (int64_t)pool_blocks * 4;
+}
+
+extern "C" int b200bt_sweep_chunked(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S,
+                                    int64_t N, const b200bt_individual* indiv, const int32_t* order, int pop,
+                                    const b200bt_chunk_item* items, int n_items, const int32_t* seg_base,
+                                    const int32_t* n_chunks, int n_seg, int warm, int max_repair_rounds, int pool_blocks,
+                                    void* workspace, int64_t workspace_bytes, const b200bt_sweep_config* cfg_host,
+                                    b200bt_lane_stats* stats, uint32_t* events, int64_t event_cap,
+                                    unsigned char* lane_invalid, int* overflow_host_or_null, b200bt_stream_t stream) {
+    B200BT_REQUIRE(price && rsi && indiv && items && seg_base && n_chunks && workspace && cfg_host && stats && lane_invalid,
+                   B200BT_EINVAL, "sweep_chunked: null pointer");
+    B200BT_REQUIRE(S > 0 && N > 0 && P > 0 && pop > 0 && n_items > 0 && n_seg > 0 && pool_blocks > 0 && warm >= 0,
+                   B200BT_EINVAL, "sweep_chunked: bad sizes");
+    B200BT_REQUIRE(ld_price >= N && ld_rsi >= N, B200BT_EINVAL, "sweep_chunked: row stride shorter than N");
+    B200BT_REQUIRE(N < (1ll << 30), B200BT_ELIMIT, "sweep_chunked: N must be < 2^30 bars");
+    B200BT_REQUIRE(cfg_host->bar_minutes > 0 && cfg_host->minute0 >= 0 &&
+                       cfg_host->minute0 + N * (int64_t)cfg_host->bar_minutes < (1ll << 32) - 1440,
+                   B200BT_ELIMIT, "sweep_chunked: minute0 + N*bar_minutes must stay below 2^32 minutes");
+    B200BT_REQUIRE(workspace_bytes >= b200bt_sweep_chunked_workspace_bytes(pool_blocks, S, n_seg), B200BT_EINVAL,
+                   "sweep_chunked: workspace too small");
+    B200BT_REQUIRE(events == nullptr || event_cap > 0, B200BT_EINVAL, "sweep_chunked: event buffer without capacity");
+    int rc = check_device();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t segs = (int64_t)S * n_seg;
+    B200BT_REQUIRE(((uintptr_t)workspace & 15) == 0, B200BT_EINVAL, "sweep_chunked: workspace must be 16-byte aligned");
+    uint2* pool = (uint2*)workspace;
+    int2* seg_in = (int2*)(pool + (int64_t)pool_blocks * CK_BLOCK);
+    int2* seg_out = seg_in + segs;
+    int* seg_first = (int*)(seg_out + segs);
+    unsigned* seg_count = (unsigned*)(seg_first + segs);
+    unsigned* alloc = seg_count + segs;
+    int* overflow = (int*)(alloc + 1);
+    unsigned* n_repair = (unsigned*)(overflow + 1);
+    int4* repair = (int4*)(n_repair + 2);
+    int* next = (int*)(repair + segs);
+    cudaError_t e = cudaMemsetAsync(seg_in, 0, (size_t)(segs * 6 + 4) * 4, st);
+    if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: memset");
+
+    ChunkScanArgs A;
+    A.price = price; A.ld_price = ld_price; A.rsi = rsi; A.ld_rsi = ld_rsi; A.P = P; A.S = S; A.N = N;
+    A.indiv = indiv; A.items = items; A.n_items = n_items; A.n_seg = n_seg; A.warm = warm;
+    A.pool = pool; A.pool_blocks = pool_blocks; A.next = next; A.alloc = alloc;
+    A.seg_first = seg_first; A.seg_count = seg_count; A.seg_in = seg_in; A.seg_out = seg_out; A.overflow = overflow;
+    A.repair = repair; A.n_chunks = n_chunks;
+    const bool vec16 = (((uintptr_t)price | (uintptr_t)rsi) & 15) == 0 && ld_price % 4 == 0 && ld_rsi % 4 == 0;
+    auto kern = vec16 ? chunk_scan_kernel<true, false> : chunk_scan_kernel<false, false>;
+    auto kern_fix = vec16 ? chunk_scan_kernel<true, true> : chunk_scan_kernel<false, true>;
+    const size_t smem = sizeof(WarpShared) * SW_WARPS;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: cudaFuncSetAttribute");
+    const int64_t blocks = (int64_t)((n_items + SW_WARPS - 1) / SW_WARPS) * S;
+    B200BT_REQUIRE(blocks < (1ll << 31), B200BT_ELIMIT, "sweep_chunked: too many work items");
+    kern<<<(unsigned)blocks, SW_WARPS * 32, smem, st>>>(A);
+    B200BT_LAUNCH_CHECK("chunk_scan launch");
+    // verify -> repair rounds: a chunk whose assumed state was wrong is re-scanned from the true state; chunks
+    // behind a wrong predecessor wait for the next round.  Each round costs one tiny verify launch, a 4-byte
+    // readback (stream synchronisation) and, if anything is listed, one repair launch.
+    for (int round = 0; round < max_repair_rounds; ++round) {
+        e = cudaMemsetAsync(n_repair, 0, sizeof(unsigned), st);
+        if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: memset");
+        const int64_t lanes = (int64_t)pop * S;
+        chunk_verify_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pop, S, seg_base, n_chunks, n_seg, seg_count, seg_in,
+                                                                            seg_out, repair, n_repair);
+        B200BT_LAUNCH_CHECK("chunk_verify launch");
+        unsigned h_rep = 0;
+        e = cudaMemcpyAsync(&h_rep, n_repair, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: verify readback");
+        if (h_rep == 0) break;
+        ChunkScanArgs R = A;
+        R.n_items = (int)h_rep;
+        kern_fix<<<(h_rep + SW_WARPS - 1) / SW_WARPS, SW_WARPS * 32, smem, st>>>(R);
+        B200BT_LAUNCH_CHECK("chunk_repair launch");
+    }
+    const int64_t mblocks = (int64_t)((pop + 3) / 4) * S;
+    chunk_metrics_kernel<<<(unsigned)mblocks, 128, 0, st>>>(indiv, order, pop, S, seg_base, n_chunks, n_seg, pool, next,
+                                                             seg_first, seg_count, seg_in, seg_out, *cfg_host, stats, events,
+                                                             event_cap, lane_invalid);
+    B200BT_LAUNCH_CHECK("chunk_metrics launch");
+    if (overflow_host_or_null) {
+        e = cudaMemcpyAsync(overflow_host_or_null, overflow, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: overflow readback");
+    }
+    return B200BT_OK;
+}

@@ -129,6 +129,59 @@ def decode_population(population: List[Dict], period_row: Dict[int, int]) -> np.
     return out
 
 
+def lane_cost(p: Dict) -> float:
+    """Fraction of bars on which RSI(w) sits outside [oversold, overbought] under the model
+    RSI(w) ~ N(50, 44/sqrt(w)): the lane's trade-event rate is proportional to it (measured on the
+    synthetic 1-minute data: events ~= 0.27 * cost * bars).  Scheduling only; never affects results."""
+    from math import erf, sqrt
+    w = int(p.get("rsi_period", 14))
+    sd = 44.0 / sqrt(max(w, 1))
+    phi = lambda x: 0.5 * (1.0 + erf(x / sqrt(2.0)))
+    return phi((float(p.get("rsi_oversold", 30)) - 50.0) / sd) + 1.0 - phi((float(p.get("rsi_overbought", 70)) - 50.0) / sd)
+
+
+EVENTS_PER_COST_BAR = 0.27
+
+
+class ChunkPlan:
+    """Host-side plan of the time-chunked sweep for one population (device tensors inside)."""
+
+    def __init__(self, population: List[Dict], n_bars: int, n_symbols: int, device, target_events: int = 16384,
+                 warm: int = 8192, max_chunks: int = 64, pool_scale: float = 1.5, pool_blocks: Optional[int] = None,
+                 max_repair_rounds: int = 8):
+        pop = len(population)
+        cost = np.array([lane_cost(p) for p in population])
+        pred = EVENTS_PER_COST_BAR * cost * n_bars
+        kmax = max(1, min(max_chunks, n_bars // max(8 * warm, 2048)))
+        k = np.clip(np.ceil(pred / target_events), 1, kmax).astype(np.int32)
+        self.n_chunks = k
+        self.seg_base = np.concatenate([[0], np.cumsum(k)[:-1]]).astype(np.int32)
+        self.n_seg = int(k.sum())
+        self.order = evaluation_order(population)
+        items = np.zeros((self.n_seg, 4), dtype=np.int32)
+        # most expensive work first (per-chunk cost), keeping one individual's chunks together
+        per_chunk = pred / k
+        row = 0
+        for i in sorted(range(pop), key=lambda j: (-per_chunk[j], int(population[j].get("rsi_period", 14)))):
+            for c in range(int(k[i])):
+                items[row] = (i, c, k[i], self.seg_base[i] + c)
+                row += 1
+        self.warm = int(warm)
+        self.max_repair_rounds = int(max_repair_rounds)
+        self.pool_blocks = int(pool_scale * pred.sum() * n_symbols / 256) + 2 * self.n_seg * n_symbols + 1024
+        if pool_blocks is not None:
+            self.pool_blocks = int(pool_blocks)
+        self.items = torch.from_numpy(items).to(device)
+        self.seg_base_dev = torch.from_numpy(self.seg_base).to(device)
+        self.n_chunks_dev = torch.from_numpy(self.n_chunks).to(device)
+        self.order_dev = torch.from_numpy(self.order).to(device)
+        ws_bytes = int(_lib.load().b200bt_sweep_chunked_workspace_bytes(self.pool_blocks, n_symbols, self.n_seg))
+        self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        self.invalid = torch.zeros((pop, n_symbols), dtype=torch.uint8, device=device)
+        self.overflow = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.pop = pop
+
+
 def evaluation_order(population: List[Dict]) -> np.ndarray:
     """Order in which the kernel dispatches individuals: same RSI period adjacent (the
     warps of a CTA then read the same RSI stream), most expensive first.
@@ -137,18 +190,7 @@ def evaluation_order(population: List[Dict]) -> np.ndarray:
     fraction of time RSI(w) spends outside [oversold, overbought]; RSI(w) is roughly
     N(50, 44/sqrt(w)) on 1-minute data.  Only scheduling depends on this, never results.
     """
-    from math import erf, sqrt
-
-    def phi(x):
-        return 0.5 * (1.0 + erf(x / sqrt(2.0)))
-
-    keys = []
-    for i, p in enumerate(population):
-        w = int(p.get("rsi_period", 14))
-        sd = 44.0 / sqrt(max(w, 1))
-        cost = phi((float(p.get("rsi_oversold", 30)) - 50.0) / sd) + 1.0 - phi((float(p.get("rsi_overbought", 70)) - 50.0) / sd)
-        keys.append((w, -cost, i))
-    keys.sort()
+    keys = sorted((int(p.get("rsi_period", 14)), -lane_cost(p), i) for i, p in enumerate(population))
     return np.array([k[2] for k in keys], dtype=np.int32)
 
 
@@ -162,7 +204,9 @@ class PopulationSweep:
 
     def __init__(self, market: MarketData, rsi_periods: Iterable[int] = range(5, 31),
                  optimization_goals: Optional[Dict] = None, initial_capital: float = 10000.0,
-                 event_cap: int = 0):
+                 event_cap: int = 0, mode: str = "auto", chunk_options: Optional[Dict] = None):
+        """mode: "fused" (one warp per lane, serial in time), "chunked" (expensive lanes split into
+        verified time chunks, csrc/sweep_chunked.cu) or "auto" (chunked from 131072 bars up)."""
         self.market = market
         self.periods = sorted(set(int(p) for p in rsi_periods))
         self.period_row = {p: i for i, p in enumerate(self.periods)}
@@ -173,6 +217,7 @@ class PopulationSweep:
             secondary_mask=sum(_lib.SECONDARY.get(m, 0) for m in goals.get("secondary", [])), variant=0)
         self.event_cap = int(event_cap)
         self.bank = rsi_bank(market.close, self.periods)
+        self.mode, self.chunk_min_bars, self.chunk_options = mode, 131072, dict(chunk_options or {})
         self._stats = None
         self._events = None
         self._pop = 0
@@ -196,6 +241,7 @@ class PopulationSweep:
         self.event_cap = int(event_cap)
         assert bank.is_cuda and bank.dtype == torch.float32 and tuple(bank.shape) == (market.S, len(self.periods), market.N)
         self.bank = bank.contiguous()
+        self.mode, self.chunk_min_bars, self.chunk_options = "fused", 131072, {}
         self._stats = self._events = None
         self._pop = 0
         self._pinned_in = self._pinned_out = None
@@ -203,7 +249,11 @@ class PopulationSweep:
 
     # -- device-side evaluation (inputs already resident) -------------------
     def evaluate_device(self, indiv_dev: torch.Tensor, order_dev: Optional[torch.Tensor], pop: int,
-                        fitness_dev: torch.Tensor) -> None:
+                        fitness_dev: torch.Tensor, plan: Optional["ChunkPlan"] = None) -> None:
+        """Sweep + fitness reduction on the current stream.  With a ChunkPlan the time-chunked kernels
+        run first and only lanes whose chunk boundaries failed verification go through the fused kernel."""
+        if plan is not None:
+            return self._evaluate_chunked(indiv_dev, pop, fitness_dev, plan)
         m = self.market
         if self._stats is None or self._pop != pop:
             self._stats = torch.empty((pop, m.S, 16), dtype=torch.float64, device=m.device)
@@ -217,6 +267,38 @@ class PopulationSweep:
                       _lib.ptr(order_dev), pop, C.byref(self.cfg), self._stats.data_ptr(),
                       _lib.ptr(self._events), self.event_cap, st)
             _lib.call("b200bt_fitness_reduce", self._stats.data_ptr(), pop, m.S, fitness_dev.data_ptr(), st)
+
+    def _ensure_buffers(self, pop: int) -> None:
+        m = self.market
+        if self._stats is None or self._pop != pop:
+            self._stats = torch.empty((pop, m.S, 16), dtype=torch.float64, device=m.device)
+            self._events = (torch.zeros((pop, m.S, self.event_cap), dtype=torch.int32, device=m.device)
+                            if self.event_cap else None)
+            self._pop = pop
+
+    def _evaluate_chunked(self, indiv_dev, pop, fitness_dev, plan: "ChunkPlan") -> None:
+        m = self.market
+        self._ensure_buffers(pop)
+        with torch.cuda.device(m.device):
+            st = _lib.current_stream()
+            _lib.call("b200bt_sweep_chunked", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
+                      len(self.periods), m.S, m.N, indiv_dev.data_ptr(), plan.order_dev.data_ptr(), pop,
+                      plan.items.data_ptr(), plan.n_seg, plan.seg_base_dev.data_ptr(), plan.n_chunks_dev.data_ptr(),
+                      plan.n_seg, plan.warm, plan.max_repair_rounds, plan.pool_blocks, plan.workspace.data_ptr(), plan.workspace.numel(),
+                      C.byref(self.cfg), self._stats.data_ptr(), _lib.ptr(self._events), self.event_cap,
+                      plan.invalid.data_ptr(), plan.overflow.data_ptr(), st)
+            bad = torch.nonzero(plan.invalid.any(dim=1)).flatten()          # device -> host sync (tiny)
+            self.last_invalid_lanes = int(plan.invalid.sum().item())
+            self.last_pool_overflow = bool(plan.overflow.item())
+            if bad.numel():
+                redo = bad.to(torch.int32).contiguous()
+                _lib.call("b200bt_sweep", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
+                          len(self.periods), m.S, m.N, indiv_dev.data_ptr(), redo.data_ptr(), int(redo.numel()),
+                          C.byref(self.cfg), self._stats.data_ptr(), _lib.ptr(self._events), self.event_cap, st)
+            _lib.call("b200bt_fitness_reduce", self._stats.data_ptr(), pop, m.S, fitness_dev.data_ptr(), st)
+
+    def plan_chunks(self, population: List[Dict], **kw) -> "ChunkPlan":
+        return ChunkPlan(population, self.market.N, self.market.S, self.market.device, **kw)
 
     # -- host-facing evaluation --------------------------------------------
     def evaluate(self, population: List[Dict]) -> np.ndarray:
@@ -239,7 +321,14 @@ class PopulationSweep:
         indiv_dev = staged[:nbytes]
         order_dev = staged[nbytes:].view(torch.int32)
         fit = torch.empty(pop, dtype=torch.float64, device=dev)
-        self.evaluate_device(indiv_dev, order_dev, pop, fit)
+        plan = None
+        if self.mode == "chunked" or (self.mode == "auto" and self.market.N >= self.chunk_min_bars):
+            plan = self.plan_chunks(population, **self.chunk_options)
+            if getattr(self, "last_pool_overflow", False):
+                grown = dict(self.chunk_options, pool_scale=4.0 * self.chunk_options.get("pool_scale", 1.5))
+                grown.pop("pool_blocks", None)
+                plan = self.plan_chunks(population, **grown)
+        self.evaluate_device(indiv_dev, order_dev, pop, fit, plan=plan)
         out = self._pinned_out[:pop]
         out.copy_(fit, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()

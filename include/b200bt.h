@@ -216,6 +216,33 @@ int b200bt_sweep(const float* price, int64_t ld_price,
                  uint32_t* events, int64_t event_cap,
                  b200bt_stream_t stream);
 
+/* Time-chunked form of b200bt_sweep (same results; csrc/sweep_chunked.cu).  Expensive lanes are split
+ * into n_chunks time chunks scanned concurrently, each started `warm` bars early from the flat state;
+ * the chunk-boundary states are verified; chunks whose assumed state was wrong are re-scanned from the
+ * true state in up to max_repair_rounds rounds (each round synchronises the stream for a 4-byte count);
+ * a lane that still has a mismatch (or lost events to a full pool) is flagged in lane_invalid[pop][S]
+ * (stats of flagged lanes are NOT written: re-evaluate those individuals with b200bt_sweep, passing them
+ * as `order`).  One work item per (individual, chunk); `segment` = seg_base[individual] + chunk.
+ *  items      [n_items] device      seg_base, n_chunks  [pop] device int32      n_seg = sum of n_chunks
+ *  pool_blocks  event pool size in blocks of 256 events; a chunk that cannot get a block flags its lane
+ *  workspace  b200bt_sweep_chunked_workspace_bytes(pool_blocks, S, n_seg) device bytes
+ *  overflow_host_or_null  optional pinned host int receiving 1 if the pool ran out (grow it next time) */
+typedef struct b200bt_chunk_item {
+    int32_t individual;
+    int32_t chunk;
+    int32_t n_chunks;
+    int32_t segment;
+} b200bt_chunk_item;
+
+int64_t b200bt_sweep_chunked_workspace_bytes(int pool_blocks, int S, int n_seg);
+int b200bt_sweep_chunked(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P,
+                         int S, int64_t N, const b200bt_individual* indiv, const int32_t* order, int pop,
+                         const b200bt_chunk_item* items, int n_items, const int32_t* seg_base,
+                         const int32_t* n_chunks, int n_seg, int warm, int max_repair_rounds, int pool_blocks,
+                         void* workspace, int64_t workspace_bytes, const b200bt_sweep_config* cfg_host,
+                         b200bt_lane_stats* stats, uint32_t* events, int64_t event_cap,
+                         unsigned char* lane_invalid, int* overflow_host_or_null, b200bt_stream_t stream);
+
 /* fitness[i] = mean over symbols of stats[i][s].score  (float64, device). */
 int b200bt_fitness_reduce(const b200bt_lane_stats* stats, int pop, int S,
                           double* fitness, b200bt_stream_t stream);

@@ -176,3 +176,56 @@ def test_evolution_service_runs_ga_on_gpu(torch_cuda):
     again = svc.sweep.evaluate(svc.last_ga.population)
     np.testing.assert_array_equal(np.array(svc.last_ga.fitness_scores), again)
     assert svc.evolution_records[-1]["new_params"] == best
+
+
+def _check_lanes_vs_oracle(sweep, population, ohlcv, cap):
+    from oracle import indicators_ref, sim_oracle
+    stats, events = sweep.lane_stats(), sweep.events()
+    cfg = sim_oracle.config_of(sweep.market.minute0, 1)
+    n_sym = ohlcv.shape[1]
+    for s in range(n_sym):
+        bank = indicators_ref.rsi_bank(ohlcv[3, s], sweep.periods)
+        for i, p in enumerate(population):
+            want, ev, _ = sim_oracle.lane(ohlcv[3, s], bank[sweep.period_row[p["rsi_period"]]], p, cfg, event_cap=cap)
+            assert int(stats["n_records"][i, s]) == int(want["n_records"]), (i, s)
+            assert int(stats["trade_hash"][i, s]) == int(want["trade_hash"]), (i, s)
+            if events is not None:
+                assert np.array_equal(events[i, s, :len(ev)], ev), (i, s)
+            for f in ("n_wins", "n_losses", "n_days", "sum_duration_bars"):
+                assert stats[f][i, s] == want[f], (i, s, f)
+            for f in ("total_profit", "total_loss", "net_profit", "max_drawdown", "sharpe_ratio", "largest_profit",
+                      "largest_loss", "win_rate", "profit_factor", "score"):
+                assert stats[f][i, s] == pytest.approx(float(want[f]), rel=1e-9, abs=1e-11), (i, s, f)
+
+
+@pytest.mark.parametrize("n_bars,opts", [
+    (300_000, dict(target_events=1500, warm=4096)),          # many chunks, verified boundaries
+    (70_001, dict(target_events=300, warm=0, max_chunks=64, max_repair_rounds=0)),  # no warm-up, no repair: fused fallback
+    (150_000, dict(target_events=300, warm=0, max_chunks=64, max_repair_rounds=64)),  # no warm-up: repaired chunk by chunk
+    (200_000, dict(target_events=2000, warm=2048, pool_blocks=8)),  # pool far too small -> flagged lanes re-run
+])
+def test_chunked_sweep_is_exact_and_self_repairing(torch_cuda, n_bars, opts):
+    """Time-chunked sweep == serial reference semantics, whether or not the speculation holds."""
+    from ai_crypto_trader_b200 import synth
+    from ai_crypto_trader_b200.sweep import MarketData, PopulationSweep
+    ohlcv = synth.synth_ohlcv(2, n_bars, first_symbol=1)
+    market = MarketData(ohlcv)
+    cap = 2048
+    population = synth.random_population(40, seed=n_bars)
+    population[0].update(rsi_oversold=35, rsi_overbought=65, rsi_period=5, take_profit=1, stop_loss=1)
+    population[1].update(rsi_oversold=34, rsi_overbought=66, rsi_period=6, take_profit=10, stop_loss=5)
+    chunked = PopulationSweep(market, event_cap=cap, mode="chunked", chunk_options=opts)
+    fused = PopulationSweep(market, event_cap=cap, mode="fused")
+    f_c = chunked.evaluate(population)
+    f_f = fused.evaluate(population)
+    plan = chunked.plan_chunks(population, **opts)
+    assert plan.n_chunks.max() > 1, "the test population must exercise real chunking"
+    if opts.get("max_repair_rounds", 8) == 0:
+        assert chunked.last_invalid_lanes > 0          # the fallback path really ran
+    if opts.get("max_repair_rounds", 8) == 64:
+        assert chunked.last_invalid_lanes == 0         # every wrong boundary was repaired in place
+    if "pool_blocks" in opts:
+        assert chunked.last_pool_overflow and chunked.last_invalid_lanes > 0
+    _check_lanes_vs_oracle(chunked, population, ohlcv, cap)
+    np.testing.assert_array_equal(chunked.lane_stats()["trade_hash"], fused.lane_stats()["trade_hash"])
+    np.testing.assert_allclose(f_c, f_f, rtol=1e-9, atol=1e-11)
