@@ -61,14 +61,6 @@ __device__ __forceinline__ double warp_min_d(double v) {
     return v;
 }
 
-// splitmix64 finaliser: the trade-hash mixer (oracle/sim_oracle.c uses the same).
-__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
-    x += 0x9E3779B97F4A7C15ull;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
-}
-
 // Trade-hash contribution of one event (event index, event word): two 32-bit multiply-xorshift
 // mixes; the lane hash is the xor over all events (oracle/sim_oracle.c computes the same).
 __host__ __device__ __forceinline__ uint64_t event_hash(uint32_t index, uint32_t word) {

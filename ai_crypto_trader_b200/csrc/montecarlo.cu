@@ -10,8 +10,9 @@
 // One thread per path.  The path lives in log space in registers
 // (logS_t = logS_{t-1} + increment), so risk-only mode never exponentiates inside
 // the time loop: the final price is s0*exp(logS_T) and the maximum drawdown is
-// 1 - exp(min_t(logS_t - max_{s<=t} logS_s)).  The log-price accumulates in fp64
-// (one DADD per step) so 10^4 fp32 increments do not drift; normals are fp32.
+// 1 - exp(min_t(logS_t - max_{s<=t} logS_s)).  Four steps (one Philox block) are
+// accumulated in fp32 relative to an fp64 base that absorbs each block's sum, so
+// 10^4 increments do not drift while the inner loop stays on the fp32 pipe.
 // Randomness is a pure function of (seed, path index, step): results do not
 // depend on the launch geometry or on how paths are sharded across GPUs.
 #include <math.h>
@@ -46,16 +47,21 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// 24-bit uniform in (0,1): exactly representable in fp32, never 0 or 1.
+// 24-bit uniform in (0,1]: (k + 0.5) * 2^-24 rounded to fp32 (for k >= 2^23 the half is absorbed by
+// round-to-even, so the top value rounds to exactly 1; never 0).
 __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
-// Box-Muller: two uniforms -> two standard normals.
+// Box-Muller: two uniforms -> two standard normals (r cos 2*pi*v, r sin 2*pi*v).  The radius uses the
+// accurate logf (the fast __logf has an ABSOLUTE error of 2^-21, which for u -> 1 exceeds -ln u itself
+// and can even flip its sign); rsqrt / sin / cos use the MUFU units: the angle is taken in (-pi, pi)
+// where __sincosf is accurate to 2^-21, the half-turn shift is undone by the sign flip.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-    const float r = sqrtf(-2.0f * logf(u01(a)));
+    const float t = -2.0f * logf(u01(a));                 // >= 0; exactly 0 when the uniform rounds to 1
+    const float r = t * rsqrtf(fmaxf(t, 1e-30f));
     float s, c;
-    sincospif(2.0f * u01(b), &s, &c);
-    z0 = r * c;
-    z1 = r * s;
+    __sincosf(6.283185307179586f * u01(b) - 3.14159265358979f, &s, &c);
+    z0 = -r * c;
+    z1 = -r * s;
 }
 
 constexpr int MC_THREADS = 256;
@@ -81,8 +87,10 @@ mc_paths_kernel(double s0, double drift, double vol, const float* __restrict__ r
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const uint32_t c0 = (uint32_t)gid, c1 = (uint32_t)(gid >> 32);
 
-    double logS = 0.0, runmax = 0.0, worst = 0.0;  // relative to log(s0)
-    const float fs0 = (float)s0;
+    // log-price relative to log(s0): block base `base` and running maximum `runmax` in fp64, the four
+    // steps of a Philox block in fp32 relative to the base (their sum is folded into the base exactly)
+    double base = 0.0, runmax = 0.0, worst = 0.0;
+    const float fs0 = (float)s0, fdrift = (float)drift, fvol = (float)vol;
     if (paths) paths[p] = fs0;
     int boot_idx = 0, boot_left = 0;
     for (int t0 = 0; t0 < steps; t0 += 4) {
@@ -94,7 +102,7 @@ mc_paths_kernel(double s0, double drift, double vol, const float* __restrict__ r
             box_muller(x[0], x[1], z[0], z[1]);
             box_muller(x[2], x[3], z[2], z[3]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) inc[j] = z[j];
+            for (int j = 0; j < 4; ++j) inc[j] = fmaf(fvol, z[j], fdrift);
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -108,16 +116,22 @@ mc_paths_kernel(double s0, double drift, double vol, const float* __restrict__ r
                 inc[j] = s_ret[boot_idx];
             }
         }
+        const float d0 = (float)(runmax - base);   // running maximum seen from the block base (>= 0)
+        float l = 0.f, mx = d0, wmin = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (t0 + j < steps) {
-                logS += (MODE == 0) ? (drift + vol * (double)inc[j]) : (double)inc[j];
-                runmax = fmax(runmax, logS);
-                worst = fmin(worst, logS - runmax);
-                if (paths) paths[(int64_t)(t0 + j + 1) * n_paths + p] = fs0 * expf((float)logS);
+                l += inc[j];
+                mx = fmaxf(mx, l);
+                wmin = fminf(wmin, l - mx);
+                if (paths) paths[(int64_t)(t0 + j + 1) * n_paths + p] = fs0 * expf((float)base + l);
             }
         }
+        if (mx > d0) runmax = base + (double)mx;
+        worst = fmin(worst, (double)wmin);
+        base += (double)l;
     }
+    const double logS = base;
     finals[p] = (float)(s0 * exp(logS));
     maxdd[p] = (float)(1.0 - exp(worst));
 }

@@ -43,7 +43,7 @@ def u01(x):
 
 
 def box_muller(a, b):
-    r = np.sqrt(np.float32(-2.0) * np.log(u01(a)))
+    r = np.sqrt(np.abs(np.float32(-2.0) * np.log(u01(a))))   # abs: -0.0 when the uniform rounds to 1
     ang = np.float32(2.0) * u01(b)             # sincospif(2u): sin/cos of pi*2u
     ang64 = ang.astype(np.float64) * np.pi
     return r * np.cos(ang64).astype(np.float32), r * np.sin(ang64).astype(np.float32)
