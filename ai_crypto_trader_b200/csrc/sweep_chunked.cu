@@ -11,9 +11,9 @@
 // state (position side + entry bar) is almost always the true one.  It is VERIFIED, not trusted:
 //   scan kernel     one warp per (individual, symbol, chunk): events -> blocks of a global pool
 //                   (bump allocator, singly linked per chunk), assumed state at T_c and end state.
-//   metrics kernel  one warp per (individual, symbol): checks end state of chunk c-1 == assumed
-//                   state of chunk c for every boundary, then folds the chunks' events in time
-//                   order through the same float64 batch arithmetic as the fused kernel.
+//   metrics kernels one warp per (individual, symbol, chunk) again (see "metrics, chunk-parallel" below), then
+//                   one thread per (individual, symbol) checks end state of chunk c-1 == assumed state
+//                   of chunk c for every boundary and merges the chunks' partial metrics.
 // A lane with any mismatching boundary is flagged; the host re-evaluates flagged lanes with the
 // fused (serial) kernel, so results never depend on the speculation being right.
 #include "sweep_dev.cuh"
@@ -234,29 +234,164 @@ __global__ void chunk_verify_kernel(int pop, int S, const int32_t* __restrict__ 
     }
 }
 
-// One warp per (individual, symbol): verify the chunk boundaries, then fold the chunks' events.
+// ---- metrics, chunk-parallel -------------------------------------------------------------------------
+// The trade-record metrics are a fold over the lane's events in time order, but every piece of it is
+// either a sum / max / xor (associative) or depends on the past only through three scalars: the equity
+// and running equity peak at the chunk's start, and the index of the chunk's first record.  So:
+//   chunk_sums_kernel    warp per (chunk, symbol): sum of record pnls and the largest prefix sum.
+//   chunk_partial_kernel warp per (chunk, symbol): exclusive scan of those over the lane's earlier chunks
+//                        -> starting equity / peak / record index, then the ordinary batch arithmetic
+//                        (batch_core) over the chunk's own events into a ChunkPartial.
+//   lane_combine_kernel  thread per (individual, symbol): verifies the boundaries, merges the partials
+//                        (calendar days that straddle a chunk boundary are re-joined) and finalises.
+struct ChunkPartial {
+    double tot_profit, tot_loss, largest_p, largest_l, maxdd, first_sum, pivot, s1, s2, day_sum;
+    long long sum_dur;
+    unsigned long long hash;
+    unsigned n_win, n_loss, n_days, count;
+    int first_done, first_day, day_cur, pad;
+};
+static_assert(sizeof(ChunkPartial) == 128, "ChunkPartial layout");
+
+// entry record a chunk's first exit is priced against, from the chunk's (verified) start state
+__device__ __forceinline__ void chunk_carry(const int2 in, const float* __restrict__ pr, unsigned& w_carry, float& p_carry) {
+    w_carry = 0u; p_carry = 0.f;
+    if (in.x != 0) {
+        w_carry = (unsigned)in.y | (in.x < 0 ? B200BT_EVENT_SELL : 0u);
+        p_carry = __ldg(pr + in.y);
+    }
+}
+
 __global__ void __launch_bounds__(128)
-chunk_metrics_kernel(const b200bt_individual* __restrict__ indiv, const int32_t* __restrict__ order, int pop, int S,
-                     const int32_t* __restrict__ seg_base, const int32_t* __restrict__ n_chunks, int n_seg,
+chunk_sums_kernel(const float* __restrict__ price, int64_t ld_price, const b200bt_individual* __restrict__ indiv,
+                  const b200bt_chunk_item* __restrict__ items, int n_items, int S, int n_seg,
+                  const uint2* __restrict__ pool, const int* __restrict__ next, const int* __restrict__ seg_first,
+                  const unsigned* __restrict__ seg_count, const int2* __restrict__ seg_in,
+                  double* __restrict__ seg_sum, double* __restrict__ seg_max) {
+    const int lane = threadIdx.x & 31;
+    const int sym = (int)(blockIdx.x % (unsigned)S);
+    const int it = (int)(blockIdx.x / (unsigned)S) * 4 + (threadIdx.x >> 5);
+    if (it >= n_items) return;
+    const b200bt_chunk_item item = items[it];
+    const int seg = sym * n_seg + item.segment;
+    const double size = indiv[item.individual].position_size;
+    const double fee1 = __dmul_rn(size, 0.001), fee2 = __dmul_rn(size, 0.002);
+    unsigned left = seg_count[seg];
+    if (left == 0xffffffffu) left = 0;
+    unsigned w_carry; float p_carry;
+    chunk_carry(seg_in[seg], price + (int64_t)sym * ld_price, w_carry, p_carry);
+    int b = left ? seg_first[seg] : -1, off = 0;
+    double run = 0.0, best = -INFINITY;
+    while (left) {
+        const int cnt = (int)min(32u, left);
+        const uint2 ev = lane < cnt ? pool[(int64_t)b * CK_BLOCK + off + lane] : make_uint2(0u, 0u);
+        const float pf = __uint_as_float(ev.y);
+        float p_prev = __shfl_up_sync(FULL, pf, 1);
+        unsigned w_prev = __shfl_up_sync(FULL, ev.x, 1);
+        if (lane == 0) { p_prev = p_carry; w_prev = w_carry; }
+        int dur;
+        double cs = record_pnl(lane < cnt, ev.x, pf, w_prev, p_prev, size, fee1, fee2, dur);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double up = shfl_up_d(cs, d);
+            if (lane >= d) cs += up;
+        }
+        best = fmax(best, warp_max_d(lane < cnt ? run + cs : -INFINITY));
+        run += shfl_d(cs, 31);
+        w_carry = __shfl_sync(FULL, ev.x, cnt - 1);
+        p_carry = __shfl_sync(FULL, pf, cnt - 1);
+        left -= cnt;
+        off += 32;
+        if (off == CK_BLOCK && left) { b = next[b]; off = 0; }
+    }
+    if (lane == 0) { seg_sum[seg] = run; seg_max[seg] = best; }
+}
+
+__global__ void __launch_bounds__(128)
+chunk_partial_kernel(const float* __restrict__ price, int64_t ld_price, const b200bt_individual* __restrict__ indiv,
+                     const b200bt_chunk_item* __restrict__ items, int n_items, int S, int n_seg,
                      const uint2* __restrict__ pool, const int* __restrict__ next, const int* __restrict__ seg_first,
                      const unsigned* __restrict__ seg_count, const int2* __restrict__ seg_in,
-                     const int2* __restrict__ seg_out, const b200bt_sweep_config cfg,
-                     b200bt_lane_stats* __restrict__ stats, uint32_t* __restrict__ events, int64_t ev_cap,
-                     unsigned char* __restrict__ invalid) {
+                     const double* __restrict__ seg_sum, const double* __restrict__ seg_max,
+                     const b200bt_sweep_config cfg, uint32_t* __restrict__ events, int64_t ev_cap,
+                     ChunkPartial* __restrict__ partial) {
     __shared__ WarpAcc s_acc[4];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int sym = (int)(blockIdx.x % (unsigned)S);
-    const int k = (int)(blockIdx.x / (unsigned)S) * 4 + wid;
-    if (k >= pop) return;
-    const int ind = order ? order[k] : k;
-    const b200bt_individual iv = indiv[ind];
+    const int it = (int)(blockIdx.x / (unsigned)S) * 4 + wid;
+    if (it >= n_items) return;
+    const b200bt_chunk_item item = items[it];
+    const int seg = sym * n_seg + item.segment;
+    const int base = seg - item.chunk;
+    const b200bt_individual iv = indiv[item.individual];
+
+    // state at the chunk's start: equity, running peak, record index -- exclusive scan over earlier chunks
+    double e0 = cfg.initial_capital, p0 = cfg.initial_capital;
+    unsigned first_index = 0;
+    for (int c0 = 0; c0 < item.chunk; c0 += 32) {
+        const int c = c0 + lane;
+        const bool in = c < item.chunk;
+        const double s = in ? seg_sum[base + c] : 0.0;
+        const double mx = in ? seg_max[base + c] : -INFINITY;
+        unsigned n = in ? seg_count[base + c] : 0u;
+        if (n == 0xffffffffu) n = 0;
+        double incl = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double up = shfl_up_d(incl, d);
+            if (lane >= d) incl += up;
+        }
+        const double start = e0 + (incl - s);            // equity at the start of chunk c
+        p0 = fmax(p0, warp_max_d(start + mx));
+        e0 += shfl_d(incl, 31);
+        first_index += __reduce_add_sync(FULL, n);
+    }
+
     WarpAcc* acc = &s_acc[wid];
     if (lane == 0) {
         WarpAcc a0;
-        init_acc(a0, iv, cfg.initial_capital, events ? events + ((int64_t)ind * S + sym) * ev_cap : nullptr);
+        init_acc(a0, iv, cfg.initial_capital, events ? events + ((int64_t)item.individual * S + sym) * ev_cap : nullptr);
+        a0.equity = e0; a0.peak = p0; a0.n_events = first_index; a0.hold_first = 1;
         *acc = a0;
     }
     __syncwarp();
+    unsigned left = seg_count[seg];
+    if (left == 0xffffffffu) left = 0;
+    const unsigned count = left;
+    unsigned w_carry; float p_carry;
+    chunk_carry(seg_in[seg], price + (int64_t)sym * ld_price, w_carry, p_carry);
+    int b = left ? seg_first[seg] : -1, off = 0;
+    while (left) {
+        const int cnt = (int)min(32u, left);
+        const uint2 ev = lane < cnt ? pool[(int64_t)b * CK_BLOCK + off + lane] : make_uint2(0u, 0u);
+        batch_core(acc, cnt, ev.x, __uint_as_float(ev.y), w_carry, p_carry, cfg.minute0, cfg.bar_minutes, ev_cap);
+        w_carry = __shfl_sync(FULL, ev.x, cnt - 1);
+        p_carry = __shfl_sync(FULL, __uint_as_float(ev.y), cnt - 1);
+        left -= cnt;
+        off += 32;
+        if (off == CK_BLOCK && left) { b = next[b]; off = 0; }
+    }
+    if (lane == 0) {
+        const WarpAcc& a = *acc;
+        ChunkPartial q;
+        q.tot_profit = a.tot_profit; q.tot_loss = a.tot_loss; q.largest_p = a.largest_p; q.largest_l = a.largest_l;
+        q.maxdd = a.maxdd; q.first_sum = a.first_sum; q.pivot = a.pivot; q.s1 = a.s1; q.s2 = a.s2; q.day_sum = a.day_sum;
+        q.sum_dur = a.sum_dur; q.hash = a.hash;
+        q.n_win = a.n_win; q.n_loss = a.n_loss; q.n_days = a.n_days; q.count = count;
+        q.first_done = a.first_done; q.first_day = a.first_day; q.day_cur = (int)a.day_cur; q.pad = 0;
+        partial[seg] = q;
+    }
+}
+
+__global__ void lane_combine_kernel(const b200bt_individual* __restrict__ indiv, int pop, int S,
+                                    const int32_t* __restrict__ seg_base, const int32_t* __restrict__ n_chunks, int n_seg,
+                                    const unsigned* __restrict__ seg_count, const int2* __restrict__ seg_in,
+                                    const int2* __restrict__ seg_out, const ChunkPartial* __restrict__ partial,
+                                    const b200bt_sweep_config cfg, b200bt_lane_stats* __restrict__ stats,
+                                    unsigned char* __restrict__ invalid) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)pop * S) return;
+    const int ind = (int)(t / S), sym = (int)(t % S);
     const int K = n_chunks[ind];
     const int base = sym * n_seg + seg_base[ind];
     bool ok = true;
@@ -269,33 +404,52 @@ chunk_metrics_kernel(const b200bt_individual* __restrict__ indiv, const int32_t*
         }
         ok = ok && (seg_count[base + c] != 0xffffffffu);
     }
-    if (ok) {
-        unsigned w_carry = 0u;
-        float p_carry = 0.f;
-        for (int c = 0; c < K; ++c) {
-            unsigned left = seg_count[base + c];
-            int b = left ? seg_first[base + c] : -1;
-            int off = 0;
-            while (left) {
-                const int cnt = (int)min(32u, left);
-                const uint2 ev = lane < cnt ? pool[(int64_t)b * CK_BLOCK + off + lane] : make_uint2(0u, 0u);
-                batch_core(acc, cnt, ev.x, __uint_as_float(ev.y), w_carry, p_carry, cfg.minute0, cfg.bar_minutes, ev_cap);
-                w_carry = __shfl_sync(FULL, ev.x, cnt - 1);
-                p_carry = __shfl_sync(FULL, __uint_as_float(ev.y), cnt - 1);
-                left -= cnt;
-                off += 32;
-                if (off == CK_BLOCK && left) { b = next[b]; off = 0; }
+    invalid[t] = ok ? 0 : 1;
+    if (!ok) return;
+    WarpAcc a;
+    init_acc(a, indiv[ind], cfg.initial_capital, nullptr);
+    DayAcc da{0.0, 0.0, 0.0, 0u, 0};
+    bool open = false;      // the lane's open (last, not yet finished) calendar day
+    int open_day = 0;
+    double open_sum = 0.0;
+    for (int c = 0; c < K; ++c) {
+        const ChunkPartial q = partial[base + c];
+        if (q.count == 0) continue;
+        a.n_events += q.count;
+        a.n_win += q.n_win; a.n_loss += q.n_loss;
+        a.tot_profit += q.tot_profit; a.tot_loss += q.tot_loss;
+        a.largest_p = fmax(a.largest_p, q.largest_p); a.largest_l = fmin(a.largest_l, q.largest_l);
+        a.maxdd = fmax(a.maxdd, q.maxdd);
+        a.sum_dur += q.sum_dur;
+        a.hash ^= q.hash;
+        if (!q.first_done) {
+            // the whole chunk lies in one calendar day, which stays open
+            if (open && open_day == q.day_cur) open_sum += q.day_sum;
+            else {
+                if (open) day_complete(da, open_sum);
+                open = true; open_day = q.day_cur; open_sum = q.day_sum;
             }
+            continue;
         }
-    }
-    if (lane == 0) {
-        invalid[(int64_t)ind * S + sym] = ok ? 0 : 1;
-        if (ok) {
-            b200bt_lane_stats o;
-            finalize_lane(*acc, cfg, o);
-            stats[(int64_t)ind * S + sym] = o;
+        double x = q.first_sum;
+        if (open) {
+            if (open_day == q.first_day) x += open_sum; else day_complete(da, open_sum);
         }
+        day_complete(da, x);
+        if (q.n_days) {
+            // the chunk's own finished days, accumulated about its pivot: shift to the lane's pivot
+            const double d = q.pivot - da.pivot, n = (double)q.n_days;
+            da.s1 += q.s1 + n * d;
+            da.s2 += q.s2 + 2.0 * d * q.s1 + n * d * d;
+            da.n_days += q.n_days;
+        }
+        open = true; open_day = q.day_cur; open_sum = q.day_sum;
     }
+    a.pivot = da.pivot; a.s1 = da.s1; a.s2 = da.s2; a.n_days = da.n_days; a.pivot_set = da.pivot_set;
+    a.day_valid = open ? 1 : 0; a.day_sum = open_sum; a.day_cur = open_day;
+    b200bt_lane_stats o;
+    finalize_lane(a, cfg, o);
+    stats[t] = o;
 }
 
 }  // namespace b200bt
@@ -306,7 +460,9 @@ extern "C" int64_t b200bt_sweep_chunked_workspace_bytes(int pool_blocks, int S, 
     const int64_t segs = (int64_t)S * n_seg;
     // pool[pool_blocks][256] uint2 | seg_in[segs] int2 | seg_out[segs] int2 | seg_first[segs] | seg_count[segs] |
     // alloc, overflow, n_repair, pad | repair[segs] int4 | next[pool_blocks]   (wide types first: base 256-byte aligned)
-    return (int64_t)pool_blocks * CK_BLOCK * 8 + segs * 16 + (segs * 2 + 4) * 4 + segs * 16 + (int64_t)pool_blocks * 4;
+    // ... | partial[segs] (128 B) | seg_sum[segs] | seg_max[segs]
+    return (int64_t)pool_blocks * CK_BLOCK * 8 + segs * 16 + (segs * 2 + 4) * 4 + segs * 16 + (int64_t)pool_blocks * 4 + 16 +
+           segs * (int64_t)(sizeof(ChunkPartial) + 16);
 }
 
 extern "C" int b200bt_sweep_chunked(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S,
@@ -343,6 +499,9 @@ extern "C" int b200bt_sweep_chunked(const float* price, int64_t ld_price, const 
     unsigned* n_repair = (unsigned*)(overflow + 1);
     int4* repair = (int4*)(n_repair + 2);
     int* next = (int*)(repair + segs);
+    ChunkPartial* partial = (ChunkPartial*)(((uintptr_t)(next + pool_blocks) + 15) & ~(uintptr_t)15);
+    double* seg_sum = (double*)(partial + segs);
+    double* seg_max = seg_sum + segs;
     cudaError_t e = cudaMemsetAsync(seg_in, 0, (size_t)(segs * 6 + 4) * 4, st);
     if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: memset");
 
@@ -383,11 +542,21 @@ extern "C" int b200bt_sweep_chunked(const float* price, int64_t ld_price, const 
         kern_fix<<<(h_rep + SW_WARPS - 1) / SW_WARPS, SW_WARPS * 32, smem, st>>>(R);
         B200BT_LAUNCH_CHECK("chunk_repair launch");
     }
-    const int64_t mblocks = (int64_t)((pop + 3) / 4) * S;
-    chunk_metrics_kernel<<<(unsigned)mblocks, 128, 0, st>>>(indiv, order, pop, S, seg_base, n_chunks, n_seg, pool, next,
-                                                             seg_first, seg_count, seg_in, seg_out, *cfg_host, stats, events,
-                                                             event_cap, lane_invalid);
-    B200BT_LAUNCH_CHECK("chunk_metrics launch");
+    const int64_t mblocks = (int64_t)((n_items + 3) / 4) * S;
+    chunk_sums_kernel<<<(unsigned)mblocks, 128, 0, st>>>(price, ld_price, indiv, items, n_items, S, n_seg, pool, next, seg_first,
+                                                          seg_count, seg_in, seg_sum, seg_max);
+    B200BT_LAUNCH_CHECK("chunk_sums launch");
+    chunk_partial_kernel<<<(unsigned)mblocks, 128, 0, st>>>(price, ld_price, indiv, items, n_items, S, n_seg, pool, next,
+                                                             seg_first, seg_count, seg_in, seg_sum, seg_max, *cfg_host, events,
+                                                             event_cap, partial);
+    B200BT_LAUNCH_CHECK("chunk_partial launch");
+    {
+        const int64_t lanes = (int64_t)pop * S;
+        lane_combine_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(indiv, pop, S, seg_base, n_chunks, n_seg, seg_count,
+                                                                            seg_in, seg_out, partial, *cfg_host, stats,
+                                                                            lane_invalid);
+    }
+    B200BT_LAUNCH_CHECK("lane_combine launch");
     if (overflow_host_or_null) {
         e = cudaMemcpyAsync(overflow_host_or_null, overflow, sizeof(int), cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: overflow readback");

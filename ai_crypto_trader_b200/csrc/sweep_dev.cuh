@@ -38,6 +38,10 @@ struct WarpAcc {
     uint32_t* ev_out;
     unsigned n_win, n_loss, n_days, n_events;
     int day_valid, pivot_set;
+    // chunk-parallel metrics only: the first calendar day of a chunk may continue the previous chunk's
+    // last day, so its sum is kept aside instead of being counted as a finished day
+    int hold_first, first_done, first_day;
+    double first_sum;
 };
 
 // Per-warp shared-memory working set.
@@ -63,6 +67,22 @@ __device__ __forceinline__ void day_complete(DayAcc& a, double x) {
     a.n_days += 1;
 }
 
+// PnL of one trade record (strategy_evaluation.py:798,:819,:836): an entry record costs the entry fee,
+// an exit record realises quantity * move - both fees, with quantity = position_size / entry_price.
+__device__ __forceinline__ double record_pnl(bool active, unsigned w, float pf, unsigned w_prev, float p_prev,
+                                             double size, double fee1, double fee2, int& dur) {
+    dur = 0;
+    if (!active) return 0.0;
+    if (w & B200BT_EVENT_EXIT) {
+        const double e = (double)p_prev, px = (double)pf;
+        const double qty = __ddiv_rn(size, e);
+        const double diff = (w_prev & B200BT_EVENT_SELL) ? __dsub_rn(e, px) : __dsub_rn(px, e);
+        dur = (int)((w & 0x3fffffffu) - (w_prev & 0x3fffffffu));
+        return __dsub_rn(__dmul_rn(qty, diff), fee2);
+    }
+    return -fee1;
+}
+
 // Consume `cnt` events in time order (lane j holds event j: word w, price pf); an exit record is
 // priced against the entry record that precedes it -- lane j-1, or for lane 0 the last event of
 // the previous batch (w_carry, p_carry).  The trade-record metrics of calculate_metrics
@@ -76,25 +96,13 @@ static __device__ __noinline__ void batch_core(WarpAcc* __restrict__ acc, int cn
     return;
 #endif
     const bool active = lane < cnt;
-    const bool is_exit = active && (w & B200BT_EVENT_EXIT);
     float p_prev = __shfl_up_sync(FULL, pf, 1);
     unsigned w_prev = __shfl_up_sync(FULL, w, 1);
     if (lane == 0) { p_prev = p_carry; w_prev = w_carry; }
     const unsigned bar = w & 0x3fffffffu;
 
-    double pnl = 0.0;
-    int dur = 0;
-    if (active) {
-        if (is_exit) {
-            const double e = (double)p_prev, px = (double)pf;
-            const double qty = __ddiv_rn(acc->size, e);
-            const double diff = (w_prev & B200BT_EVENT_SELL) ? __dsub_rn(e, px) : __dsub_rn(px, e);
-            pnl = __dsub_rn(__dmul_rn(qty, diff), acc->fee2);
-            dur = (int)(bar - (w_prev & 0x3fffffffu));
-        } else {
-            pnl = -acc->fee1;
-        }
-    }
+    int dur;
+    const double pnl = record_pnl(active, w, pf, w_prev, p_prev, acc->size, acc->fee1, acc->fee2, dur);
     // wins / losses
     const bool win = active && pnl > 0.0, loss = active && pnl < 0.0;
     const unsigned n_win = acc->n_win + __popc(__ballot_sync(FULL, win));
@@ -142,6 +150,13 @@ static __device__ __noinline__ void batch_core(WarpAcc* __restrict__ acc, int cn
     // calendar day of a record, relative to bar 0's day (32-bit: the host checks N*bar_minutes < 2^31 - 1440)
     const int day = active ? (int)(((unsigned)minute0 + bar * (unsigned)bar_minutes) / 1440u) : 0;
     DayAcc da{acc->pivot, acc->s1, acc->s2, acc->n_days, acc->pivot_set};
+    const int hold_first = acc->hold_first;
+    int first_done = acc->first_done, first_id = acc->first_day;
+    double first_sum = acc->first_sum;
+    auto finish_day = [&](int id, double x) {
+        if (hold_first && !first_done) { first_done = 1; first_id = id; first_sum = x; }
+        else day_complete(da, x);
+    };
     const int day_valid = acc->day_valid;
     const int day_cur = (int)acc->day_cur;
     double day_sum = acc->day_sum;
@@ -172,11 +187,11 @@ static __device__ __noinline__ void batch_core(WarpAcc* __restrict__ acc, int cn
         unsigned done = __ballot_sync(FULL, tail && !last_seg_tail);
         // ... plus the carried day when the batch starts on a later day;
         // fold in time order (carry first, then lanes ascending)
-        if (day_valid && !merge_carry) day_complete(da, day_sum);
+        if (day_valid && !merge_carry) finish_day(day_cur, day_sum);
         while (done) {
             const int j = __ffs(done) - 1;
             done &= done - 1;
-            day_complete(da, shfl_d(x, j));
+            finish_day(__shfl_sync(FULL, day, j), shfl_d(x, j));
         }
         day_sum = shfl_d(seg, cnt - 1);
     }
@@ -200,6 +215,7 @@ static __device__ __noinline__ void batch_core(WarpAcc* __restrict__ acc, int cn
         acc->equity = equity_out; acc->peak = peak_out; acc->maxdd = maxdd;
         acc->pivot = da.pivot; acc->s1 = da.s1; acc->s2 = da.s2; acc->n_days = da.n_days; acc->pivot_set = da.pivot_set;
         acc->day_sum = day_sum; acc->day_cur = last_day; acc->day_valid = 1;
+        acc->first_done = first_done; acc->first_day = first_id; acc->first_sum = first_sum;
         acc->hash ^= ((unsigned long long)hhi << 32) | hlo;
         acc->n_events = n_events + cnt;
     }
@@ -273,6 +289,8 @@ __device__ __forceinline__ void init_acc(WarpAcc& a, const b200bt_individual& iv
     a.ev_out = ev_out;
     a.n_win = a.n_loss = a.n_days = a.n_events = 0;
     a.day_valid = a.pivot_set = 0;
+    a.hold_first = a.first_done = a.first_day = 0;
+    a.first_sum = 0.0;
 }
 
 __device__ __forceinline__ void init_scan_const(ScanConst& c, const b200bt_individual& iv) {
