@@ -12,8 +12,15 @@ constexpr int SW_WARPS = 8;         // warps (lanes of the sweep) per CTA
 #define B200BT_SW_MIN_BLOCKS 2
 #endif
 constexpr int SW_MIN_BLOCKS = B200BT_SW_MIN_BLOCKS;    // CTAs per SM the register budget is held to (<= 64 regs/thread)
-constexpr int SW_GROUP = 256;       // bars per cp.async group (per stream)
-constexpr int SW_STAGES = 3;        // shared-memory ring depth per warp
+#ifndef B200BT_SW_GROUP
+#define B200BT_SW_GROUP 512
+#endif
+#ifndef B200BT_SW_STAGES
+#define B200BT_SW_STAGES 2
+#endif
+// 512 bars x 2 stages measured best on the C2 workload (256x3: +5 %, 128x4: +18 %; tools/build_variant.py)
+constexpr int SW_GROUP = B200BT_SW_GROUP;     // bars per cp.async group (per stream)
+constexpr int SW_STAGES = B200BT_SW_STAGES;   // shared-memory ring depth per warp
 constexpr int SW_EVQ = 128;         // event queue entries per warp (>= 32 + 64 new events per window pair)
 constexpr float SW_MARGIN = 1e-6f;  // relative width of the fp32 screening band
 

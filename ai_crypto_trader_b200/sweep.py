@@ -143,15 +143,22 @@ def lane_cost(p: Dict) -> float:
 EVENTS_PER_COST_BAR = 0.27
 
 
+def predicted_events(population: List[Dict], n_bars: int) -> np.ndarray:
+    """Expected trade records per (individual, symbol) lane under the lane_cost model."""
+    return EVENTS_PER_COST_BAR * np.array([lane_cost(p) for p in population]) * n_bars
+
+
 class ChunkPlan:
     """Host-side plan of the time-chunked sweep for one population (device tensors inside)."""
 
     def __init__(self, population: List[Dict], n_bars: int, n_symbols: int, device, target_events: int = 16384,
                  warm: int = 8192, max_chunks: int = 64, pool_scale: float = 1.5, pool_blocks: Optional[int] = None,
-                 max_repair_rounds: int = 8):
+                 max_repair_rounds: int = 8, lo: int = 0, workspace: Optional[torch.Tensor] = None):
+        """`population` is the slice [lo, lo + len) of the caller's population (individual indices inside the
+        plan are slice-relative); `workspace` may be shared between the plans of successive slices."""
         pop = len(population)
-        cost = np.array([lane_cost(p) for p in population])
-        pred = EVENTS_PER_COST_BAR * cost * n_bars
+        self.lo = int(lo)
+        pred = predicted_events(population, n_bars)
         kmax = max(1, min(max_chunks, n_bars // max(8 * warm, 2048)))
         k = np.clip(np.ceil(pred / target_events), 1, kmax).astype(np.int32)
         self.n_chunks = k
@@ -176,7 +183,10 @@ class ChunkPlan:
         self.n_chunks_dev = torch.from_numpy(self.n_chunks).to(device)
         self.order_dev = torch.from_numpy(self.order).to(device)
         ws_bytes = int(_lib.load().b200bt_sweep_chunked_workspace_bytes(self.pool_blocks, n_symbols, self.n_seg))
-        self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        if workspace is not None and workspace.numel() >= ws_bytes:
+            self.workspace = workspace
+        else:
+            self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
         self.invalid = torch.zeros((pop, n_symbols), dtype=torch.uint8, device=device)
         self.overflow = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.pop = pop
@@ -252,8 +262,17 @@ class PopulationSweep:
                         fitness_dev: torch.Tensor, plan: Optional["ChunkPlan"] = None) -> None:
         """Sweep + fitness reduction on the current stream.  With a ChunkPlan the time-chunked kernels
         run first and only lanes whose chunk boundaries failed verification go through the fused kernel."""
+        self._inverse = None
         if plan is not None:
-            return self._evaluate_chunked(indiv_dev, pop, fitness_dev, plan)
+            plans = plan if isinstance(plan, (list, tuple)) else [plan]
+            self._ensure_buffers(pop)
+            self.last_invalid_lanes, self.last_pool_overflow = 0, False
+            for pl in plans:
+                self._evaluate_chunked(indiv_dev, pl)
+            with torch.cuda.device(self.market.device):
+                _lib.call("b200bt_fitness_reduce", self._stats.data_ptr(), pop, self.market.S, fitness_dev.data_ptr(),
+                          _lib.current_stream())
+            return
         m = self.market
         if self._stats is None or self._pop != pop:
             self._stats = torch.empty((pop, m.S, 16), dtype=torch.float64, device=m.device)
@@ -276,43 +295,81 @@ class PopulationSweep:
                             if self.event_cap else None)
             self._pop = pop
 
-    def _evaluate_chunked(self, indiv_dev, pop, fitness_dev, plan: "ChunkPlan") -> None:
+    def _evaluate_chunked(self, indiv_dev, plan: "ChunkPlan") -> None:
+        """One slice [plan.lo, plan.lo + plan.pop) of the population through the chunked kernels; lanes whose
+        chunk boundaries failed verification are re-evaluated by the fused kernel."""
         m = self.market
-        self._ensure_buffers(pop)
+        lo, n = plan.lo, plan.pop
+        stats = self._stats[lo:lo + n]
+        events = self._events[lo:lo + n] if self._events is not None else None
         with torch.cuda.device(m.device):
             st = _lib.current_stream()
             _lib.call("b200bt_sweep_chunked", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
-                      len(self.periods), m.S, m.N, indiv_dev.data_ptr(), plan.order_dev.data_ptr(), pop,
+                      len(self.periods), m.S, m.N, indiv_dev.data_ptr() + lo * C.sizeof(_lib.Individual),
+                      plan.order_dev.data_ptr(), n,
                       plan.items.data_ptr(), plan.n_seg, plan.seg_base_dev.data_ptr(), plan.n_chunks_dev.data_ptr(),
                       plan.n_seg, plan.warm, plan.max_repair_rounds, plan.pool_blocks, plan.workspace.data_ptr(), plan.workspace.numel(),
-                      C.byref(self.cfg), self._stats.data_ptr(), _lib.ptr(self._events), self.event_cap,
+                      C.byref(self.cfg), stats.data_ptr(), _lib.ptr(events), self.event_cap,
                       plan.invalid.data_ptr(), plan.overflow.data_ptr(), st)
             bad = torch.nonzero(plan.invalid.any(dim=1)).flatten()          # device -> host sync (tiny)
-            self.last_invalid_lanes = int(plan.invalid.sum().item())
-            self.last_pool_overflow = bool(plan.overflow.item())
+            self.last_invalid_lanes += int(plan.invalid.sum().item())
+            self.last_pool_overflow |= bool(plan.overflow.item())
             if bad.numel():
-                redo = bad.to(torch.int32).contiguous()
+                redo = (bad + lo).to(torch.int32).contiguous()
                 _lib.call("b200bt_sweep", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
                           len(self.periods), m.S, m.N, indiv_dev.data_ptr(), redo.data_ptr(), int(redo.numel()),
                           C.byref(self.cfg), self._stats.data_ptr(), _lib.ptr(self._events), self.event_cap, st)
-            _lib.call("b200bt_fitness_reduce", self._stats.data_ptr(), pop, m.S, fitness_dev.data_ptr(), st)
 
     def plan_chunks(self, population: List[Dict], **kw) -> "ChunkPlan":
         return ChunkPlan(population, self.market.N, self.market.S, self.market.device, **kw)
+
+    def plan_batches(self, population: List[Dict], max_pool_bytes: int = 8 << 30, **kw) -> List["ChunkPlan"]:
+        """Plans for contiguous slices of the population whose event pools each stay below `max_pool_bytes`
+        and share one workspace: large populations (BASELINE configs[4]: 10 000 x 50 symbols) record more
+        events than fit in HBM at once, so they go through the chunked kernels slice by slice."""
+        if kw.get("pool_blocks") is not None:
+            return [self.plan_chunks(population, **kw)]
+        pred = predicted_events(population, self.market.N) * self.market.S * 8 * kw.get("pool_scale", 1.5)
+        cuts, acc = [0], 0.0
+        for i, b in enumerate(pred):
+            if acc + b > max_pool_bytes and i > cuts[-1]:
+                cuts.append(i)
+                acc = 0.0
+            acc += b
+        cuts.append(len(population))
+        if len(cuts) == 2:
+            return [self.plan_chunks(population, **kw)]
+        plans, shared = [], None
+        for lo, hi in sorted(zip(cuts[:-1], cuts[1:]), key=lambda c: -float(pred[c[0]:c[1]].sum())):
+            pl = ChunkPlan(population[lo:hi], self.market.N, self.market.S, self.market.device, lo=lo, workspace=shared, **kw)
+            shared = shared if shared is not None else pl.workspace     # the largest slice is planned first
+            plans.append(pl)
+        return sorted(plans, key=lambda pl: pl.lo)
 
     # -- host-facing evaluation --------------------------------------------
     def evaluate(self, population: List[Dict]) -> np.ndarray:
         """fitness (float64[pop]) of a list of parameter dicts; H2D of the decoded
         population and D2H of the fitness vector happen inside this call."""
-        pop = len(population)
         dev = self.market.device
         packed = decode_population(population, self.period_row)
+        # individuals that decode to the same kernel parameters (the reference rule reads 6 of the 18 genes,
+        # and elitism / crossover copy individuals) are evaluated once
+        uniq, first, inverse = np.unique(packed, return_index=True, return_inverse=True)
+        expand = None
+        if len(uniq) < len(packed):
+            keep = np.sort(first)                       # unique individuals in population order
+            rank = np.empty(len(first), dtype=np.int64)
+            rank[np.argsort(first)] = np.arange(len(first))
+            expand = rank[inverse.reshape(-1)]
+            packed = np.ascontiguousarray(packed[keep])
+            population = [population[i] for i in keep]
+        self.last_unique = len(population)
+        pop = len(population)
         order = evaluation_order(population)
         nbytes = packed.nbytes
         if self._pinned_in is None or self._pinned_in.numel() < nbytes + order.nbytes:
             self._pinned_in = torch.empty(nbytes + order.nbytes, dtype=torch.uint8, pin_memory=True)
-            self._pinned_out = torch.empty(pop, dtype=torch.float64, pin_memory=True)
-        if self._pinned_out.numel() < pop:
+        if self._pinned_out is None or self._pinned_out.numel() < pop:
             self._pinned_out = torch.empty(pop, dtype=torch.float64, pin_memory=True)
         hin = self._pinned_in.numpy()
         hin[:nbytes] = packed.view(np.uint8)
@@ -323,22 +380,26 @@ class PopulationSweep:
         fit = torch.empty(pop, dtype=torch.float64, device=dev)
         plan = None
         if self.mode == "chunked" or (self.mode == "auto" and self.market.N >= self.chunk_min_bars):
-            plan = self.plan_chunks(population, **self.chunk_options)
+            plan = self.plan_batches(population, **self.chunk_options)
             if getattr(self, "last_pool_overflow", False):
                 grown = dict(self.chunk_options, pool_scale=4.0 * self.chunk_options.get("pool_scale", 1.5))
                 grown.pop("pool_blocks", None)
-                plan = self.plan_chunks(population, **grown)
+                plan = self.plan_batches(population, **grown)
         self.evaluate_device(indiv_dev, order_dev, pop, fit, plan=plan)
+        self._inverse = expand
         out = self._pinned_out[:pop]
         out.copy_(fit, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         self.h2d_bytes = nbytes + order.nbytes
         self.d2h_bytes = pop * 8
-        return out.numpy().copy()
+        res = out.numpy().copy()
+        return res if self._inverse is None else res[self._inverse]
 
     def lane_stats(self) -> Dict[str, np.ndarray]:
         """Per-lane metrics of the last evaluation: dict field -> [pop][S] array."""
         raw = self._stats.cpu().numpy()
+        if getattr(self, "_inverse", None) is not None:
+            raw = raw[self._inverse]
         out = {name: raw[:, :, i] for i, name in enumerate(_lib.LANE_STATS_FIELDS[:-1])}
         out["trade_hash"] = np.ascontiguousarray(raw[:, :, 15]).view(np.uint64)
         return out
@@ -347,7 +408,8 @@ class PopulationSweep:
         """First `event_cap` event words per lane, uint32 [pop][S][cap] (see B200BT_EVENT_*)."""
         if self._events is None:
             return None
-        return self._events.cpu().numpy().view(np.uint32)
+        ev = self._events.cpu().numpy().view(np.uint32)
+        return ev if getattr(self, "_inverse", None) is None else ev[self._inverse]
 
     @property
     def fitness_function(self):

@@ -317,6 +317,28 @@ int b200bt_select(const float* x, int64_t n, const int64_t* ranks_dev, int n_ran
 int b200bt_mc_moments(const float* finals, const float* maxdd, int64_t n, double s0,
                       double var_threshold, double* out7, b200bt_stream_t stream);
 
+/* ---- portfolio risk -------------------------------------------------------------------
+ * Replaces the numeric core of services/portfolio_risk_service.py. */
+
+/* Simple returns, df['close'].pct_change() (portfolio_risk_service.py:208): out[s][0] = NaN,
+ * out[s][t] = close[s][t]/close[s][t-1] - 1 in float64, stored fp32.  close, out: device [S][ld]. */
+int b200bt_pct_change(const float* close, int64_t ld, int S, int64_t N, float* out, int64_t ld_out,
+                      b200bt_stream_t stream);
+
+/* Tail sums for historical CVaR (calculate_conditional_var :248-284), NaN entries skipped (dropna):
+ * out4 (device, float64) = [ sum x[x <= threshold], #(x <= threshold), #(non-NaN), sum non-NaN ].
+ * Deterministic (fixed-order fold of per-CTA partials). */
+int64_t b200bt_tail_stats_workspace_bytes(int64_t n);
+int b200bt_tail_stats(const float* x, int64_t n, double threshold, double* out4, void* workspace,
+                      int64_t workspace_bytes, b200bt_stream_t stream);
+
+/* Pearson correlation matrix of S return rows (calculate_asset_correlation :286-326, pandas
+ * DataFrame.corr(): pairwise-complete observations, NaN = missing; NaN out for <1 joint observation or zero
+ * variance).  x: device [S][ld] fp32, out: device float64 [S][S], S <= 512. */
+int64_t b200bt_correlation_workspace_bytes(int S, int64_t N);
+int b200bt_correlation(const float* x, int64_t ld, int S, int64_t N, double* out, void* workspace,
+                       int64_t workspace_bytes, b200bt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,20 @@ def genetic_algorithm_class():
     return GeneticAlgorithm
 
 
+def portfolio_risk_service():
+    """A PortfolioRiskService built without __init__ (Redis / Binance clients, portfolio_risk_service.py:47-110);
+    only the pure numeric methods (:217-396) are used."""
+    _prepare()
+    import logging
+    from services.portfolio_risk_service import PortfolioRiskService
+    logging.getLogger().setLevel(logging.ERROR)
+    svc = object.__new__(PortfolioRiskService)
+    svc.historical_data = {}
+    svc.asset_correlations = {}
+    svc.risk_config = {}
+    return svc
+
+
 def monte_carlo_service(mc_params: dict):
     """A MonteCarloService built without __init__ (which needs Binance keys and
     rewrites config.json, monte_carlo_service.py:47-108)."""

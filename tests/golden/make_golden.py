@@ -10,6 +10,7 @@ Writes (all small, committed):
     tests/golden/ga_run.json      seeded GeneticAlgorithm trajectory
     tests/golden/mc_reference.*   MonteCarloService results + its own paths (NumPy seed fixed)
     tests/golden/bt_reference.*   StrategyTester.backtest_strategy runs (LLM stubbed, `ta` shimmed)
+    tests/golden/pf_reference.json PortfolioRiskService VaR / CVaR / correlation / portfolio VaR
 Inputs are the fp32 synthetic series of ai_crypto_trader_b200.synth; the RSI
 bank is oracle.indicators_ref.rsi_bank (float64 pandas, rounded to fp32).
 The reference functions executed are
@@ -243,8 +244,49 @@ def make_bt():
     (OUT / "bt_reference.json").write_text(json.dumps({"cases": meta}, indent=1))
 
 
+def make_pf():
+    """Reference PortfolioRiskService.calculate_var / calculate_conditional_var / calculate_asset_correlation /
+    calculate_portfolio_var (services/portfolio_risk_service.py:217-396) on the synthetic closes (fp32 values
+    held in float64 frames, as the other fixtures)."""
+    import pandas as pd
+    svc = ref_runner.portfolio_risk_service()
+    S, N = 6, 5000
+    ohlcv = synth.synth_ohlcv(S, N)
+    close = ohlcv[3].astype(np.float64)
+    # make the series co-move a little (the synthetic symbols are independent) and punch holes into one of them
+    close[1] = close[1] * (close[0] / close[0][0]) ** 0.5
+    close[2] = close[2] * (close[0][0] / close[0]) ** 0.25
+    close = close.astype(np.float32).astype(np.float64)
+    symbols = [f"S{i}USDC" for i in range(S)]
+    frames = {}
+    for i, sym in enumerate(symbols):
+        df = pd.DataFrame({"close": close[i]})
+        df["returns"] = df["close"].pct_change()
+        frames[sym] = df
+    holes = [100, 101, 2500, 4999]
+    frames[symbols[3]].loc[holes, "returns"] = np.nan
+    svc.historical_data = frames
+    out = {"S": S, "N": N, "symbols": symbols, "holes": holes, "var": {}, "cvar": {}}
+    for conf in (0.95, 0.99, 0.9):
+        out["var"][str(conf)] = [svc.calculate_var(frames[s]["returns"], conf, 1000.0) for s in symbols]
+        out["cvar"][str(conf)] = [svc.calculate_conditional_var(frames[s]["returns"], conf, 1000.0) for s in symbols]
+    corr = svc.calculate_asset_correlation(symbols)
+    out["correlation"] = [[float(corr[a][b]) for b in symbols] for a in symbols]
+    svc.asset_correlations = corr
+    values = [1200.0, 800.0, 50.0, 3000.0, 10.0, 440.0]
+    holdings = {"assets": {s.replace("USDC", ""): {"value_usdc": v} for s, v in zip(symbols, values)}, "total_value": 6000.0}
+    holdings["assets"]["USDC"] = {"value_usdc": 500.0}
+    svc.asset_correlations = {a.replace("USDC", ""): {b.replace("USDC", ""): corr[a][b] for b in symbols} for a in symbols}
+    var_est = {s.replace("USDC", ""): v / 1000.0 for s, v in zip(symbols, out["var"]["0.95"])}
+    out["holdings_values"] = values
+    out["portfolio_var"] = float(svc.calculate_portfolio_var(holdings, var_est))
+    out["close_transform"] = "close[1] *= (close[0]/close[0][0])**0.5; close[2] *= (close[0][0]/close[0])**0.25; rounded to fp32"
+    (OUT / "pf_reference.json").write_text(json.dumps(out, indent=1))
+    print("PF: var95", out["var"]["0.95"][:3], "corr01", out["correlation"][0][1], "pvar", out["portfolio_var"])
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sim", "ga", "mc", "bt"]
+    which = sys.argv[1:] or ["sim", "ga", "mc", "bt", "pf"]
     if "sim" in which:
         make_sim()
     if "ga" in which:
@@ -253,3 +295,5 @@ if __name__ == "__main__":
         make_mc()
     if "bt" in which:
         make_bt()
+    if "pf" in which:
+        make_pf()

@@ -229,3 +229,35 @@ def test_chunked_sweep_is_exact_and_self_repairing(torch_cuda, n_bars, opts):
     _check_lanes_vs_oracle(chunked, population, ohlcv, cap)
     np.testing.assert_array_equal(chunked.lane_stats()["trade_hash"], fused.lane_stats()["trade_hash"])
     np.testing.assert_allclose(f_c, f_f, rtol=1e-9, atol=1e-11)
+
+
+def test_chunked_sweep_in_population_slices_with_duplicates(torch_cuda):
+    """Large populations go through the chunked kernels slice by slice (shared workspace) and identical
+    individuals are evaluated once: results are those of the plain fused sweep, in population order."""
+    from ai_crypto_trader_b200 import synth
+    from ai_crypto_trader_b200.sweep import MarketData, PopulationSweep
+    n_bars = 180_000
+    ohlcv = synth.synth_ohlcv(2, n_bars, first_symbol=2)
+    market = MarketData(ohlcv)
+    cap = 1024
+    population = synth.random_population(48, seed=77)
+    population[5].update(rsi_oversold=35, rsi_overbought=65, rsi_period=5, take_profit=1, stop_loss=1)
+    population += [dict(population[5]), dict(population[0], macd_fast=9, ema_long=77), dict(population[5], atr_period=9)]
+    opts = dict(target_events=1500, warm=2048, max_pool_bytes=200_000)
+    chunked = PopulationSweep(market, event_cap=cap, mode="chunked", chunk_options=opts)
+    fused = PopulationSweep(market, event_cap=cap, mode="fused")
+    plans = chunked.plan_batches(population[:48], **opts)
+    assert len(plans) > 2 and [p.lo for p in plans] == sorted(p.lo for p in plans)
+    assert sum(p.pop for p in plans) == 48 and all(p.workspace.data_ptr() == plans[0].workspace.data_ptr() or
+                                                  p.workspace.numel() <= max(q.workspace.numel() for q in plans) for p in plans)
+    f_c = chunked.evaluate(population)
+    assert chunked.last_unique == 48 and len(f_c) == 51
+    f_f = fused.evaluate(population)
+    assert fused.last_unique == 48
+    np.testing.assert_allclose(f_c, f_f, rtol=1e-9, atol=1e-11)
+    assert f_c[48] == f_c[5] and f_c[49] == f_c[0] and f_c[50] == f_c[5]
+    sc, sf = chunked.lane_stats(), fused.lane_stats()
+    assert sc["trade_hash"].shape == (51, 2)
+    np.testing.assert_array_equal(sc["trade_hash"], sf["trade_hash"])
+    np.testing.assert_array_equal(chunked.events(), fused.events())
+    _check_lanes_vs_oracle(chunked, population, ohlcv, cap)

@@ -29,7 +29,9 @@ for _ in range(2): sw.evaluate_device(indiv, order, POP, fit)
 torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); [sw.evaluate_device(indiv, order, POP, fit) for _ in range(3)]; e1.record(); torch.cuda.synchronize()
 ref = fit.clone(); print("fused %.2f ms" % (e0.elapsed_time(e1) / 3))
-for target, warm in itertools.product((2048, 4096, 8192, 16384), (2048, 4096, 8192)):
+targets = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else (2048, 4096, 8192, 16384)
+warms = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else (2048, 4096, 8192)
+for target, warm in itertools.product(targets, warms):
     plan = sw.plan_chunks(pop, target_events=target, warm=warm)
     ms = timed(plan)
-    print(f"target_events {target:6d} warm {warm:5d}: {ms:6.2f} ms  items {plan.n_seg:5d}  max K {int(plan.n_chunks.max()):3d}  invalid lanes {sw.last_invalid_lanes:4d}  same {bool(torch.equal(ref, fit))}")
+    print(f"target_events {target:6d} warm {warm:5d}: {ms:6.2f} ms  items {plan.n_seg:5d}  max K {int(plan.n_chunks.max()):3d}  invalid lanes {sw.last_invalid_lanes:4d}  close {bool(torch.allclose(ref, fit, rtol=1e-9, atol=1e-12, equal_nan=True))}")
