@@ -66,7 +66,7 @@ sweep_kernel(const float* __restrict__ price, int64_t ld_price,
 
     Machine m;
     m.pos = 0; m.e = 0.f;
-    m.rlo = iv.rsi_lo; m.rhi = iv.rsi_hi; m.plo = m.plo_d = -INFINITY; m.phi = m.phi_d = INFINITY;
+    m.rlo = iv.rsi_lo; m.rhi = iv.rsi_hi; m.plo = -INFINITY; m.phi = INFINITY;
     m.qhead = 0; m.entry_bar = 0;
     const ScanConst c = ws->sc;                // warp-uniform constants of the scan, kept in registers
     unsigned qtail = 0;

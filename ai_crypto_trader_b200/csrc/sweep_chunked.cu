@@ -86,7 +86,7 @@ chunk_scan_kernel(const ChunkScanArgs A) {   // by value, not __grid_constant__ 
 
     Machine m;
     m.pos = 0; m.e = 0.f; m.entry_bar = 0;
-    m.rlo = iv.rsi_lo; m.rhi = iv.rsi_hi; m.plo = m.plo_d = -INFINITY; m.phi = m.phi_d = INFINITY;
+    m.rlo = iv.rsi_lo; m.rhi = iv.rsi_hi; m.plo = -INFINITY; m.phi = INFINITY;
     m.qhead = 0;
     unsigned qtail = 0;
     if (REPAIR) {
@@ -97,10 +97,10 @@ chunk_scan_kernel(const ChunkScanArgs A) {   // by value, not __grid_constant__ 
             m.pos = z.x; m.e = e; m.entry_bar = z.y;
             if (z.x > 0) {
                 m.rlo = -INFINITY; m.rhi = c.ob_f;
-                m.phi = e * c.hiL_c; m.plo = e * c.loL_c; m.phi_d = e * c.hiL_d; m.plo_d = e * c.loL_d;
+                m.phi = e * c.hiL_c; m.plo = e * c.loL_c;
             } else {
                 m.rlo = c.os_f; m.rhi = INFINITY;
-                m.phi = e * c.hiS_c; m.plo = e * c.loS_c; m.phi_d = e * c.hiS_d; m.plo_d = e * c.loS_d;
+                m.phi = e * c.hiS_c; m.plo = e * c.loS_c;
             }
         }
     }

@@ -329,7 +329,6 @@ struct Machine {
     int pos;                                   // 0 flat, +1 long, -1 short
     float e;                                   // entry price
     float rlo, rhi, plo, phi;                  // event thresholds of the current state (screening bounds)
-    float plo_d, phi_d;                        // "definite exit" price bounds of the open position
     int entry_bar;                             // bar of the open position's entry (chunk-boundary check)
     unsigned qhead;                            // events pushed so far (queue head)
 };
@@ -350,42 +349,46 @@ __device__ __forceinline__ void scan_window(const float p, const float r, const 
         const int kk = __ffs(hit) - 1;
         const float pk = __shfl_sync(FULL, p, kk);
         const float rk = __shfl_sync(FULL, r, kk);
-        live = (kk == 31) ? 0u : (FULL << (kk + 1));
+        live = 0xfffffffeu << kk;
+        const unsigned bar = (unsigned)(t0 + kk);
         unsigned word;
+        bool ev = true;
         if (m.pos == 0) {
             // entry (strategy_evaluation.py:784-813): long has priority over short
+            const bool lng = rk < c.os_f;
             m.e = pk;
-            m.entry_bar = t0 + kk;
-            if (rk < c.os_f) {
-                m.pos = 1;
-                m.rlo = -INFINITY; m.rhi = c.ob_f;
-                m.phi = pk * c.hiL_c; m.plo = pk * c.loL_c;
-                m.phi_d = pk * c.hiL_d; m.plo_d = pk * c.loL_d;
-                word = (unsigned)(t0 + kk);
-            } else {
-                m.pos = -1;
-                m.rlo = c.os_f; m.rhi = INFINITY;
-                m.phi = pk * c.hiS_c; m.plo = pk * c.loS_c;
-                m.phi_d = pk * c.hiS_d; m.plo_d = pk * c.loS_d;
-                word = (unsigned)(t0 + kk) | B200BT_EVENT_SELL;
-            }
+            m.entry_bar = (int)bar;
+            m.pos = lng ? 1 : -1;
+            m.rlo = lng ? -INFINITY : c.os_f;
+            m.rhi = lng ? c.ob_f : INFINITY;
+            m.phi = pk * (lng ? c.hiL_c : c.hiS_c);
+            m.plo = pk * (lng ? c.loL_c : c.loS_c);
+            word = lng ? bar : (bar | B200BT_EVENT_SELL);
         } else {
-            // exit candidate (:815-847)
-            const bool definite = (rk < m.rlo) || (rk > m.rhi) || (pk >= m.phi_d) || (pk <= m.plo_d);
-            if (!definite) {
-                // inside the fp32 screening band: decide with the reference's float64 expression
-                const double ed = (double)m.e, pd = (double)pk;
-                const double q = (m.pos > 0) ? __ddiv_rn(__dsub_rn(pd, ed), ed) : __ddiv_rn(__dsub_rn(ed, pd), ed);
-                if (!(q >= ws->acc.tp || q <= -ws->acc.sl)) continue;
+            // exit candidate (:815-847); an RSI reversal is always definite, a price trigger inside the
+            // fp32 screening band is decided with the reference's float64 expression
+            if (!((rk < m.rlo) || (rk > m.rhi))) {
+                const bool lng = m.pos > 0;
+                const float hd = m.e * (lng ? c.hiL_d : c.hiS_d), ld = m.e * (lng ? c.loL_d : c.loS_d);
+                if (!((pk >= hd) || (pk <= ld))) {
+                    const double ed = (double)m.e, pd = (double)pk;
+                    const double q = lng ? __ddiv_rn(__dsub_rn(pd, ed), ed) : __ddiv_rn(__dsub_rn(ed, pd), ed);
+                    ev = (q >= ws->acc.tp) || (q <= -ws->acc.sl);
+                }
             }
-            word = (unsigned)(t0 + kk) | B200BT_EVENT_EXIT | (m.pos > 0 ? B200BT_EVENT_SELL : 0u);
-            m.pos = 0;
-            m.rlo = c.os_f; m.rhi = c.ob_f;
-            m.plo = -INFINITY; m.phi = INFINITY;
+            if (ev) {
+                word = bar | B200BT_EVENT_EXIT | (m.pos > 0 ? B200BT_EVENT_SELL : 0u);
+                m.pos = 0;
+                m.rlo = c.os_f; m.rhi = c.ob_f;
+                m.plo = -INFINITY; m.phi = INFINITY;
+            }
         }
-        if (!emit) continue;
-        if (lane == 0) ws->evq[m.qhead & (SW_EVQ - 1)] = make_uint2(word, __float_as_uint(pk));
-        ++m.qhead;
+        if (ev) {
+            // every lane stores the same word to the same slot (one wavefront); while not recording, the
+            // head does not advance and the slot is simply overwritten by the next event
+            ws->evq[m.qhead & (SW_EVQ - 1)] = make_uint2(word, __float_as_uint(pk));
+            m.qhead += emit ? 1u : 0u;
+        }
     }
 }
 
