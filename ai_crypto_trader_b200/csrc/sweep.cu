@@ -132,8 +132,8 @@ sweep_kernel(const float* __restrict__ price, int64_t ld_price,
             const unsigned h0 = __ballot_sync(FULL, fires(m, p0, r0));
             const unsigned h1 = __ballot_sync(FULL, fires(m, p1, r1));
             if (h0 | h1) {
-                if (h0) scan_window(p0, r0, t0, lane, ws, c, m);
-                scan_window(p1, r1, t0 + 32, lane, ws, c, m);
+                if (h0) scan_window(p0, r0, w - lane, t0, ws, c, m);
+                scan_window(p1, r1, w - lane + 32, t0 + 32, ws, c, m);
                 while (m.qhead - qtail >= 32) {
                     __syncwarp();
                     process_batch(ws, qtail, 32, minute0, bar_minutes, ev_cap);

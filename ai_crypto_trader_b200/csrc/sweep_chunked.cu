@@ -184,8 +184,8 @@ chunk_scan_kernel(const ChunkScanArgs A) {   // by value, not __grid_constant__ 
             const unsigned h0 = __ballot_sync(FULL, fires(m, p0, r0));
             const unsigned h1 = __ballot_sync(FULL, fires(m, p1, r1));
             if (h0 | h1) {
-                if (h0) scan_window(p0, r0, t0, lane, ws, c, m, emit);
-                scan_window(p1, r1, t0 + 32, lane, ws, c, m, emit);
+                if (h0) scan_window(p0, r0, w - lane, t0, ws, c, m, emit);
+                scan_window(p1, r1, w - lane + 32, t0 + 32, ws, c, m, emit);
                 while (m.qhead - qtail >= 32) {
                     __syncwarp();
                     flush(32);
@@ -211,6 +211,176 @@ chunk_scan_kernel(const ChunkScanArgs A) {   // by value, not __grid_constant__ 
     __syncwarp();
     while (m.qhead != qtail) flush((int)min(32u, m.qhead - qtail));
     if (lane == 0) A.seg_count[seg] = dead ? 0xffffffffu : m.qhead;
+}
+
+// ---- thread-per-lane scan ---------------------------------------------------------------------------
+// The warp-per-lane scan above spends a full warp on the scalar event chain of one lane.  With every lane cut
+// into the SAME K time chunks there are pop x S x K independent machines -- enough to give each one a THREAD:
+// a CTA owns (symbol, chunk, 256 individuals), streams tiles of the price row and the whole RSI bank of that
+// symbol through shared memory (cp.async, two stages) and every thread steps its own machine through the tile,
+// four bars per step.  The event path then runs in SIMT fashion for up to 32 lanes at once, all threads walk
+// the same bars (no tail), and the bank is fetched once per 256 lanes.  Events go to the same pool / segment
+// tables as the warp scan, so verification, repair and the metrics kernels are shared.
+constexpr int LS_T = 128;               // bars per tile
+constexpr int LS_STRIDE = LS_T + 4;     // row stride in floats (16-byte aligned rows, rows 8 apart share banks)
+constexpr int LS_THREADS = 256;
+
+struct LaneScanArgs {
+    const float* price; int64_t ld_price;
+    const float* rsi; int64_t ld_rsi;
+    int P, S; int64_t N;
+    const b200bt_individual* indiv; const int32_t* order; int pop; int K; int warm;
+    uint2* pool; int pool_blocks; int* next; unsigned* alloc;
+    int* seg_first; unsigned* seg_count; int2* seg_in; int2* seg_out; int* overflow;
+};
+
+// device-side tables the shared kernels expect: uniform K chunks per individual
+__global__ void lane_tables_kernel(int pop, int K, b200bt_chunk_item* __restrict__ items, int32_t* __restrict__ seg_base,
+                                   int32_t* __restrict__ n_chunks) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pop * K) return;
+    const int ind = i / K, c = i - ind * K;
+    b200bt_chunk_item it;
+    it.individual = ind; it.chunk = c; it.n_chunks = K; it.segment = i;
+    items[i] = it;
+    if (c == 0) { seg_base[ind] = i; n_chunks[ind] = K; }
+}
+
+template <bool VEC16>
+__global__ void __launch_bounds__(LS_THREADS, 3)
+lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (see sweep.cu)
+    extern __shared__ __align__(16) float ls_tile[];   // [2][P + 1][LS_STRIDE]
+    const int rows = A.P + 1;
+    const int sym = (int)(blockIdx.x % (unsigned)A.S);
+    const int c = (int)((blockIdx.x / (unsigned)A.S) % (unsigned)A.K);
+    const int blk = (int)(blockIdx.x / ((unsigned)A.S * (unsigned)A.K));
+    const int k = blk * LS_THREADS + (int)threadIdx.x;
+    const bool active = k < A.pop;
+    const int ind = active ? (A.order ? A.order[k] : k) : 0;
+    const b200bt_individual iv = A.indiv[ind];
+    ScanConst sc;
+    init_scan_const(sc, iv);
+    const double tp = iv.take_profit, sl = iv.stop_loss;
+    const float* __restrict__ pr = A.price + (int64_t)sym * A.ld_price;
+    const float* __restrict__ rb = A.rsi + (int64_t)sym * A.P * A.ld_rsi;
+
+    const int n = (int)A.N;
+    const int T0 = (int)chunk_begin(A.N, c, A.K);       // first recorded bar (multiple of SW_GROUP, hence of LS_T)
+    const int T1 = (int)chunk_begin(A.N, c + 1, A.K);   // end (exclusive)
+    int s0 = (c == 0) ? 0 : T0 - A.warm;
+    if (s0 < 0) s0 = 0;
+    s0 &= ~(LS_T - 1);
+    const int tl_begin = s0 / LS_T, tl_end = (T1 + LS_T - 1) / LS_T;
+    const int seg = sym * (A.pop * A.K) + ind * A.K + c;
+
+    auto load_tile = [&](int tl, int stage) {
+        float* dst0 = ls_tile + (size_t)stage * rows * LS_STRIDE;
+        const int t0 = tl * LS_T;
+        if (VEC16 && t0 + LS_T <= n) {
+            for (int e = threadIdx.x; e < rows * (LS_T / 4); e += LS_THREADS) {
+                const int row = e / (LS_T / 4), piece = e - row * (LS_T / 4);
+                const float* src = (row == 0 ? pr : rb + (int64_t)(row - 1) * A.ld_rsi) + t0 + piece * 4;
+                cp_async16(dst0 + row * LS_STRIDE + piece * 4, src);
+            }
+        } else {
+            const float qnan = __int_as_float(0x7fc00000);   // unaligned input or the ragged last tile
+            for (int e = threadIdx.x; e < rows * LS_T; e += LS_THREADS) {
+                const int row = e / LS_T, col = e - row * LS_T;
+                const float* src = (row == 0 ? pr : rb + (int64_t)(row - 1) * A.ld_rsi) + t0 + col;
+                dst0[row * LS_STRIDE + col] = (t0 + col < n) ? __ldg(src) : qnan;
+            }
+        }
+        cp_async_commit();
+    };
+
+    // machine state (per thread)
+    int pos = 0, entry_bar = 0;
+    float e_px = 0.f, rlo = iv.rsi_lo, rhi = iv.rsi_hi, plo = -INFINITY, phi = INFINITY;
+    // event sink: this thread's chunk owns a chain of pool blocks
+    int cur_block = -1, fill = CK_BLOCK, dead = 0;
+    unsigned count = 0;
+    bool rec = false;
+
+    auto emit = [&](unsigned word, float px) {
+        if (!rec) return;
+        if (fill == CK_BLOCK && !dead) {
+            const int b = (int)atomicAdd(A.alloc, 1u);
+            if (b >= A.pool_blocks) { atomicExch(A.overflow, 1); dead = 1; }
+            else {
+                A.next[b] = -1;
+                if (cur_block < 0) A.seg_first[seg] = b; else A.next[cur_block] = b;
+                cur_block = b; fill = 0;
+            }
+        }
+        if (!dead) { A.pool[(int64_t)cur_block * CK_BLOCK + fill] = make_uint2(word, __float_as_uint(px)); ++fill; }
+        ++count;
+    };
+    // one bar of the state machine; same decisions as scan_window (sweep_dev.cuh)
+    auto step = [&](float p, float r, int t) {
+        if (!((r < rlo) | (r > rhi) | (p <= plo) | (p >= phi))) return;
+        if (pos == 0) {
+            const bool lng = r < sc.os_f;                 // long has priority (:784, :799)
+            e_px = p; entry_bar = t;
+            pos = lng ? 1 : -1;
+            rlo = lng ? -INFINITY : sc.os_f;
+            rhi = lng ? sc.ob_f : INFINITY;
+            phi = p * (lng ? sc.hiL_c : sc.hiS_c);
+            plo = p * (lng ? sc.loL_c : sc.loS_c);
+            emit(lng ? (unsigned)t : ((unsigned)t | B200BT_EVENT_SELL), p);
+        } else {
+            bool ev = true;
+            if (!((r < rlo) || (r > rhi))) {
+                const bool lng = pos > 0;
+                const float hd = e_px * (lng ? sc.hiL_d : sc.hiS_d), ld = e_px * (lng ? sc.loL_d : sc.loS_d);
+                if (!((p >= hd) || (p <= ld))) {
+                    const double ed = (double)e_px, pd = (double)p;
+                    const double q = lng ? __ddiv_rn(__dsub_rn(pd, ed), ed) : __ddiv_rn(__dsub_rn(ed, pd), ed);
+                    ev = (q >= tp) || (q <= -sl);
+                }
+            }
+            if (ev) {
+                emit((unsigned)t | B200BT_EVENT_EXIT | (pos > 0 ? B200BT_EVENT_SELL : 0u), p);
+                pos = 0;
+                rlo = sc.os_f; rhi = sc.ob_f; plo = -INFINITY; phi = INFINITY;
+            }
+        }
+    };
+
+    load_tile(tl_begin, 0);
+    for (int tl = tl_begin; tl < tl_end; ++tl) {
+        const int stage = (tl - tl_begin) & 1;
+        if (tl + 1 < tl_end) load_tile(tl + 1, stage ^ 1); else cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const int t0 = tl * LS_T;
+        if (active) {
+            if (t0 == T0) { A.seg_in[seg] = make_int2(pos, pos != 0 ? entry_bar : -1); rec = true; }
+            const float4* __restrict__ pp = reinterpret_cast<const float4*>(ls_tile + (size_t)stage * rows * LS_STRIDE);
+            const float4* __restrict__ rr = reinterpret_cast<const float4*>(ls_tile + ((size_t)stage * rows + 1 + iv.rsi_row) * LS_STRIDE);
+#pragma unroll 2
+            for (int g = 0; g < LS_T / 4; ++g) {
+                const float4 p = pp[g], r = rr[g];
+                const bool any = (r.x < rlo) | (r.x > rhi) | (p.x <= plo) | (p.x >= phi) |
+                                 (r.y < rlo) | (r.y > rhi) | (p.y <= plo) | (p.y >= phi) |
+                                 (r.z < rlo) | (r.z > rhi) | (p.z <= plo) | (p.z >= phi) |
+                                 (r.w < rlo) | (r.w > rhi) | (p.w <= plo) | (p.w >= phi);
+                if (any) {
+                    const int t = t0 + g * 4;
+                    step(p.x, r.x, t);
+                    step(p.y, r.y, t + 1);
+                    step(p.z, r.z, t + 2);
+                    step(p.w, r.w, t + 3);
+                }
+            }
+        }
+        __syncthreads();   // the stage is refilled by the next iteration's load
+    }
+    cp_async_wait<0>();
+    if (!active) return;
+    A.seg_out[seg] = make_int2(pos, pos != 0 ? entry_bar : -1);
+    if (c == A.K - 1 && pos != 0)   // force-close at the last bar (:849-876)
+        emit((unsigned)(n - 1) | B200BT_EVENT_EXIT | (pos > 0 ? B200BT_EVENT_SELL : 0u), __ldg(pr + (n - 1)));
+    A.seg_count[seg] = dead ? 0xffffffffu : count;
 }
 
 // One thread per (individual, symbol): list every chunk whose assumed state differs from the end state
@@ -456,84 +626,64 @@ __global__ void lane_combine_kernel(const b200bt_individual* __restrict__ indiv,
 
 using namespace b200bt;
 
-extern "C" int64_t b200bt_sweep_chunked_workspace_bytes(int pool_blocks, int S, int n_seg) {
-    const int64_t segs = (int64_t)S * n_seg;
-    // pool[pool_blocks][256] uint2 | seg_in[segs] int2 | seg_out[segs] int2 | seg_first[segs] | seg_count[segs] |
-    // alloc, overflow, n_repair, pad | repair[segs] int4 | next[pool_blocks]   (wide types first: base 256-byte aligned)
-    // ... | partial[segs] (128 B) | seg_sum[segs] | seg_max[segs]
+namespace {
+
+struct ChunkWorkspace {
+    uint2* pool; int2* seg_in; int2* seg_out; int* seg_first; unsigned* seg_count; unsigned* alloc; int* overflow;
+    unsigned* n_repair; int4* repair; int* next; ChunkPartial* partial; double* seg_sum; double* seg_max;
+    unsigned char* end;
+};
+
+// pool[pool_blocks][256] uint2 | seg_in[segs] int2 | seg_out[segs] int2 | seg_first[segs] | seg_count[segs] |
+// alloc, overflow, n_repair, pad | repair[segs] int4 | next[pool_blocks] | (16-byte aligned) partial[segs] (128 B) |
+// seg_sum[segs] | seg_max[segs]      (wide types first: the base must be 16-byte aligned)
+ChunkWorkspace carve(void* workspace, int pool_blocks, int64_t segs) {
+    ChunkWorkspace w;
+    w.pool = (uint2*)workspace;
+    w.seg_in = (int2*)(w.pool + (int64_t)pool_blocks * CK_BLOCK);
+    w.seg_out = w.seg_in + segs;
+    w.seg_first = (int*)(w.seg_out + segs);
+    w.seg_count = (unsigned*)(w.seg_first + segs);
+    w.alloc = w.seg_count + segs;
+    w.overflow = (int*)(w.alloc + 1);
+    w.n_repair = (unsigned*)(w.overflow + 1);
+    w.repair = (int4*)(w.n_repair + 2);
+    w.next = (int*)(w.repair + segs);
+    w.partial = (ChunkPartial*)(((uintptr_t)(w.next + pool_blocks) + 15) & ~(uintptr_t)15);
+    w.seg_sum = (double*)(w.partial + segs);
+    w.seg_max = w.seg_sum + segs;
+    w.end = (unsigned char*)(w.seg_max + segs);
+    return w;
+}
+
+int64_t chunk_workspace_bytes(int pool_blocks, int64_t segs) {
     return (int64_t)pool_blocks * CK_BLOCK * 8 + segs * 16 + (segs * 2 + 4) * 4 + segs * 16 + (int64_t)pool_blocks * 4 + 16 +
            segs * (int64_t)(sizeof(ChunkPartial) + 16);
 }
 
-extern "C" int b200bt_sweep_chunked(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S,
-                                    int64_t N, const b200bt_individual* indiv, const int32_t* order, int pop,
-                                    const b200bt_chunk_item* items, int n_items, const int32_t* seg_base,
-                                    const int32_t* n_chunks, int n_seg, int warm, int max_repair_rounds, int pool_blocks,
-                                    void* workspace, int64_t workspace_bytes, const b200bt_sweep_config* cfg_host,
-                                    b200bt_lane_stats* stats, uint32_t* events, int64_t event_cap,
-                                    unsigned char* lane_invalid, int* overflow_host_or_null, b200bt_stream_t stream) {
-    B200BT_REQUIRE(price && rsi && indiv && items && seg_base && n_chunks && workspace && cfg_host && stats && lane_invalid,
-                   B200BT_EINVAL, "sweep_chunked: null pointer");
-    B200BT_REQUIRE(S > 0 && N > 0 && P > 0 && pop > 0 && n_items > 0 && n_seg > 0 && pool_blocks > 0 && warm >= 0,
-                   B200BT_EINVAL, "sweep_chunked: bad sizes");
-    B200BT_REQUIRE(ld_price >= N && ld_rsi >= N, B200BT_EINVAL, "sweep_chunked: row stride shorter than N");
-    B200BT_REQUIRE(N < (1ll << 30), B200BT_ELIMIT, "sweep_chunked: N must be < 2^30 bars");
-    B200BT_REQUIRE(cfg_host->bar_minutes > 0 && cfg_host->minute0 >= 0 &&
-                       cfg_host->minute0 + N * (int64_t)cfg_host->bar_minutes < (1ll << 32) - 1440,
-                   B200BT_ELIMIT, "sweep_chunked: minute0 + N*bar_minutes must stay below 2^32 minutes");
-    B200BT_REQUIRE(workspace_bytes >= b200bt_sweep_chunked_workspace_bytes(pool_blocks, S, n_seg), B200BT_EINVAL,
-                   "sweep_chunked: workspace too small");
-    B200BT_REQUIRE(events == nullptr || event_cap > 0, B200BT_EINVAL, "sweep_chunked: event buffer without capacity");
-    int rc = check_device();
-    if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t segs = (int64_t)S * n_seg;
-    B200BT_REQUIRE(((uintptr_t)workspace & 15) == 0, B200BT_EINVAL, "sweep_chunked: workspace must be 16-byte aligned");
-    uint2* pool = (uint2*)workspace;
-    int2* seg_in = (int2*)(pool + (int64_t)pool_blocks * CK_BLOCK);
-    int2* seg_out = seg_in + segs;
-    int* seg_first = (int*)(seg_out + segs);
-    unsigned* seg_count = (unsigned*)(seg_first + segs);
-    unsigned* alloc = seg_count + segs;
-    int* overflow = (int*)(alloc + 1);
-    unsigned* n_repair = (unsigned*)(overflow + 1);
-    int4* repair = (int4*)(n_repair + 2);
-    int* next = (int*)(repair + segs);
-    ChunkPartial* partial = (ChunkPartial*)(((uintptr_t)(next + pool_blocks) + 15) & ~(uintptr_t)15);
-    double* seg_sum = (double*)(partial + segs);
-    double* seg_max = seg_sum + segs;
-    cudaError_t e = cudaMemsetAsync(seg_in, 0, (size_t)(segs * 6 + 4) * 4, st);
-    if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: memset");
-
-    ChunkScanArgs A;
-    A.price = price; A.ld_price = ld_price; A.rsi = rsi; A.ld_rsi = ld_rsi; A.P = P; A.S = S; A.N = N;
-    A.indiv = indiv; A.items = items; A.n_items = n_items; A.n_seg = n_seg; A.warm = warm;
-    A.pool = pool; A.pool_blocks = pool_blocks; A.next = next; A.alloc = alloc;
-    A.seg_first = seg_first; A.seg_count = seg_count; A.seg_in = seg_in; A.seg_out = seg_out; A.overflow = overflow;
-    A.repair = repair; A.n_chunks = n_chunks;
-    const bool vec16 = (((uintptr_t)price | (uintptr_t)rsi) & 15) == 0 && ld_price % 4 == 0 && ld_rsi % 4 == 0;
-    auto kern = vec16 ? chunk_scan_kernel<true, false> : chunk_scan_kernel<false, false>;
+// Everything after the speculative scan: verify -> repair rounds -> chunk-parallel metrics.
+int finish_chunks(const ChunkScanArgs& A, const ChunkWorkspace& w, const b200bt_chunk_item* items, int n_items,
+                  const int32_t* seg_base, int pop, int max_repair_rounds, const b200bt_sweep_config* cfg_host,
+                  b200bt_lane_stats* stats, uint32_t* events, int64_t event_cap, unsigned char* lane_invalid,
+                  int* overflow_host_or_null, cudaStream_t st) {
+    const int S = A.S, n_seg = A.n_seg;
+    const bool vec16 = (((uintptr_t)A.price | (uintptr_t)A.rsi) & 15) == 0 && A.ld_price % 4 == 0 && A.ld_rsi % 4 == 0;
     auto kern_fix = vec16 ? chunk_scan_kernel<true, true> : chunk_scan_kernel<false, true>;
     const size_t smem = sizeof(WarpShared) * SW_WARPS;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: cudaFuncSetAttribute");
-    const int64_t blocks = (int64_t)((n_items + SW_WARPS - 1) / SW_WARPS) * S;
-    B200BT_REQUIRE(blocks < (1ll << 31), B200BT_ELIMIT, "sweep_chunked: too many work items");
-    kern<<<(unsigned)blocks, SW_WARPS * 32, smem, st>>>(A);
-    B200BT_LAUNCH_CHECK("chunk_scan launch");
     // verify -> repair rounds: a chunk whose assumed state was wrong is re-scanned from the true state; chunks
     // behind a wrong predecessor wait for the next round.  Each round costs one tiny verify launch, a 4-byte
     // readback (stream synchronisation) and, if anything is listed, one repair launch.
     for (int round = 0; round < max_repair_rounds; ++round) {
-        e = cudaMemsetAsync(n_repair, 0, sizeof(unsigned), st);
+        e = cudaMemsetAsync(w.n_repair, 0, sizeof(unsigned), st);
         if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: memset");
         const int64_t lanes = (int64_t)pop * S;
-        chunk_verify_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pop, S, seg_base, n_chunks, n_seg, seg_count, seg_in,
-                                                                            seg_out, repair, n_repair);
+        chunk_verify_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pop, S, seg_base, A.n_chunks, n_seg, w.seg_count,
+                                                                            w.seg_in, w.seg_out, w.repair, w.n_repair);
         B200BT_LAUNCH_CHECK("chunk_verify launch");
         unsigned h_rep = 0;
-        e = cudaMemcpyAsync(&h_rep, n_repair, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+        e = cudaMemcpyAsync(&h_rep, w.n_repair, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: verify readback");
         if (h_rep == 0) break;
@@ -543,23 +693,144 @@ extern "C" int b200bt_sweep_chunked(const float* price, int64_t ld_price, const 
         B200BT_LAUNCH_CHECK("chunk_repair launch");
     }
     const int64_t mblocks = (int64_t)((n_items + 3) / 4) * S;
-    chunk_sums_kernel<<<(unsigned)mblocks, 128, 0, st>>>(price, ld_price, indiv, items, n_items, S, n_seg, pool, next, seg_first,
-                                                          seg_count, seg_in, seg_sum, seg_max);
+    B200BT_REQUIRE(mblocks < (1ll << 31), B200BT_ELIMIT, "sweep_chunked: too many work items");
+    chunk_sums_kernel<<<(unsigned)mblocks, 128, 0, st>>>(A.price, A.ld_price, A.indiv, items, n_items, S, n_seg, w.pool, w.next,
+                                                          w.seg_first, w.seg_count, w.seg_in, w.seg_sum, w.seg_max);
     B200BT_LAUNCH_CHECK("chunk_sums launch");
-    chunk_partial_kernel<<<(unsigned)mblocks, 128, 0, st>>>(price, ld_price, indiv, items, n_items, S, n_seg, pool, next,
-                                                             seg_first, seg_count, seg_in, seg_sum, seg_max, *cfg_host, events,
-                                                             event_cap, partial);
+    chunk_partial_kernel<<<(unsigned)mblocks, 128, 0, st>>>(A.price, A.ld_price, A.indiv, items, n_items, S, n_seg, w.pool, w.next,
+                                                             w.seg_first, w.seg_count, w.seg_in, w.seg_sum, w.seg_max, *cfg_host,
+                                                             events, event_cap, w.partial);
     B200BT_LAUNCH_CHECK("chunk_partial launch");
-    {
-        const int64_t lanes = (int64_t)pop * S;
-        lane_combine_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(indiv, pop, S, seg_base, n_chunks, n_seg, seg_count,
-                                                                            seg_in, seg_out, partial, *cfg_host, stats,
-                                                                            lane_invalid);
-    }
+    const int64_t lanes = (int64_t)pop * S;
+    lane_combine_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(A.indiv, pop, S, seg_base, A.n_chunks, n_seg, w.seg_count,
+                                                                        w.seg_in, w.seg_out, w.partial, *cfg_host, stats,
+                                                                        lane_invalid);
     B200BT_LAUNCH_CHECK("lane_combine launch");
     if (overflow_host_or_null) {
-        e = cudaMemcpyAsync(overflow_host_or_null, overflow, sizeof(int), cudaMemcpyDeviceToHost, st);
+        e = cudaMemcpyAsync(overflow_host_or_null, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: overflow readback");
     }
     return B200BT_OK;
+}
+
+int check_sweep_args(const char* who, const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S,
+                     int64_t N, const b200bt_sweep_config* cfg_host, const uint32_t* events, int64_t event_cap) {
+    B200BT_REQUIRE(price && rsi && cfg_host, B200BT_EINVAL, "%s: null pointer", who);
+    B200BT_REQUIRE(S > 0 && N > 0 && P > 0, B200BT_EINVAL, "%s: bad sizes", who);
+    B200BT_REQUIRE(ld_price >= N && ld_rsi >= N, B200BT_EINVAL, "%s: row stride shorter than N", who);
+    B200BT_REQUIRE(N < (1ll << 30), B200BT_ELIMIT, "%s: N must be < 2^30 bars", who);
+    B200BT_REQUIRE(cfg_host->bar_minutes > 0 && cfg_host->minute0 >= 0 &&
+                       cfg_host->minute0 + N * (int64_t)cfg_host->bar_minutes < (1ll << 32) - 1440,
+                   B200BT_ELIMIT, "%s: minute0 + N*bar_minutes must stay below 2^32 minutes", who);
+    B200BT_REQUIRE(events == nullptr || event_cap > 0, B200BT_EINVAL, "%s: event buffer without capacity", who);
+    return B200BT_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t b200bt_sweep_chunked_workspace_bytes(int pool_blocks, int S, int n_seg) {
+    return chunk_workspace_bytes(pool_blocks, (int64_t)S * n_seg);
+}
+
+extern "C" int b200bt_sweep_chunked(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S,
+                                    int64_t N, const b200bt_individual* indiv, const int32_t* order, int pop,
+                                    const b200bt_chunk_item* items, int n_items, const int32_t* seg_base,
+                                    const int32_t* n_chunks, int n_seg, int warm, int max_repair_rounds, int pool_blocks,
+                                    void* workspace, int64_t workspace_bytes, const b200bt_sweep_config* cfg_host,
+                                    b200bt_lane_stats* stats, uint32_t* events, int64_t event_cap,
+                                    unsigned char* lane_invalid, int* overflow_host_or_null, b200bt_stream_t stream) {
+    (void)order;
+    B200BT_REQUIRE(indiv && items && seg_base && n_chunks && workspace && stats && lane_invalid, B200BT_EINVAL,
+                   "sweep_chunked: null pointer");
+    B200BT_REQUIRE(pop > 0 && n_items > 0 && n_seg > 0 && pool_blocks > 0 && warm >= 0, B200BT_EINVAL, "sweep_chunked: bad sizes");
+    int rc = check_sweep_args("sweep_chunked", price, ld_price, rsi, ld_rsi, P, S, N, cfg_host, events, event_cap);
+    if (rc) return rc;
+    B200BT_REQUIRE(workspace_bytes >= b200bt_sweep_chunked_workspace_bytes(pool_blocks, S, n_seg), B200BT_EINVAL,
+                   "sweep_chunked: workspace too small");
+    B200BT_REQUIRE(((uintptr_t)workspace & 15) == 0, B200BT_EINVAL, "sweep_chunked: workspace must be 16-byte aligned");
+    rc = check_device();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t segs = (int64_t)S * n_seg;
+    const ChunkWorkspace w = carve(workspace, pool_blocks, segs);
+    cudaError_t e = cudaMemsetAsync(w.seg_in, 0, (size_t)(segs * 6 + 4) * 4, st);
+    if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: memset");
+
+    ChunkScanArgs A;
+    A.price = price; A.ld_price = ld_price; A.rsi = rsi; A.ld_rsi = ld_rsi; A.P = P; A.S = S; A.N = N;
+    A.indiv = indiv; A.items = items; A.n_items = n_items; A.n_seg = n_seg; A.warm = warm;
+    A.pool = w.pool; A.pool_blocks = pool_blocks; A.next = w.next; A.alloc = w.alloc;
+    A.seg_first = w.seg_first; A.seg_count = w.seg_count; A.seg_in = w.seg_in; A.seg_out = w.seg_out; A.overflow = w.overflow;
+    A.repair = w.repair; A.n_chunks = n_chunks;
+    const bool vec16 = (((uintptr_t)price | (uintptr_t)rsi) & 15) == 0 && ld_price % 4 == 0 && ld_rsi % 4 == 0;
+    auto kern = vec16 ? chunk_scan_kernel<true, false> : chunk_scan_kernel<false, false>;
+    const size_t smem = sizeof(WarpShared) * SW_WARPS;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: cudaFuncSetAttribute");
+    const int64_t blocks = (int64_t)((n_items + SW_WARPS - 1) / SW_WARPS) * S;
+    B200BT_REQUIRE(blocks < (1ll << 31), B200BT_ELIMIT, "sweep_chunked: too many work items");
+    kern<<<(unsigned)blocks, SW_WARPS * 32, smem, st>>>(A);
+    B200BT_LAUNCH_CHECK("chunk_scan launch");
+    return finish_chunks(A, w, items, n_items, seg_base, pop, max_repair_rounds, cfg_host, stats, events, event_cap,
+                         lane_invalid, overflow_host_or_null, st);
+}
+
+extern "C" int64_t b200bt_sweep_tiled_workspace_bytes(int pool_blocks, int S, int pop, int K) {
+    const int64_t n_seg = (int64_t)pop * K;
+    return chunk_workspace_bytes(pool_blocks, S * n_seg) + 16 + n_seg * 16 + (int64_t)pop * 8;
+}
+
+extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S,
+                                  int64_t N, const b200bt_individual* indiv, const int32_t* order, int pop, int K, int warm,
+                                  int max_repair_rounds, int pool_blocks, void* workspace, int64_t workspace_bytes,
+                                  const b200bt_sweep_config* cfg_host, b200bt_lane_stats* stats, uint32_t* events,
+                                  int64_t event_cap, unsigned char* lane_invalid, int* overflow_host_or_null,
+                                  b200bt_stream_t stream) {
+    B200BT_REQUIRE(indiv && workspace && stats && lane_invalid, B200BT_EINVAL, "sweep_tiled: null pointer");
+    B200BT_REQUIRE(pop > 0 && K > 0 && pool_blocks > 0 && warm >= 0, B200BT_EINVAL, "sweep_tiled: bad sizes");
+    int rc = check_sweep_args("sweep_tiled", price, ld_price, rsi, ld_rsi, P, S, N, cfg_host, events, event_cap);
+    if (rc) return rc;
+    B200BT_REQUIRE((int64_t)pop * K * S < (1ll << 31), B200BT_ELIMIT, "sweep_tiled: too many chunks");
+    B200BT_REQUIRE(K == 1 || N / K >= SW_GROUP, B200BT_EINVAL, "sweep_tiled: chunks shorter than %d bars", SW_GROUP);
+    const size_t smem = (size_t)2 * (P + 1) * LS_STRIDE * sizeof(float);
+    B200BT_REQUIRE(smem <= 72 * 1024, B200BT_ELIMIT, "sweep_tiled: RSI bank of %d periods exceeds the shared-memory tile", P);
+    B200BT_REQUIRE(workspace_bytes >= b200bt_sweep_tiled_workspace_bytes(pool_blocks, S, pop, K), B200BT_EINVAL,
+                   "sweep_tiled: workspace too small");
+    B200BT_REQUIRE(((uintptr_t)workspace & 15) == 0, B200BT_EINVAL, "sweep_tiled: workspace must be 16-byte aligned");
+    rc = check_device();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_seg = pop * K;
+    const int64_t segs = (int64_t)S * n_seg;
+    const ChunkWorkspace w = carve(workspace, pool_blocks, segs);
+    b200bt_chunk_item* items = (b200bt_chunk_item*)(((uintptr_t)w.end + 15) & ~(uintptr_t)15);
+    int32_t* seg_base = (int32_t*)(items + n_seg);
+    int32_t* n_chunks = seg_base + pop;
+    cudaError_t e = cudaMemsetAsync(w.seg_in, 0, (size_t)(segs * 6 + 4) * 4, st);
+    if (e != cudaSuccess) return cuda_status(e, "sweep_tiled: memset");
+    lane_tables_kernel<<<(n_seg + 255) / 256, 256, 0, st>>>(pop, K, items, seg_base, n_chunks);
+    B200BT_LAUNCH_CHECK("lane_tables launch");
+
+    LaneScanArgs L;
+    L.price = price; L.ld_price = ld_price; L.rsi = rsi; L.ld_rsi = ld_rsi; L.P = P; L.S = S; L.N = N;
+    L.indiv = indiv; L.order = order; L.pop = pop; L.K = K; L.warm = warm;
+    L.pool = w.pool; L.pool_blocks = pool_blocks; L.next = w.next; L.alloc = w.alloc;
+    L.seg_first = w.seg_first; L.seg_count = w.seg_count; L.seg_in = w.seg_in; L.seg_out = w.seg_out; L.overflow = w.overflow;
+    const bool vec16 = (((uintptr_t)price | (uintptr_t)rsi) & 15) == 0 && ld_price % 4 == 0 && ld_rsi % 4 == 0;
+    auto kern = vec16 ? lane_scan_kernel<true> : lane_scan_kernel<false>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "sweep_tiled: cudaFuncSetAttribute");
+    const int64_t blocks = (int64_t)((pop + LS_THREADS - 1) / LS_THREADS) * K * S;
+    B200BT_REQUIRE(blocks < (1ll << 31), B200BT_ELIMIT, "sweep_tiled: too many work items");
+    kern<<<(unsigned)blocks, LS_THREADS, smem, st>>>(L);
+    B200BT_LAUNCH_CHECK("lane_scan launch");
+
+    ChunkScanArgs A;   // for the shared repair / metrics kernels
+    A.price = price; A.ld_price = ld_price; A.rsi = rsi; A.ld_rsi = ld_rsi; A.P = P; A.S = S; A.N = N;
+    A.indiv = indiv; A.items = items; A.n_items = n_seg; A.n_seg = n_seg; A.warm = warm;
+    A.pool = w.pool; A.pool_blocks = pool_blocks; A.next = w.next; A.alloc = w.alloc;
+    A.seg_first = w.seg_first; A.seg_count = w.seg_count; A.seg_in = w.seg_in; A.seg_out = w.seg_out; A.overflow = w.overflow;
+    A.repair = w.repair; A.n_chunks = n_chunks;
+    return finish_chunks(A, w, items, n_seg, seg_base, pop, max_repair_rounds, cfg_host, stats, events, event_cap, lane_invalid,
+                         overflow_host_or_null, st);
 }

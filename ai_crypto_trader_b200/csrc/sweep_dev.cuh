@@ -339,7 +339,9 @@ __device__ __forceinline__ bool fires(const Machine& m, float p, float r) {
 
 // Advance the machine through every event of one 32-bar window (lane l holds bar t0+l).
 // `emit` = false runs the machine without recording events (warm-up bars of a time chunk).
-__device__ __forceinline__ void scan_window(const float p, const float r, const int t0, const int lane,
+// `win` points at the window's 32 prices in the shared-memory ring (RSI values SW_GROUP floats further):
+// the event bar's price / RSI are re-read from there with a warp-uniform address.
+__device__ __forceinline__ void scan_window(const float p, const float r, const float* __restrict__ win, const int t0,
                                             WarpShared* __restrict__ ws, const ScanConst& c, Machine& m,
                                             const bool emit = true) {
     unsigned live = FULL;  // bars of the window not yet consumed
@@ -347,8 +349,8 @@ __device__ __forceinline__ void scan_window(const float p, const float r, const 
         const unsigned hit = __ballot_sync(FULL, fires(m, p, r)) & live;
         if (hit == 0) break;
         const int kk = __ffs(hit) - 1;
-        const float pk = __shfl_sync(FULL, p, kk);
-        const float rk = __shfl_sync(FULL, r, kk);
+        const float pk = win[kk];
+        const float rk = win[SW_GROUP + kk];
         live = 0xfffffffeu << kk;
         const unsigned bar = (unsigned)(t0 + kk);
         unsigned word;

@@ -141,6 +141,7 @@ def lane_cost(p: Dict) -> float:
 
 
 EVENTS_PER_COST_BAR = 0.27
+TILED_MAX_PERIODS = 68      # shared-memory tile of the thread-per-lane sweep: 2 (P + 1) 528 B <= 72 KB
 
 
 def predicted_events(population: List[Dict], n_bars: int) -> np.ndarray:
@@ -192,6 +193,47 @@ class ChunkPlan:
         self.pop = pop
 
 
+class TilePlan:
+    """Host-side plan of the thread-per-lane sweep (b200bt_sweep_tiled) for one population slice: every
+    individual gets the same K time chunks, chosen so that the CTAs fill whole waves of the GPU."""
+
+    THREADS = 256          # individuals per CTA (csrc/sweep_chunked.cu LS_THREADS)
+    CTAS_PER_SM = 3
+
+    def __init__(self, population: List[Dict], n_bars: int, n_symbols: int, device, warm: int = 8192,
+                 max_chunks: int = 64, chunks: Optional[int] = None, pool_scale: float = 1.5,
+                 pool_blocks: Optional[int] = None, max_repair_rounds: Optional[int] = None, lo: int = 0,
+                 workspace: Optional[torch.Tensor] = None):
+        pop = len(population)
+        self.lo, self.pop = int(lo), pop
+        self.warm = int(warm)
+        kmax = max(1, min(max_chunks, n_bars // max(8 * warm, 2048)))
+        if chunks is None:
+            slots = torch.cuda.get_device_properties(device).multi_processor_count * self.CTAS_PER_SM
+            groups = -(-pop // self.THREADS) * n_symbols
+            waves = lambda k: -(-groups * k // slots)
+            # time ~ waves x bars per CTA; ties go to the larger K (shorter serial repair re-scans)
+            chunks = min(range(1, kmax + 1), key=lambda k: (waves(k) * (n_bars / k + (warm if k > 1 else 0)), -k))
+        self.K = int(chunks)
+        # a lane that holds one position across many chunks needs one repair round per boundary
+        self.max_repair_rounds = int(max_repair_rounds) if max_repair_rounds is not None else min(self.K, 24)
+        self.n_seg = pop * self.K
+        pred = predicted_events(population, n_bars)
+        self.order = evaluation_order(population)
+        # every segment owns at least one block, and a repaired segment abandons its first chain
+        self.pool_blocks = int(pool_scale * pred.sum() * n_symbols / 256) + 2 * self.n_seg * n_symbols + 1024
+        if pool_blocks is not None:
+            self.pool_blocks = int(pool_blocks)
+        self.order_dev = torch.from_numpy(self.order).to(device)
+        ws_bytes = int(_lib.load().b200bt_sweep_tiled_workspace_bytes(self.pool_blocks, n_symbols, pop, self.K))
+        if workspace is not None and workspace.numel() >= ws_bytes:
+            self.workspace = workspace
+        else:
+            self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        self.invalid = torch.zeros((pop, n_symbols), dtype=torch.uint8, device=device)
+        self.overflow = torch.zeros(1, dtype=torch.int32).pin_memory()
+
+
 def evaluation_order(population: List[Dict]) -> np.ndarray:
     """Order in which the kernel dispatches individuals: same RSI period adjacent (the
     warps of a CTA then read the same RSI stream), most expensive first.
@@ -215,8 +257,9 @@ class PopulationSweep:
     def __init__(self, market: MarketData, rsi_periods: Iterable[int] = range(5, 31),
                  optimization_goals: Optional[Dict] = None, initial_capital: float = 10000.0,
                  event_cap: int = 0, mode: str = "auto", chunk_options: Optional[Dict] = None):
-        """mode: "fused" (one warp per lane, serial in time), "chunked" (expensive lanes split into
-        verified time chunks, csrc/sweep_chunked.cu) or "auto" (chunked from 131072 bars up)."""
+        """mode: "fused" (one warp per lane, serial in time), "chunked" (expensive lanes split into verified
+        time chunks, one warp per chunk), "tiled" (every lane split into the same K verified chunks, one THREAD
+        per chunk; csrc/sweep_chunked.cu) or "auto" (tiled from 131072 bars up, fused below)."""
         self.market = market
         self.periods = sorted(set(int(p) for p in rsi_periods))
         self.period_row = {p: i for i, p in enumerate(self.periods)}
@@ -268,7 +311,7 @@ class PopulationSweep:
             self._ensure_buffers(pop)
             self.last_invalid_lanes, self.last_pool_overflow = 0, False
             for pl in plans:
-                self._evaluate_chunked(indiv_dev, pl)
+                (self._evaluate_tiled if isinstance(pl, TilePlan) else self._evaluate_chunked)(indiv_dev, pl)
             with torch.cuda.device(self.market.device):
                 _lib.call("b200bt_fitness_reduce", self._stats.data_ptr(), pop, self.market.S, fitness_dev.data_ptr(),
                           _lib.current_stream())
@@ -320,15 +363,41 @@ class PopulationSweep:
                           len(self.periods), m.S, m.N, indiv_dev.data_ptr(), redo.data_ptr(), int(redo.numel()),
                           C.byref(self.cfg), self._stats.data_ptr(), _lib.ptr(self._events), self.event_cap, st)
 
+    def _evaluate_tiled(self, indiv_dev, plan: "TilePlan") -> None:
+        """One slice of the population through the thread-per-lane kernels (same verification / fallback)."""
+        m = self.market
+        lo, n = plan.lo, plan.pop
+        stats = self._stats[lo:lo + n]
+        events = self._events[lo:lo + n] if self._events is not None else None
+        with torch.cuda.device(m.device):
+            st = _lib.current_stream()
+            _lib.call("b200bt_sweep_tiled", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
+                      len(self.periods), m.S, m.N, indiv_dev.data_ptr() + lo * C.sizeof(_lib.Individual),
+                      plan.order_dev.data_ptr(), n, plan.K, plan.warm, plan.max_repair_rounds, plan.pool_blocks,
+                      plan.workspace.data_ptr(), plan.workspace.numel(), C.byref(self.cfg), stats.data_ptr(),
+                      _lib.ptr(events), self.event_cap, plan.invalid.data_ptr(), plan.overflow.data_ptr(), st)
+            bad = torch.nonzero(plan.invalid.any(dim=1)).flatten()          # device -> host sync (tiny)
+            self.last_invalid_lanes += int(plan.invalid.sum().item())
+            self.last_pool_overflow |= bool(plan.overflow.item())
+            if bad.numel():
+                redo = (bad + lo).to(torch.int32).contiguous()
+                _lib.call("b200bt_sweep", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
+                          len(self.periods), m.S, m.N, indiv_dev.data_ptr(), redo.data_ptr(), int(redo.numel()),
+                          C.byref(self.cfg), self._stats.data_ptr(), _lib.ptr(self._events), self.event_cap, st)
+
+    def plan_tiles(self, population: List[Dict], **kw) -> "TilePlan":
+        return TilePlan(population, self.market.N, self.market.S, self.market.device, **kw)
+
     def plan_chunks(self, population: List[Dict], **kw) -> "ChunkPlan":
         return ChunkPlan(population, self.market.N, self.market.S, self.market.device, **kw)
 
-    def plan_batches(self, population: List[Dict], max_pool_bytes: int = 8 << 30, **kw) -> List["ChunkPlan"]:
+    def plan_batches(self, population: List[Dict], max_pool_bytes: int = 8 << 30, tiled: bool = False, **kw) -> List:
         """Plans for contiguous slices of the population whose event pools each stay below `max_pool_bytes`
         and share one workspace: large populations (BASELINE configs[4]: 10 000 x 50 symbols) record more
         events than fit in HBM at once, so they go through the chunked kernels slice by slice."""
+        cls = TilePlan if tiled else ChunkPlan
         if kw.get("pool_blocks") is not None:
-            return [self.plan_chunks(population, **kw)]
+            return [cls(population, self.market.N, self.market.S, self.market.device, **kw)]
         pred = predicted_events(population, self.market.N) * self.market.S * 8 * kw.get("pool_scale", 1.5)
         cuts, acc = [0], 0.0
         for i, b in enumerate(pred):
@@ -338,10 +407,10 @@ class PopulationSweep:
             acc += b
         cuts.append(len(population))
         if len(cuts) == 2:
-            return [self.plan_chunks(population, **kw)]
+            return [cls(population, self.market.N, self.market.S, self.market.device, **kw)]
         plans, shared = [], None
         for lo, hi in sorted(zip(cuts[:-1], cuts[1:]), key=lambda c: -float(pred[c[0]:c[1]].sum())):
-            pl = ChunkPlan(population[lo:hi], self.market.N, self.market.S, self.market.device, lo=lo, workspace=shared, **kw)
+            pl = cls(population[lo:hi], self.market.N, self.market.S, self.market.device, lo=lo, workspace=shared, **kw)
             shared = shared if shared is not None else pl.workspace     # the largest slice is planned first
             plans.append(pl)
         return sorted(plans, key=lambda pl: pl.lo)
@@ -379,12 +448,14 @@ class PopulationSweep:
         order_dev = staged[nbytes:].view(torch.int32)
         fit = torch.empty(pop, dtype=torch.float64, device=dev)
         plan = None
-        if self.mode == "chunked" or (self.mode == "auto" and self.market.N >= self.chunk_min_bars):
-            plan = self.plan_batches(population, **self.chunk_options)
+        tiled = self.mode == "tiled" or (self.mode == "auto" and self.market.N >= self.chunk_min_bars
+                                         and len(self.periods) <= TILED_MAX_PERIODS)
+        if tiled or self.mode == "chunked" or (self.mode == "auto" and self.market.N >= self.chunk_min_bars):
+            plan = self.plan_batches(population, tiled=tiled, **self.chunk_options)
             if getattr(self, "last_pool_overflow", False):
                 grown = dict(self.chunk_options, pool_scale=4.0 * self.chunk_options.get("pool_scale", 1.5))
                 grown.pop("pool_blocks", None)
-                plan = self.plan_batches(population, **grown)
+                plan = self.plan_batches(population, tiled=tiled, **grown)
         self.evaluate_device(indiv_dev, order_dev, pop, fit, plan=plan)
         self._inverse = expand
         out = self._pinned_out[:pop]

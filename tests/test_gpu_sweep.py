@@ -261,3 +261,44 @@ def test_chunked_sweep_in_population_slices_with_duplicates(torch_cuda):
     np.testing.assert_array_equal(sc["trade_hash"], sf["trade_hash"])
     np.testing.assert_array_equal(chunked.events(), fused.events())
     _check_lanes_vs_oracle(chunked, population, ohlcv, cap)
+
+
+@pytest.mark.parametrize("n_bars,opts", [
+    (300_000, dict(warm=4096)),                                        # wave-fitted K, verified boundaries
+    (300_001, dict(warm=4096, chunks=7)),                              # ragged last tile
+    (70_001, dict(warm=0, chunks=16, max_repair_rounds=0)),            # no warm-up, no repair: fused fallback
+    (150_000, dict(warm=0, chunks=32, max_repair_rounds=64)),          # no warm-up: repaired chunk by chunk
+    (200_000, dict(warm=2048, chunks=8, pool_blocks=8)),               # pool far too small -> flagged lanes re-run
+    (5_000, dict(warm=512, chunks=1)),                                 # a single chunk
+])
+def test_tiled_sweep_is_exact_and_self_repairing(torch_cuda, n_bars, opts):
+    """Thread-per-lane sweep == serial reference semantics, whether or not the speculation holds."""
+    from ai_crypto_trader_b200 import synth
+    from ai_crypto_trader_b200.sweep import MarketData, PopulationSweep
+    ohlcv = synth.synth_ohlcv(2, n_bars, first_symbol=1)
+    market = MarketData(ohlcv)
+    cap = 2048
+    population = synth.random_population(300, seed=n_bars)            # two CTAs per (symbol, chunk), one ragged
+    population[0].update(rsi_oversold=35, rsi_overbought=65, rsi_period=5, take_profit=1, stop_loss=1)
+    population[1].update(rsi_oversold=34, rsi_overbought=66, rsi_period=6, take_profit=10, stop_loss=5)
+    population[2].update(rsi_oversold=60, rsi_overbought=40, rsi_period=10, take_profit=2, stop_loss=2)   # inverted
+    tiled = PopulationSweep(market, event_cap=cap, mode="tiled", chunk_options=opts)
+    fused = PopulationSweep(market, event_cap=cap, mode="fused")
+    f_t = tiled.evaluate(population)
+    f_f = fused.evaluate(population)
+    plan = tiled.plan_tiles(population, **opts)
+    if "chunks" in opts:
+        assert plan.K == opts["chunks"]
+    if opts.get("max_repair_rounds", 8) == 0:
+        assert tiled.last_invalid_lanes > 0            # the fallback path really ran
+    if opts.get("max_repair_rounds", 8) == 64:
+        assert tiled.last_invalid_lanes == 0           # every wrong boundary was repaired in place
+    if "pool_blocks" in opts:
+        assert tiled.last_pool_overflow and tiled.last_invalid_lanes > 0
+    np.testing.assert_array_equal(tiled.lane_stats()["trade_hash"], fused.lane_stats()["trade_hash"])
+    np.testing.assert_array_equal(tiled.lane_stats()["n_records"], fused.lane_stats()["n_records"])
+    ev_t, ev_f, n_rec = tiled.events(), fused.events(), fused.lane_stats()["n_records"]
+    live = np.arange(cap)[None, None, :] < n_rec[:, :, None]          # slots past a lane's last record are undefined
+    np.testing.assert_array_equal(ev_t[live], ev_f[live])
+    np.testing.assert_allclose(f_t, f_f, rtol=1e-9, atol=1e-11)
+    _check_lanes_vs_oracle(tiled, population[:24], ohlcv, cap)
