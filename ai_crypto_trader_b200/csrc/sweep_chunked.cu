@@ -221,7 +221,10 @@ chunk_scan_kernel(const ChunkScanArgs A) {   // by value, not __grid_constant__ 
 // four bars per step.  The event path then runs in SIMT fashion for up to 32 lanes at once, all threads walk
 // the same bars (no tail), and the bank is fetched once per 256 lanes.  Events go to the same pool / segment
 // tables as the warp scan, so verification, repair and the metrics kernels are shared.
-constexpr int LS_T = 128;               // bars per tile
+#ifndef B200BT_LS_T
+#define B200BT_LS_T 128
+#endif
+constexpr int LS_T = B200BT_LS_T;       // bars per tile
 constexpr int LS_STRIDE = LS_T + 4;     // row stride in floats (16-byte aligned rows, rows 8 apart share banks)
 constexpr int LS_THREADS = 256;
 
@@ -246,8 +249,11 @@ __global__ void lane_tables_kernel(int pop, int K, b200bt_chunk_item* __restrict
     if (c == 0) { seg_base[ind] = i; n_chunks[ind] = K; }
 }
 
+#ifndef B200BT_LS_MIN_BLOCKS
+#define B200BT_LS_MIN_BLOCKS 4
+#endif
 template <bool VEC16>
-__global__ void __launch_bounds__(LS_THREADS, 3)
+__global__ void __launch_bounds__(LS_THREADS, B200BT_LS_MIN_BLOCKS)
 lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (see sweep.cu)
     extern __shared__ __align__(16) float ls_tile[];   // [2][P + 1][LS_STRIDE]
     const int rows = A.P + 1;
@@ -297,52 +303,51 @@ lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (s
     int pos = 0, entry_bar = 0;
     float e_px = 0.f, rlo = iv.rsi_lo, rhi = iv.rsi_hi, plo = -INFINITY, phi = INFINITY;
     // event sink: this thread's chunk owns a chain of pool blocks
-    int cur_block = -1, fill = CK_BLOCK, dead = 0;
+    int cur_block = -1, fill = CK_BLOCK;
     unsigned count = 0;
-    bool rec = false;
+    bool rec = false, dead = false;
+    uint2* wptr = A.pool;
 
-    auto emit = [&](unsigned word, float px) {
-        if (!rec) return;
-        if (fill == CK_BLOCK && !dead) {
-            const int b = (int)atomicAdd(A.alloc, 1u);
-            if (b >= A.pool_blocks) { atomicExch(A.overflow, 1); dead = 1; }
-            else {
-                A.next[b] = -1;
-                if (cur_block < 0) A.seg_first[seg] = b; else A.next[cur_block] = b;
-                cur_block = b; fill = 0;
+    // one bar of the state machine; same decisions as scan_window (sweep_dev.cuh).  Written as straight-line
+    // selects: the threads of a warp that fire on the same bar (entries and exits alike) share one pass.
+    auto step = [&](float p, float r, int t) {
+        const bool rsi_hit = (r < rlo) | (r > rhi);
+        if (!(rsi_hit | (p <= plo) | (p >= phi))) return;
+        const bool flat = pos == 0, lng_open = pos > 0;
+        bool ev = true;
+        if (!flat && !rsi_hit) {
+            // price trigger: definite outside the fp32 screening band, else the reference's float64 expression
+            const float hd = e_px * (lng_open ? sc.hiL_d : sc.hiS_d), ld = e_px * (lng_open ? sc.loL_d : sc.loS_d);
+            if (!((p >= hd) || (p <= ld))) {
+                const double ed = (double)e_px, pd = (double)p;
+                const double q = lng_open ? __ddiv_rn(__dsub_rn(pd, ed), ed) : __ddiv_rn(__dsub_rn(ed, pd), ed);
+                ev = (q >= tp) || (q <= -sl);
             }
         }
-        if (!dead) { A.pool[(int64_t)cur_block * CK_BLOCK + fill] = make_uint2(word, __float_as_uint(px)); ++fill; }
-        ++count;
-    };
-    // one bar of the state machine; same decisions as scan_window (sweep_dev.cuh)
-    auto step = [&](float p, float r, int t) {
-        if (!((r < rlo) | (r > rhi) | (p <= plo) | (p >= phi))) return;
-        if (pos == 0) {
-            const bool lng = r < sc.os_f;                 // long has priority (:784, :799)
-            e_px = p; entry_bar = t;
-            pos = lng ? 1 : -1;
-            rlo = lng ? -INFINITY : sc.os_f;
-            rhi = lng ? sc.ob_f : INFINITY;
-            phi = p * (lng ? sc.hiL_c : sc.hiS_c);
-            plo = p * (lng ? sc.loL_c : sc.loS_c);
-            emit(lng ? (unsigned)t : ((unsigned)t | B200BT_EVENT_SELL), p);
-        } else {
-            bool ev = true;
-            if (!((r < rlo) || (r > rhi))) {
-                const bool lng = pos > 0;
-                const float hd = e_px * (lng ? sc.hiL_d : sc.hiS_d), ld = e_px * (lng ? sc.loL_d : sc.loS_d);
-                if (!((p >= hd) || (p <= ld))) {
-                    const double ed = (double)e_px, pd = (double)p;
-                    const double q = lng ? __ddiv_rn(__dsub_rn(pd, ed), ed) : __ddiv_rn(__dsub_rn(ed, pd), ed);
-                    ev = (q >= tp) || (q <= -sl);
+        if (!ev) return;
+        const bool lng = r < sc.os_f;                     // entry side: long has priority (:784, :799)
+        const unsigned word = flat ? ((unsigned)t | (lng ? 0u : B200BT_EVENT_SELL))
+                                   : ((unsigned)t | B200BT_EVENT_EXIT | (lng_open ? B200BT_EVENT_SELL : 0u));
+        pos = flat ? (lng ? 1 : -1) : 0;
+        rlo = (flat && lng) ? -INFINITY : sc.os_f;
+        rhi = (flat && !lng) ? INFINITY : sc.ob_f;
+        phi = flat ? p * (lng ? sc.hiL_c : sc.hiS_c) : INFINITY;
+        plo = flat ? p * (lng ? sc.loL_c : sc.loS_c) : -INFINITY;
+        e_px = flat ? p : e_px;
+        entry_bar = flat ? t : entry_bar;
+        if (rec) {
+            if (fill == CK_BLOCK && !dead) {
+                const int b = (int)atomicAdd(A.alloc, 1u);
+                if (b >= A.pool_blocks) { atomicExch(A.overflow, 1); dead = true; }
+                else {
+                    A.next[b] = -1;
+                    if (cur_block < 0) A.seg_first[seg] = b; else A.next[cur_block] = b;
+                    cur_block = b; fill = 0;
+                    wptr = A.pool + (int64_t)b * CK_BLOCK;
                 }
             }
-            if (ev) {
-                emit((unsigned)t | B200BT_EVENT_EXIT | (pos > 0 ? B200BT_EVENT_SELL : 0u), p);
-                pos = 0;
-                rlo = sc.os_f; rhi = sc.ob_f; plo = -INFINITY; phi = INFINITY;
-            }
+            if (!dead) { *wptr++ = make_uint2(word, __float_as_uint(p)); ++fill; }
+            ++count;
         }
     };
 
@@ -360,11 +365,10 @@ lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (s
 #pragma unroll 2
             for (int g = 0; g < LS_T / 4; ++g) {
                 const float4 p = pp[g], r = rr[g];
-                const bool any = (r.x < rlo) | (r.x > rhi) | (p.x <= plo) | (p.x >= phi) |
-                                 (r.y < rlo) | (r.y > rhi) | (p.y <= plo) | (p.y >= phi) |
-                                 (r.z < rlo) | (r.z > rhi) | (p.z <= plo) | (p.z >= phi) |
-                                 (r.w < rlo) | (r.w > rhi) | (p.w <= plo) | (p.w >= phi);
-                if (any) {
+                // any bar of the four beyond a threshold?  (fminf / fmaxf drop NaNs, as the per-bar compares do)
+                const float r_min = fminf(fminf(r.x, r.y), fminf(r.z, r.w)), r_max = fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w));
+                const float p_min = fminf(fminf(p.x, p.y), fminf(p.z, p.w)), p_max = fmaxf(fmaxf(p.x, p.y), fmaxf(p.z, p.w));
+                if ((r_min < rlo) | (r_max > rhi) | (p_min <= plo) | (p_max >= phi)) {
                     const int t = t0 + g * 4;
                     step(p.x, r.x, t);
                     step(p.y, r.y, t + 1);
@@ -379,7 +383,21 @@ lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (s
     if (!active) return;
     A.seg_out[seg] = make_int2(pos, pos != 0 ? entry_bar : -1);
     if (c == A.K - 1 && pos != 0)   // force-close at the last bar (:849-876)
-        emit((unsigned)(n - 1) | B200BT_EVENT_EXIT | (pos > 0 ? B200BT_EVENT_SELL : 0u), __ldg(pr + (n - 1)));
+    {
+        rec = true;   // (the last chunk always records: T0 < N)
+        const unsigned word = (unsigned)(n - 1) | B200BT_EVENT_EXIT | (pos > 0 ? B200BT_EVENT_SELL : 0u);
+        if (fill == CK_BLOCK && !dead) {
+            const int b = (int)atomicAdd(A.alloc, 1u);
+            if (b >= A.pool_blocks) { atomicExch(A.overflow, 1); dead = true; }
+            else {
+                A.next[b] = -1;
+                if (cur_block < 0) A.seg_first[seg] = b; else A.next[cur_block] = b;
+                wptr = A.pool + (int64_t)b * CK_BLOCK;
+            }
+        }
+        if (!dead) *wptr = make_uint2(word, __float_as_uint(__ldg(pr + (n - 1))));
+        ++count;
+    }
     A.seg_count[seg] = dead ? 0xffffffffu : count;
 }
 
@@ -787,7 +805,7 @@ extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const fl
                                   int64_t event_cap, unsigned char* lane_invalid, int* overflow_host_or_null,
                                   b200bt_stream_t stream) {
     B200BT_REQUIRE(indiv && workspace && stats && lane_invalid, B200BT_EINVAL, "sweep_tiled: null pointer");
-    B200BT_REQUIRE(pop > 0 && K > 0 && pool_blocks > 0 && warm >= 0, B200BT_EINVAL, "sweep_tiled: bad sizes");
+    B200BT_REQUIRE(pop > 0 && K > 0 && K <= 120 && pool_blocks > 0 && warm >= 0, B200BT_EINVAL, "sweep_tiled: bad sizes (1 <= K <= 120)");
     int rc = check_sweep_args("sweep_tiled", price, ld_price, rsi, ld_rsi, P, S, N, cfg_host, events, event_cap);
     if (rc) return rc;
     B200BT_REQUIRE((int64_t)pop * K * S < (1ll << 31), B200BT_ELIMIT, "sweep_tiled: too many chunks");

@@ -198,28 +198,31 @@ class TilePlan:
     individual gets the same K time chunks, chosen so that the CTAs fill whole waves of the GPU."""
 
     THREADS = 256          # individuals per CTA (csrc/sweep_chunked.cu LS_THREADS)
-    CTAS_PER_SM = 3
+    CTAS_PER_SM = 4
 
     def __init__(self, population: List[Dict], n_bars: int, n_symbols: int, device, warm: int = 8192,
                  max_chunks: int = 64, chunks: Optional[int] = None, pool_scale: float = 1.5,
                  pool_blocks: Optional[int] = None, max_repair_rounds: Optional[int] = None, lo: int = 0,
-                 workspace: Optional[torch.Tensor] = None):
+                 workspace: Optional[torch.Tensor] = None, order_by: str = "cost"):
         pop = len(population)
         self.lo, self.pop = int(lo), pop
         self.warm = int(warm)
-        kmax = max(1, min(max_chunks, n_bars // max(8 * warm, 2048)))
+        kmax = max(1, min(max_chunks, n_bars // max(4 * warm, 2048)))
         if chunks is None:
+            # about 1.5 resident sets of CTAs (measured optimum on the C2 workload: heavy CTAs run longer, so
+            # whole "waves" do not exist), chunks at least 4 warm-ups long
             slots = torch.cuda.get_device_properties(device).multi_processor_count * self.CTAS_PER_SM
             groups = -(-pop // self.THREADS) * n_symbols
-            waves = lambda k: -(-groups * k // slots)
-            # time ~ waves x bars per CTA; ties go to the larger K (shorter serial repair re-scans)
-            chunks = min(range(1, kmax + 1), key=lambda k: (waves(k) * (n_bars / k + (warm if k > 1 else 0)), -k))
+            chunks = min(kmax, max(1, round(1.5 * slots / groups)))
         self.K = int(chunks)
         # a lane that holds one position across many chunks needs one repair round per boundary
         self.max_repair_rounds = int(max_repair_rounds) if max_repair_rounds is not None else min(self.K, 24)
         self.n_seg = pop * self.K
         pred = predicted_events(population, n_bars)
-        self.order = evaluation_order(population)
+        # threads of a CTA wait for each other at every tile: neighbours should cost the same ("cost"), which
+        # matters more than sharing RSI rows ("period": the fused kernel's order)
+        self.order = (np.argsort(-pred, kind="stable").astype(np.int32) if order_by == "cost"
+                      else evaluation_order(population))
         # every segment owns at least one block, and a repaired segment abandons its first chain
         self.pool_blocks = int(pool_scale * pred.sum() * n_symbols / 256) + 2 * self.n_seg * n_symbols + 1024
         if pool_blocks is not None:

@@ -27,8 +27,9 @@ order = torch.from_numpy(evaluation_order(pop)).cuda()
 print("fused %.2f ms" % timed(None, order)); ref = fit.clone()
 ks = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else (0, 7, 11, 15)
 warms = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else (4096, 8192)
-for k, warm in itertools.product(ks, warms):
-    plan = sw.plan_tiles(pop, warm=warm, **({"chunks": k} if k else {}))
+orders = sys.argv[3].split(",") if len(sys.argv) > 3 else ("cost",)
+for k, warm, ob in itertools.product(ks, warms, orders):
+    plan = sw.plan_tiles(pop, warm=warm, order_by=ob, **({"chunks": k} if k else {}))
     ms = timed(plan)
-    print(f"K {plan.K:3d} warm {warm:5d}: {ms:6.2f} ms  invalid lanes {sw.last_invalid_lanes:4d}  "
+    print(f"K {plan.K:3d} warm {warm:5d} order {ob:6s}: {ms:6.2f} ms  invalid lanes {sw.last_invalid_lanes:4d}  "
           f"close {bool(torch.allclose(ref, fit, rtol=1e-9, atol=1e-12, equal_nan=True))}")
