@@ -18,6 +18,7 @@ the hand-written sm_100a kernels behind the C-ABI.
 from __future__ import annotations
 
 import ctypes as C
+import inspect
 from typing import Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -200,6 +201,15 @@ class TilePlan:
     THREADS = 256          # individuals per CTA (csrc/sweep_chunked.cu LS_THREADS)
     CTAS_PER_SM = 4
 
+    @classmethod
+    def chunks_for(cls, pop: int, n_bars: int, n_symbols: int, device, warm: int = 8192, max_chunks: int = 64) -> int:
+        """About 1.5 resident sets of CTAs (measured optimum on the C2 workload: heavy CTAs run longer, so whole
+        "waves" do not exist), chunks at least 4 warm-ups long."""
+        kmax = max(1, min(max_chunks, n_bars // max(4 * warm, 2048)))
+        slots = torch.cuda.get_device_properties(device).multi_processor_count * cls.CTAS_PER_SM
+        groups = -(-pop // cls.THREADS) * n_symbols
+        return min(kmax, max(1, round(1.5 * slots / groups)))
+
     def __init__(self, population: List[Dict], n_bars: int, n_symbols: int, device, warm: int = 8192,
                  max_chunks: int = 64, chunks: Optional[int] = None, pool_scale: float = 1.5,
                  pool_blocks: Optional[int] = None, max_repair_rounds: Optional[int] = None, lo: int = 0,
@@ -207,13 +217,8 @@ class TilePlan:
         pop = len(population)
         self.lo, self.pop = int(lo), pop
         self.warm = int(warm)
-        kmax = max(1, min(max_chunks, n_bars // max(4 * warm, 2048)))
         if chunks is None:
-            # about 1.5 resident sets of CTAs (measured optimum on the C2 workload: heavy CTAs run longer, so
-            # whole "waves" do not exist), chunks at least 4 warm-ups long
-            slots = torch.cuda.get_device_properties(device).multi_processor_count * self.CTAS_PER_SM
-            groups = -(-pop // self.THREADS) * n_symbols
-            chunks = min(kmax, max(1, round(1.5 * slots / groups)))
+            chunks = self.chunks_for(pop, n_bars, n_symbols, device, warm, max_chunks)
         self.K = int(chunks)
         # a lane that holds one position across many chunks needs one repair round per boundary
         self.max_repair_rounds = int(max_repair_rounds) if max_repair_rounds is not None else min(self.K, 24)
@@ -388,6 +393,27 @@ class PopulationSweep:
                           len(self.periods), m.S, m.N, indiv_dev.data_ptr(), redo.data_ptr(), int(redo.numel()),
                           C.byref(self.cfg), self._stats.data_ptr(), _lib.ptr(self._events), self.event_cap, st)
 
+    def plan(self, population: List[Dict]) -> Optional[List]:
+        """The kernel path `evaluate` takes for this population under self.mode: None = fused kernel, else the
+        list of TilePlan / ChunkPlan slices to pass to evaluate_device(plan=...)."""
+        long_enough = self.market.N >= self.chunk_min_bars
+        tiled = self.mode == "tiled"
+        if self.mode == "auto" and long_enough and len(self.periods) <= TILED_MAX_PERIODS:
+            # thread-per-lane needs many machines: enough chunks per lane, or enough lanes (tools/mode_crossover.py:
+            # at 200k bars the warp-per-chunk path is faster below ~2000 individuals x 10 symbols)
+            k = TilePlan.chunks_for(len(population), self.market.N, self.market.S, self.market.device,
+                                    self.chunk_options.get("warm", 8192), self.chunk_options.get("max_chunks", 64))
+            tiled = k >= 16 or len(population) * self.market.S * k >= 100_000
+        if not (tiled or self.mode == "chunked" or (self.mode == "auto" and long_enough)):
+            return None
+        options = dict(self.chunk_options)
+        if not tiled and self.mode == "auto":
+            options.setdefault("target_events", 8192)
+        if getattr(self, "last_pool_overflow", False):      # the previous sweep ran out of event pool: plan larger
+            options["pool_scale"] = 4.0 * options.get("pool_scale", 1.5)
+            options.pop("pool_blocks", None)
+        return self.plan_batches(population, tiled=tiled, **options)
+
     def plan_tiles(self, population: List[Dict], **kw) -> "TilePlan":
         return TilePlan(population, self.market.N, self.market.S, self.market.device, **kw)
 
@@ -399,6 +425,8 @@ class PopulationSweep:
         and share one workspace: large populations (BASELINE configs[4]: 10 000 x 50 symbols) record more
         events than fit in HBM at once, so they go through the chunked kernels slice by slice."""
         cls = TilePlan if tiled else ChunkPlan
+        accepted = inspect.signature(cls.__init__).parameters     # chunk_options may carry the other path's knobs
+        kw = {k: v for k, v in kw.items() if k in accepted}
         if kw.get("pool_blocks") is not None:
             return [cls(population, self.market.N, self.market.S, self.market.device, **kw)]
         pred = predicted_events(population, self.market.N) * self.market.S * 8 * kw.get("pool_scale", 1.5)
@@ -450,15 +478,7 @@ class PopulationSweep:
         indiv_dev = staged[:nbytes]
         order_dev = staged[nbytes:].view(torch.int32)
         fit = torch.empty(pop, dtype=torch.float64, device=dev)
-        plan = None
-        tiled = self.mode == "tiled" or (self.mode == "auto" and self.market.N >= self.chunk_min_bars
-                                         and len(self.periods) <= TILED_MAX_PERIODS)
-        if tiled or self.mode == "chunked" or (self.mode == "auto" and self.market.N >= self.chunk_min_bars):
-            plan = self.plan_batches(population, tiled=tiled, **self.chunk_options)
-            if getattr(self, "last_pool_overflow", False):
-                grown = dict(self.chunk_options, pool_scale=4.0 * self.chunk_options.get("pool_scale", 1.5))
-                grown.pop("pool_blocks", None)
-                plan = self.plan_batches(population, tiled=tiled, **grown)
+        plan = self.plan(population)
         self.evaluate_device(indiv_dev, order_dev, pop, fit, plan=plan)
         self._inverse = expand
         out = self._pinned_out[:pop]

@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--symbols", type=int, default=N_SYMBOLS)
     ap.add_argument("--bars", type=int, default=N_BARS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="auto", choices=["auto", "fused", "chunked"], help="sweep kernel path (auto = product default)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "fused", "chunked", "tiled"], help="sweep kernel path (auto = product default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -228,7 +228,7 @@ def main():
     # synthetic market, identical on every rank (replicated), pinned on the host for the e2e leg
     ohlcv_host = torch.from_numpy(synth.synth_ohlcv(S, N)).pin_memory()
     market = MarketData(ohlcv_host)
-    sweep = PopulationSweep(market)
+    sweep = PopulationSweep(market, mode=args.mode)
     population = synth.random_population(pop_global, seed=42)
     my_pop = population[rank * pop_local:(rank + 1) * pop_local]
     packed = decode_population(my_pop, sweep.period_row)
@@ -237,7 +237,10 @@ def main():
     order_dev = torch.from_numpy(order).to(dev)
     fit_local = torch.empty(pop_local, dtype=torch.float64, device=dev)
     fit_global = torch.empty(pop_global, dtype=torch.float64, device=dev)
-    plan = sweep.plan_chunks(my_pop) if (args.mode == "chunked" or (args.mode == "auto" and N >= sweep.chunk_min_bars)) else None
+    plan = sweep.plan(my_pop)          # the path sweep.evaluate() takes: None = fused kernel, else tile / chunk plans
+    path = "fused" if plan is None else ("tiled" if type(plan[0]).__name__ == "TilePlan" else "chunked")
+    path_kernels = {"fused": "sweep_kernel", "chunked": "chunk_scan_kernel + chunk_sums/partial/lane_combine",
+                    "tiled": "lane_scan_kernel + chunk_sums/partial/lane_combine"}[path]
 
     def step():
         sweep.evaluate_device(indiv_dev, order_dev, pop_local, fit_local, plan=plan)
@@ -289,7 +292,7 @@ def main():
     # ---- end-to-end leg: host OHLCV + host population in, host fitness out ----
     def e2e_step():
         mk = MarketData(ohlcv_host)                      # H2D of the pinned OHLCV (5 fields)
-        sw = PopulationSweep(mk)                         # RSI bank on device
+        sw = PopulationSweep(mk, mode=args.mode)         # RSI bank on device
         f = sw.evaluate(my_pop)                          # H2D params, sweep, reduce, D2H fitness
         if world > 1:
             g = torch.from_numpy(f).to(dev)
@@ -326,9 +329,9 @@ def main():
             "config": {"workload": f"GA fitness sweep (BASELINE configs[1] per GPU): population {pop_local}/GPU x {S} symbols x {N} 1-min bars, reference RSI rule",
                        "global_population": pop_global, "symbols": S, "bars": N, "parallelism": f"individuals sharded x{world}, market replicated, 1 all-gather/generation" if world > 1 else "single GPU",
                        "l2_policy": "inputs larger than L2 (price+RSI bank = %.2f GB per GPU)" % ((S * N * 4 + sweep.bank.numel() * 4) / 1e9)},
-            "roofline": {"bound": "hbm", "kernel": ("chunk_scan_kernel + chunk_metrics_kernel" if plan is not None else "sweep_kernel"), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": path_kernels, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "bytes_per_eval": BYTES_PER_EVAL,
-                         "kernel_ms": ms_kernel, "sweep_mode": ("chunked" if plan is not None else "fused"), "note": "achieved = 8 B x evals per sweep / CUDA-event duration of the sweep kernels (scan, verify/repair, metrics, fitness reduce); lanes sharing a (symbol, period) stream are served from L1/L2, so DRAM traffic is far below the algorithmic bytes (see profiles/)"},
+                         "kernel_ms": ms_kernel, "sweep_mode": path, "note": "achieved = 8 B x evals per sweep / CUDA-event duration of the sweep kernels (scan, verify/repair, metrics, fitness reduce); lanes sharing a (symbol, period) stream are served from L1/L2, so DRAM traffic is far below the algorithmic bytes (see profiles/)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "path": "MarketData(pinned host OHLCV) -> PopulationSweep (RSI bank) -> evaluate(list of dicts) -> host fitness"},
             "gpu_launches": int(launches),
