@@ -226,7 +226,10 @@ chunk_scan_kernel(const ChunkScanArgs A) {   // by value, not __grid_constant__ 
 #endif
 constexpr int LS_T = B200BT_LS_T;       // bars per tile
 constexpr int LS_STRIDE = LS_T + 4;     // row stride in floats (16-byte aligned rows, rows 8 apart share banks)
-constexpr int LS_THREADS = 256;
+#ifndef B200BT_LS_THREADS
+#define B200BT_LS_THREADS 256
+#endif
+constexpr int LS_THREADS = B200BT_LS_THREADS;
 
 struct LaneScanArgs {
     const float* price; int64_t ld_price;

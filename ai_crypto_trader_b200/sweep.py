@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import inspect
+import os
 from typing import Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -116,17 +117,26 @@ def decode_population(population: List[Dict], period_row: Dict[int, int]) -> np.
                    ("take_profit", "<f8"), ("stop_loss", "<f8"), ("position_size", "<f8")])
     assert dt.itemsize == C.sizeof(_lib.Individual)
     out = np.zeros(len(population), dtype=dt)
-    for i, p in enumerate(population):
-        period = int(p.get("rsi_period", 14))
-        if period not in period_row:
-            raise KeyError(f"rsi_period {period} is not in the RSI bank {sorted(period_row)}")
-        out["rsi_row"][i] = period_row[period]
-        out["rsi_lo"][i] = _f32_up(float(p.get("rsi_oversold", 30)))
-        out["rsi_hi"][i] = _f32_down(float(p.get("rsi_overbought", 70)))
-        # strategy_evaluation.py:762-764, :773-774 (same float64 expressions)
-        out["take_profit"][i] = p.get("take_profit", 3) / 100
-        out["stop_loss"][i] = p.get("stop_loss", 2) / 100
-        out["position_size"][i] = 10000 * (min(p.get("max_position_size", 5), 20) / 100)
+    g = lambda key, default: np.array([p.get(key, default) for p in population], dtype=np.float64)
+    period = g("rsi_period", 14).astype(np.int64)
+    rows = np.full(int(period.max()) + 2 if len(period) else 1, -1, dtype=np.int64)
+    for w, r in period_row.items():
+        if 0 <= w < len(rows):
+            rows[w] = r
+    row = rows[np.clip(period, 0, len(rows) - 1)]
+    if len(period) and (period.min() < 0 or row.min() < 0):
+        bad = int(period[(row < 0) | (period < 0)][0])
+        raise KeyError(f"rsi_period {bad} is not in the RSI bank {sorted(period_row)}")
+    out["rsi_row"] = row
+    # thresholds rounded towards the side that keeps `rsi < oversold` / `rsi > overbought` exact in fp32
+    lo, hi = g("rsi_oversold", 30), g("rsi_overbought", 70)
+    lo32, hi32 = lo.astype(np.float32), hi.astype(np.float32)
+    out["rsi_lo"] = np.where(lo32.astype(np.float64) >= lo, lo32, np.nextafter(lo32, np.float32(np.inf)))
+    out["rsi_hi"] = np.where(hi32.astype(np.float64) <= hi, hi32, np.nextafter(hi32, np.float32(-np.inf)))
+    # strategy_evaluation.py:762-764, :773-774 (same float64 expressions)
+    out["take_profit"] = g("take_profit", 3) / 100
+    out["stop_loss"] = g("stop_loss", 2) / 100
+    out["position_size"] = 10000 * (np.minimum(g("max_position_size", 5), 20) / 100)
     return out
 
 
@@ -147,7 +157,27 @@ TILED_MAX_PERIODS = 68      # shared-memory tile of the thread-per-lane sweep: 2
 
 def predicted_events(population: List[Dict], n_bars: int) -> np.ndarray:
     """Expected trade records per (individual, symbol) lane under the lane_cost model."""
-    return EVENTS_PER_COST_BAR * np.array([lane_cost(p) for p in population]) * n_bars
+    return EVENTS_PER_COST_BAR * lane_costs(population) * n_bars
+
+
+def lane_costs(population: List[Dict]) -> np.ndarray:
+    """lane_cost for a whole population (vectorised)."""
+    from scipy.special import ndtr
+    g = lambda key, default: np.array([float(p.get(key, default)) for p in population], dtype=np.float64)
+    sd = 44.0 / np.sqrt(np.maximum(g("rsi_period", 14).astype(np.int64), 1))
+    return ndtr((g("rsi_oversold", 30) - 50.0) / sd) + 1.0 - ndtr((g("rsi_overbought", 70) - 50.0) / sd)
+
+
+_PINNED_FLAG = None
+
+
+def _pinned_flag() -> torch.Tensor:
+    """One pinned int32 the kernels' pool-overflow flag is copied into (page-locking memory is slow: shared by
+    every plan; each sweep call reads it right after its own stream synchronisation)."""
+    global _PINNED_FLAG
+    if _PINNED_FLAG is None:
+        _PINNED_FLAG = torch.zeros(1, dtype=torch.int32).pin_memory()
+    return _PINNED_FLAG
 
 
 class ChunkPlan:
@@ -190,7 +220,7 @@ class ChunkPlan:
         else:
             self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
         self.invalid = torch.zeros((pop, n_symbols), dtype=torch.uint8, device=device)
-        self.overflow = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.overflow = _pinned_flag()
         self.pop = pop
 
 
@@ -198,8 +228,8 @@ class TilePlan:
     """Host-side plan of the thread-per-lane sweep (b200bt_sweep_tiled) for one population slice: every
     individual gets the same K time chunks, chosen so that the CTAs fill whole waves of the GPU."""
 
-    THREADS = 256          # individuals per CTA (csrc/sweep_chunked.cu LS_THREADS)
-    CTAS_PER_SM = 4
+    THREADS = int(os.environ.get("B200BT_LS_THREADS", 256))     # individuals per CTA (csrc/sweep_chunked.cu LS_THREADS)
+    CTAS_PER_SM = int(os.environ.get("B200BT_LS_CTAS", 4))
 
     @classmethod
     def chunks_for(cls, pop: int, n_bars: int, n_symbols: int, device, warm: int = 8192, max_chunks: int = 64) -> int:
@@ -239,7 +269,7 @@ class TilePlan:
         else:
             self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
         self.invalid = torch.zeros((pop, n_symbols), dtype=torch.uint8, device=device)
-        self.overflow = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.overflow = _pinned_flag()
 
 
 def evaluation_order(population: List[Dict]) -> np.ndarray:
@@ -250,8 +280,8 @@ def evaluation_order(population: List[Dict]) -> np.ndarray:
     fraction of time RSI(w) spends outside [oversold, overbought]; RSI(w) is roughly
     N(50, 44/sqrt(w)) on 1-minute data.  Only scheduling depends on this, never results.
     """
-    keys = sorted((int(p.get("rsi_period", 14)), -lane_cost(p), i) for i, p in enumerate(population))
-    return np.array([k[2] for k in keys], dtype=np.int32)
+    period = np.array([int(p.get("rsi_period", 14)) for p in population], dtype=np.int64)
+    return np.lexsort((np.arange(len(population)), -lane_costs(population), period)).astype(np.int32)
 
 
 class PopulationSweep:

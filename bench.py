@@ -241,6 +241,11 @@ def main():
     path = "fused" if plan is None else ("tiled" if type(plan[0]).__name__ == "TilePlan" else "chunked")
     path_kernels = {"fused": "sweep_kernel", "chunked": "chunk_scan_kernel + chunk_sums/partial/lane_combine",
                     "tiled": "lane_scan_kernel + chunk_sums/partial/lane_combine"}[path]
+    # DRAM bytes (read + write) of the dominant kernel per launch on THIS workload, from the committed
+    # `ncu --set full` captures (profiles/r1_lane_scan_ncu.txt, r1_chunk_scan_ncu.txt, r1_sweep_v2_ncu.txt);
+    # null for any other workload size
+    ncu_traffic = {"tiled": 4.581e9 + 1.032e9, "chunked": 45.6e9, "fused": 3.3e9}[path] \
+        if (pop_local, S, N) == (POP_PER_GPU, N_SYMBOLS, N_BARS) else None
 
     def step():
         sweep.evaluate_device(indiv_dev, order_dev, pop_local, fit_local, plan=plan)
@@ -330,7 +335,7 @@ def main():
                        "global_population": pop_global, "symbols": S, "bars": N, "parallelism": f"individuals sharded x{world}, market replicated, 1 all-gather/generation" if world > 1 else "single GPU",
                        "l2_policy": "inputs larger than L2 (price+RSI bank = %.2f GB per GPU)" % ((S * N * 4 + sweep.bank.numel() * 4) / 1e9)},
             "roofline": {"bound": "hbm", "kernel": path_kernels, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_eval": BYTES_PER_EVAL,
+                         "traffic": ncu_traffic, "traffic_unit": "bytes per launch of the dominant kernel (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "peak_source": peak_src, "bytes_per_eval": BYTES_PER_EVAL,
                          "kernel_ms": ms_kernel, "sweep_mode": path, "note": "achieved = 8 B x evals per sweep / CUDA-event duration of the sweep kernels (scan, verify/repair, metrics, fitness reduce); lanes sharing a (symbol, period) stream are served from L1/L2, so DRAM traffic is far below the algorithmic bytes (see profiles/)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "path": "MarketData(pinned host OHLCV) -> PopulationSweep (RSI bank) -> evaluate(list of dicts) -> host fitness"},
