@@ -16,6 +16,7 @@
 //                   of chunk c for every boundary and merges the chunks' partial metrics.
 // A lane with any mismatching boundary is flagged; the host re-evaluates flagged lanes with the
 // fused (serial) kernel, so results never depend on the speculation being right.
+#include <stdlib.h>
 #include "sweep_dev.cuh"
 
 namespace b200bt {
@@ -33,6 +34,7 @@ struct ChunkScanArgs {
     int* seg_first; unsigned* seg_count; int2* seg_in; int2* seg_out; int* overflow;
     const int4* repair;   // REPAIR launches: (individual, chunk, segment, symbol) per work item
     const int32_t* n_chunks;
+    unsigned char* redo;  // REPAIR launches of the overlapped tail: individuals whose metrics must be recomputed
 };
 
 __device__ __forceinline__ int64_t chunk_begin(int64_t N, int c, int K) {
@@ -56,6 +58,7 @@ chunk_scan_kernel(const ChunkScanArgs A) {   // by value, not __grid_constant__ 
         const int4 r = A.repair[it];
         item.individual = r.x; item.chunk = r.y; item.segment = r.z; item.n_chunks = A.n_chunks[r.x];
         sym = r.w;
+        if (A.redo && lane == 0) A.redo[r.x] = 1;
     } else {
         sym = (int)(blockIdx.x % (unsigned)A.S);
         it = (int)(blockIdx.x / (unsigned)A.S) * SW_WARPS + (threadIdx.x >> 5);
@@ -458,11 +461,11 @@ chunk_sums_kernel(const float* __restrict__ price, int64_t ld_price, const b200b
                   const b200bt_chunk_item* __restrict__ items, int n_items, int S, int n_seg,
                   const uint2* __restrict__ pool, const int* __restrict__ next, const int* __restrict__ seg_first,
                   const unsigned* __restrict__ seg_count, const int2* __restrict__ seg_in,
-                  double* __restrict__ seg_sum, double* __restrict__ seg_max) {
+                  double* __restrict__ seg_sum, double* __restrict__ seg_max, const int* __restrict__ n_items_dev) {
     const int lane = threadIdx.x & 31;
     const int sym = (int)(blockIdx.x % (unsigned)S);
     const int it = (int)(blockIdx.x / (unsigned)S) * 4 + (threadIdx.x >> 5);
-    if (it >= n_items) return;
+    if (it >= (n_items_dev ? *n_items_dev : n_items)) return;
     const b200bt_chunk_item item = items[it];
     const int seg = sym * n_seg + item.segment;
     const double size = indiv[item.individual].position_size;
@@ -493,7 +496,7 @@ chunk_sums_kernel(const float* __restrict__ price, int64_t ld_price, const b200b
         p_carry = __shfl_sync(FULL, pf, cnt - 1);
         left -= cnt;
         off += 32;
-        if (off == CK_BLOCK && left) { b = next[b]; off = 0; }
+        if (off == CK_BLOCK && left) { b = next[b]; off = 0; if (b < 0) break; }
     }
     if (lane == 0) { seg_sum[seg] = run; seg_max[seg] = best; }
 }
@@ -505,12 +508,12 @@ chunk_partial_kernel(const float* __restrict__ price, int64_t ld_price, const b2
                      const unsigned* __restrict__ seg_count, const int2* __restrict__ seg_in,
                      const double* __restrict__ seg_sum, const double* __restrict__ seg_max,
                      const b200bt_sweep_config cfg, uint32_t* __restrict__ events, int64_t ev_cap,
-                     ChunkPartial* __restrict__ partial) {
+                     ChunkPartial* __restrict__ partial, const int* __restrict__ n_items_dev) {
     __shared__ WarpAcc s_acc[4];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int sym = (int)(blockIdx.x % (unsigned)S);
     const int it = (int)(blockIdx.x / (unsigned)S) * 4 + wid;
-    if (it >= n_items) return;
+    if (it >= (n_items_dev ? *n_items_dev : n_items)) return;
     const b200bt_chunk_item item = items[it];
     const int seg = sym * n_seg + item.segment;
     const int base = seg - item.chunk;
@@ -560,7 +563,7 @@ chunk_partial_kernel(const float* __restrict__ price, int64_t ld_price, const b2
         p_carry = __shfl_sync(FULL, __uint_as_float(ev.y), cnt - 1);
         left -= cnt;
         off += 32;
-        if (off == CK_BLOCK && left) { b = next[b]; off = 0; }
+        if (off == CK_BLOCK && left) { b = next[b]; off = 0; if (b < 0) break; }
     }
     if (lane == 0) {
         const WarpAcc& a = *acc;
@@ -572,6 +575,15 @@ chunk_partial_kernel(const float* __restrict__ price, int64_t ld_price, const b2
         q.first_done = a.first_done; q.first_day = a.first_day; q.day_cur = (int)a.day_cur; q.pad = 0;
         partial[seg] = q;
     }
+}
+
+// Work items (all chunks) of the individuals flagged in `redo`, for the recomputation after the overlapped repairs.
+__global__ void fix_items_kernel(const b200bt_chunk_item* __restrict__ items, int n_items, const unsigned char* __restrict__ redo,
+                                 b200bt_chunk_item* __restrict__ out, int* __restrict__ n_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const b200bt_chunk_item it = items[i];
+    if (redo[it.individual]) out[atomicAdd(n_out, 1)] = it;
 }
 
 __global__ void lane_combine_kernel(const b200bt_individual* __restrict__ indiv, int pop, int S,
@@ -652,13 +664,15 @@ namespace {
 struct ChunkWorkspace {
     uint2* pool; int2* seg_in; int2* seg_out; int* seg_first; unsigned* seg_count; unsigned* alloc; int* overflow;
     unsigned* n_repair; int4* repair; int* next; ChunkPartial* partial; double* seg_sum; double* seg_max;
+    b200bt_chunk_item* fix_items; int* n_fix; unsigned char* redo;   // overlapped repair tail (n_seg items, pop flags)
     unsigned char* end;
 };
 
 // pool[pool_blocks][256] uint2 | seg_in[segs] int2 | seg_out[segs] int2 | seg_first[segs] | seg_count[segs] |
 // alloc, overflow, n_repair, pad | repair[segs] int4 | next[pool_blocks] | (16-byte aligned) partial[segs] (128 B) |
-// seg_sum[segs] | seg_max[segs]      (wide types first: the base must be 16-byte aligned)
-ChunkWorkspace carve(void* workspace, int pool_blocks, int64_t segs) {
+// seg_sum[segs] | seg_max[segs] | fix_items[n_seg] (16 B) | n_fix (16 B) | redo[pop]
+// (wide types first: the base must be 16-byte aligned)
+ChunkWorkspace carve(void* workspace, int pool_blocks, int64_t segs, int n_seg, int pop) {
     ChunkWorkspace w;
     w.pool = (uint2*)workspace;
     w.seg_in = (int2*)(w.pool + (int64_t)pool_blocks * CK_BLOCK);
@@ -673,16 +687,55 @@ ChunkWorkspace carve(void* workspace, int pool_blocks, int64_t segs) {
     w.partial = (ChunkPartial*)(((uintptr_t)(w.next + pool_blocks) + 15) & ~(uintptr_t)15);
     w.seg_sum = (double*)(w.partial + segs);
     w.seg_max = w.seg_sum + segs;
-    w.end = (unsigned char*)(w.seg_max + segs);
+    w.fix_items = (b200bt_chunk_item*)(w.seg_max + segs);
+    w.n_fix = (int*)(w.fix_items + n_seg);
+    w.redo = (unsigned char*)(w.n_fix + 4);
+    w.end = w.redo + ((pop + 15) & ~15);
     return w;
 }
 
-int64_t chunk_workspace_bytes(int pool_blocks, int64_t segs) {
+int64_t chunk_workspace_bytes(int pool_blocks, int64_t segs, int n_seg, int pop) {
     return (int64_t)pool_blocks * CK_BLOCK * 8 + segs * 16 + (segs * 2 + 4) * 4 + segs * 16 + (int64_t)pool_blocks * 4 + 16 +
-           segs * (int64_t)(sizeof(ChunkPartial) + 16);
+           segs * (int64_t)(sizeof(ChunkPartial) + 16) + (int64_t)n_seg * 16 + 16 + ((pop + 15) & ~15);
+}
+
+// second stream + events for the overlapped repair tail, one set per device
+struct SideStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+int side_stream(SideStream** out) {
+    static SideStream table[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_status(e, "cudaGetDevice");
+    B200BT_REQUIRE(dev >= 0 && dev < 64, B200BT_ELIMIT, "device ordinal %d out of range", dev);
+    SideStream& s = table[dev];
+    if (!s.stream) {
+        int lo_p = 0, hi_p = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);   // highest priority: its few small kernels go first
+        e = cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, hi_p);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
+        if (e != cudaSuccess) { s.stream = nullptr; return cuda_status(e, "side stream"); }
+    }
+    *out = &s;
+    return B200BT_OK;
+}
+
+// rounds on the critical path; later ones run beside the metrics kernels (B200BT_MAIN_REPAIR_ROUNDS overrides, for tuning)
+int main_repair_rounds() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200BT_MAIN_REPAIR_ROUNDS");
+        v = e ? atoi(e) : 2;
+    }
+    return v;
 }
 
 // Everything after the speculative scan: verify -> repair rounds -> chunk-parallel metrics.
+//
+// Almost all wrong chunks are fixed by the first two rounds; what remains is a handful of lanes whose
+// trajectories never merge (always in the market) and which are re-scanned chunk after chunk, one round per
+// chunk, by a single warp each.  Those rounds run on a second stream BESIDE the metrics kernels of all lanes;
+// the individuals they touch are flagged and only their metrics are recomputed afterwards.
 int finish_chunks(const ChunkScanArgs& A, const ChunkWorkspace& w, const b200bt_chunk_item* items, int n_items,
                   const int32_t* seg_base, int pop, int max_repair_rounds, const b200bt_sweep_config* cfg_host,
                   b200bt_lane_stats* stats, uint32_t* events, int64_t event_cap, unsigned char* lane_invalid,
@@ -693,36 +746,67 @@ int finish_chunks(const ChunkScanArgs& A, const ChunkWorkspace& w, const b200bt_
     const size_t smem = sizeof(WarpShared) * SW_WARPS;
     cudaError_t e = cudaFuncSetAttribute(kern_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: cudaFuncSetAttribute");
-    // verify -> repair rounds: a chunk whose assumed state was wrong is re-scanned from the true state; chunks
-    // behind a wrong predecessor wait for the next round.  Each round costs one tiny verify launch, a 4-byte
-    // readback (stream synchronisation) and, if anything is listed, one repair launch.
-    for (int round = 0; round < max_repair_rounds; ++round) {
-        e = cudaMemsetAsync(w.n_repair, 0, sizeof(unsigned), st);
-        if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: memset");
-        const int64_t lanes = (int64_t)pop * S;
-        chunk_verify_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pop, S, seg_base, A.n_chunks, n_seg, w.seg_count,
-                                                                            w.seg_in, w.seg_out, w.repair, w.n_repair);
-        B200BT_LAUNCH_CHECK("chunk_verify launch");
-        unsigned h_rep = 0;
-        e = cudaMemcpyAsync(&h_rep, w.n_repair, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: verify readback");
-        if (h_rep == 0) break;
-        ChunkScanArgs R = A;
-        R.n_items = (int)h_rep;
-        kern_fix<<<(h_rep + SW_WARPS - 1) / SW_WARPS, SW_WARPS * 32, smem, st>>>(R);
-        B200BT_LAUNCH_CHECK("chunk_repair launch");
-    }
+    const int64_t lanes = (int64_t)pop * S;
     const int64_t mblocks = (int64_t)((n_items + 3) / 4) * S;
     B200BT_REQUIRE(mblocks < (1ll << 31), B200BT_ELIMIT, "sweep_chunked: too many work items");
-    chunk_sums_kernel<<<(unsigned)mblocks, 128, 0, st>>>(A.price, A.ld_price, A.indiv, items, n_items, S, n_seg, w.pool, w.next,
-                                                          w.seg_first, w.seg_count, w.seg_in, w.seg_sum, w.seg_max);
-    B200BT_LAUNCH_CHECK("chunk_sums launch");
-    chunk_partial_kernel<<<(unsigned)mblocks, 128, 0, st>>>(A.price, A.ld_price, A.indiv, items, n_items, S, n_seg, w.pool, w.next,
-                                                             w.seg_first, w.seg_count, w.seg_in, w.seg_sum, w.seg_max, *cfg_host,
-                                                             events, event_cap, w.partial);
-    B200BT_LAUNCH_CHECK("chunk_partial launch");
-    const int64_t lanes = (int64_t)pop * S;
+
+    // one verify -> (readback) -> repair round on stream `rs`; *left = chunks listed (0: everything is consistent)
+    auto repair_round = [&](cudaStream_t rs, unsigned char* redo, unsigned* left) -> int {
+        cudaError_t er = cudaMemsetAsync(w.n_repair, 0, sizeof(unsigned), rs);
+        if (er != cudaSuccess) return cuda_status(er, "sweep_chunked: memset");
+        chunk_verify_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, rs>>>(pop, S, seg_base, A.n_chunks, n_seg, w.seg_count,
+                                                                             w.seg_in, w.seg_out, w.repair, w.n_repair);
+        B200BT_LAUNCH_CHECK("chunk_verify launch");
+        unsigned h_rep = 0;
+        er = cudaMemcpyAsync(&h_rep, w.n_repair, sizeof(unsigned), cudaMemcpyDeviceToHost, rs);
+        if (er == cudaSuccess) er = cudaStreamSynchronize(rs);
+        if (er != cudaSuccess) return cuda_status(er, "sweep_chunked: verify readback");
+        *left = h_rep;
+        if (h_rep == 0) return B200BT_OK;
+        ChunkScanArgs R = A;
+        R.n_items = (int)h_rep;
+        R.redo = redo;
+        kern_fix<<<(h_rep + SW_WARPS - 1) / SW_WARPS, SW_WARPS * 32, smem, rs>>>(R);
+        B200BT_LAUNCH_CHECK("chunk_repair launch");
+        return B200BT_OK;
+    };
+    auto metrics = [&](const b200bt_chunk_item* its, const int* n_dev) -> int {
+        chunk_sums_kernel<<<(unsigned)mblocks, 128, 0, st>>>(A.price, A.ld_price, A.indiv, its, n_items, S, n_seg, w.pool, w.next,
+                                                              w.seg_first, w.seg_count, w.seg_in, w.seg_sum, w.seg_max, n_dev);
+        B200BT_LAUNCH_CHECK("chunk_sums launch");
+        chunk_partial_kernel<<<(unsigned)mblocks, 128, 0, st>>>(A.price, A.ld_price, A.indiv, its, n_items, S, n_seg, w.pool, w.next,
+                                                                 w.seg_first, w.seg_count, w.seg_in, w.seg_sum, w.seg_max,
+                                                                 *cfg_host, events, event_cap, w.partial, n_dev);
+        B200BT_LAUNCH_CHECK("chunk_partial launch");
+        return B200BT_OK;
+    };
+
+    // rounds on the critical path
+    int round = 0, rc = B200BT_OK;
+    unsigned left = 1;
+    for (; round < max_repair_rounds && round < main_repair_rounds() && left; ++round)
+        if ((rc = repair_round(st, nullptr, &left))) return rc;
+    const bool tail = left != 0 && round < max_repair_rounds;   // a repair was just launched and more rounds are allowed
+    SideStream* side = nullptr;
+    if (tail) {
+        if ((rc = side_stream(&side))) return rc;
+        e = cudaMemsetAsync(w.n_fix, 0, 16 + ((pop + 15) & ~15), st);   // n_fix + redo flags
+        if (e == cudaSuccess) e = cudaEventRecord(side->fork, st);
+        if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: fork");
+    }
+    if ((rc = metrics(items, nullptr))) return rc;
+    if (tail) {
+        e = cudaStreamWaitEvent(side->stream, side->fork, 0);
+        if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: side wait");
+        for (; round < max_repair_rounds && left; ++round)
+            if ((rc = repair_round(side->stream, w.redo, &left))) return rc;
+        e = cudaEventRecord(side->join, side->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, side->join, 0);
+        if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: join");
+        fix_items_kernel<<<(n_items + 255) / 256, 256, 0, st>>>(items, n_items, w.redo, w.fix_items, w.n_fix);
+        B200BT_LAUNCH_CHECK("fix_items launch");
+        if ((rc = metrics(w.fix_items, w.n_fix))) return rc;
+    }
     lane_combine_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(A.indiv, pop, S, seg_base, A.n_chunks, n_seg, w.seg_count,
                                                                         w.seg_in, w.seg_out, w.partial, *cfg_host, stats,
                                                                         lane_invalid);
@@ -750,7 +834,7 @@ int check_sweep_args(const char* who, const float* price, int64_t ld_price, cons
 }  // namespace
 
 extern "C" int64_t b200bt_sweep_chunked_workspace_bytes(int pool_blocks, int S, int n_seg) {
-    return chunk_workspace_bytes(pool_blocks, (int64_t)S * n_seg);
+    return chunk_workspace_bytes(pool_blocks, (int64_t)S * n_seg, n_seg, n_seg);   // pop <= n_seg
 }
 
 extern "C" int b200bt_sweep_chunked(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S,
@@ -773,7 +857,8 @@ extern "C" int b200bt_sweep_chunked(const float* price, int64_t ld_price, const 
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t segs = (int64_t)S * n_seg;
-    const ChunkWorkspace w = carve(workspace, pool_blocks, segs);
+    B200BT_REQUIRE(pop <= n_seg, B200BT_EINVAL, "sweep_chunked: fewer segments than individuals");
+    const ChunkWorkspace w = carve(workspace, pool_blocks, segs, n_seg, pop);
     cudaError_t e = cudaMemsetAsync(w.seg_in, 0, (size_t)(segs * 6 + 4) * 4, st);
     if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: memset");
 
@@ -782,7 +867,7 @@ extern "C" int b200bt_sweep_chunked(const float* price, int64_t ld_price, const 
     A.indiv = indiv; A.items = items; A.n_items = n_items; A.n_seg = n_seg; A.warm = warm;
     A.pool = w.pool; A.pool_blocks = pool_blocks; A.next = w.next; A.alloc = w.alloc;
     A.seg_first = w.seg_first; A.seg_count = w.seg_count; A.seg_in = w.seg_in; A.seg_out = w.seg_out; A.overflow = w.overflow;
-    A.repair = w.repair; A.n_chunks = n_chunks;
+    A.repair = w.repair; A.n_chunks = n_chunks; A.redo = nullptr;
     const bool vec16 = (((uintptr_t)price | (uintptr_t)rsi) & 15) == 0 && ld_price % 4 == 0 && ld_rsi % 4 == 0;
     auto kern = vec16 ? chunk_scan_kernel<true, false> : chunk_scan_kernel<false, false>;
     const size_t smem = sizeof(WarpShared) * SW_WARPS;
@@ -798,7 +883,7 @@ extern "C" int b200bt_sweep_chunked(const float* price, int64_t ld_price, const 
 
 extern "C" int64_t b200bt_sweep_tiled_workspace_bytes(int pool_blocks, int S, int pop, int K) {
     const int64_t n_seg = (int64_t)pop * K;
-    return chunk_workspace_bytes(pool_blocks, S * n_seg) + 16 + n_seg * 16 + (int64_t)pop * 8;
+    return chunk_workspace_bytes(pool_blocks, S * n_seg, (int)n_seg, pop) + 16 + n_seg * 16 + (int64_t)pop * 8;
 }
 
 extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S,
@@ -823,7 +908,7 @@ extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const fl
     cudaStream_t st = (cudaStream_t)stream;
     const int n_seg = pop * K;
     const int64_t segs = (int64_t)S * n_seg;
-    const ChunkWorkspace w = carve(workspace, pool_blocks, segs);
+    const ChunkWorkspace w = carve(workspace, pool_blocks, segs, n_seg, pop);
     b200bt_chunk_item* items = (b200bt_chunk_item*)(((uintptr_t)w.end + 15) & ~(uintptr_t)15);
     int32_t* seg_base = (int32_t*)(items + n_seg);
     int32_t* n_chunks = seg_base + pop;
@@ -851,7 +936,7 @@ extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const fl
     A.indiv = indiv; A.items = items; A.n_items = n_seg; A.n_seg = n_seg; A.warm = warm;
     A.pool = w.pool; A.pool_blocks = pool_blocks; A.next = w.next; A.alloc = w.alloc;
     A.seg_first = w.seg_first; A.seg_count = w.seg_count; A.seg_in = w.seg_in; A.seg_out = w.seg_out; A.overflow = w.overflow;
-    A.repair = w.repair; A.n_chunks = n_chunks;
+    A.repair = w.repair; A.n_chunks = n_chunks; A.redo = nullptr;
     return finish_chunks(A, w, items, n_seg, seg_base, pop, max_repair_rounds, cfg_host, stats, events, event_cap, lane_invalid,
                          overflow_host_or_null, st);
 }
