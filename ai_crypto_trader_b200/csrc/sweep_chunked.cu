@@ -270,9 +270,17 @@ lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (s
     const bool active = k < A.pop;
     const int ind = active ? (A.order ? A.order[k] : k) : 0;
     const b200bt_individual iv = A.indiv[ind];
-    ScanConst sc;
-    init_scan_const(sc, iv);
-    const double tp = iv.take_profit, sl = iv.stop_loss;
+    // the screening multipliers are needed on events only: shared memory, [multiplier][thread] (conflict-free),
+    // side-major so that the side selects an address instead of a value: long hi_c lo_c hi_d lo_d, short ...
+    __shared__ float ls_mul[8][LS_THREADS];
+    const float os_f = iv.rsi_lo, ob_f = iv.rsi_hi;
+    {
+        ScanConst sc;
+        init_scan_const(sc, iv);
+        float* m = &ls_mul[0][threadIdx.x];
+        m[0 * LS_THREADS] = sc.hiL_c; m[1 * LS_THREADS] = sc.loL_c; m[2 * LS_THREADS] = sc.hiL_d; m[3 * LS_THREADS] = sc.loL_d;
+        m[4 * LS_THREADS] = sc.hiS_c; m[5 * LS_THREADS] = sc.loS_c; m[6 * LS_THREADS] = sc.hiS_d; m[7 * LS_THREADS] = sc.loS_d;
+    }
     const float* __restrict__ pr = A.price + (int64_t)sym * A.ld_price;
     const float* __restrict__ rb = A.rsi + (int64_t)sym * A.P * A.ld_rsi;
 
@@ -323,22 +331,24 @@ lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (s
         bool ev = true;
         if (!flat && !rsi_hit) {
             // price trigger: definite outside the fp32 screening band, else the reference's float64 expression
-            const float hd = e_px * (lng_open ? sc.hiL_d : sc.hiS_d), ld = e_px * (lng_open ? sc.loL_d : sc.loS_d);
+            const float* m = &ls_mul[lng_open ? 2 : 6][threadIdx.x];
+            const float hd = e_px * m[0], ld = e_px * m[LS_THREADS];
             if (!((p >= hd) || (p <= ld))) {
                 const double ed = (double)e_px, pd = (double)p;
                 const double q = lng_open ? __ddiv_rn(__dsub_rn(pd, ed), ed) : __ddiv_rn(__dsub_rn(ed, pd), ed);
-                ev = (q >= tp) || (q <= -sl);
+                ev = (q >= A.indiv[ind].take_profit) || (q <= -A.indiv[ind].stop_loss);
             }
         }
         if (!ev) return;
-        const bool lng = r < sc.os_f;                     // entry side: long has priority (:784, :799)
+        const bool lng = r < os_f;                        // entry side: long has priority (:784, :799)
         const unsigned word = flat ? ((unsigned)t | (lng ? 0u : B200BT_EVENT_SELL))
                                    : ((unsigned)t | B200BT_EVENT_EXIT | (lng_open ? B200BT_EVENT_SELL : 0u));
         pos = flat ? (lng ? 1 : -1) : 0;
-        rlo = (flat && lng) ? -INFINITY : sc.os_f;
-        rhi = (flat && !lng) ? INFINITY : sc.ob_f;
-        phi = flat ? p * (lng ? sc.hiL_c : sc.hiS_c) : INFINITY;
-        plo = flat ? p * (lng ? sc.loL_c : sc.loS_c) : -INFINITY;
+        rlo = (flat && lng) ? -INFINITY : os_f;
+        rhi = (flat && !lng) ? INFINITY : ob_f;
+        const float* mc = &ls_mul[lng ? 0 : 4][threadIdx.x];
+        phi = flat ? p * mc[0] : INFINITY;
+        plo = flat ? p * mc[LS_THREADS] : -INFINITY;
         e_px = flat ? p : e_px;
         entry_bar = flat ? t : entry_bar;
         if (rec) {
