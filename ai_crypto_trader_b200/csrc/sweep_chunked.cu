@@ -471,7 +471,8 @@ chunk_sums_kernel(const float* __restrict__ price, int64_t ld_price, const b200b
                   const b200bt_chunk_item* __restrict__ items, int n_items, int S, int n_seg,
                   const uint2* __restrict__ pool, const int* __restrict__ next, const int* __restrict__ seg_first,
                   const unsigned* __restrict__ seg_count, const int2* __restrict__ seg_in,
-                  double* __restrict__ seg_sum, double* __restrict__ seg_max, const int* __restrict__ n_items_dev) {
+                  double* __restrict__ seg_sum, double* __restrict__ seg_max, const int* __restrict__ n_items_dev,
+                  int pool_blocks) {
     const int lane = threadIdx.x & 31;
     const int sym = (int)(blockIdx.x % (unsigned)S);
     const int it = (int)(blockIdx.x / (unsigned)S) * 4 + (threadIdx.x >> 5);
@@ -485,6 +486,7 @@ chunk_sums_kernel(const float* __restrict__ price, int64_t ld_price, const b200b
     unsigned w_carry; float p_carry;
     chunk_carry(seg_in[seg], price + (int64_t)sym * ld_price, w_carry, p_carry);
     int b = left ? seg_first[seg] : -1, off = 0;
+    if ((unsigned)b >= (unsigned)pool_blocks) left = 0;   // (a segment being re-scanned on the side stream)
     double run = 0.0, best = -INFINITY;
     while (left) {
         const int cnt = (int)min(32u, left);
@@ -506,7 +508,7 @@ chunk_sums_kernel(const float* __restrict__ price, int64_t ld_price, const b200b
         p_carry = __shfl_sync(FULL, pf, cnt - 1);
         left -= cnt;
         off += 32;
-        if (off == CK_BLOCK && left) { b = next[b]; off = 0; if (b < 0) break; }
+        if (off == CK_BLOCK && left) { b = next[b]; off = 0; if ((unsigned)b >= (unsigned)pool_blocks) break; }
     }
     if (lane == 0) { seg_sum[seg] = run; seg_max[seg] = best; }
 }
@@ -518,8 +520,7 @@ chunk_partial_kernel(const float* __restrict__ price, int64_t ld_price, const b2
                      const unsigned* __restrict__ seg_count, const int2* __restrict__ seg_in,
                      const double* __restrict__ seg_sum, const double* __restrict__ seg_max,
                      const b200bt_sweep_config cfg, uint32_t* __restrict__ events, int64_t ev_cap,
-                     ChunkPartial* __restrict__ partial, const int* __restrict__ n_items_dev) {
-    __shared__ WarpAcc s_acc[4];
+                     ChunkPartial* __restrict__ partial, const int* __restrict__ n_items_dev, int pool_blocks) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int sym = (int)(blockIdx.x % (unsigned)S);
     const int it = (int)(blockIdx.x / (unsigned)S) * 4 + wid;
@@ -551,38 +552,138 @@ chunk_partial_kernel(const float* __restrict__ price, int64_t ld_price, const b2
         first_index += __reduce_add_sync(FULL, n);
     }
 
-    WarpAcc* acc = &s_acc[wid];
-    if (lane == 0) {
-        WarpAcc a0;
-        init_acc(a0, iv, cfg.initial_capital, events ? events + ((int64_t)item.individual * S + sym) * ev_cap : nullptr);
-        a0.equity = e0; a0.peak = p0; a0.n_events = first_index; a0.hold_first = 1;
-        *acc = a0;
-    }
-    __syncwarp();
+    // Order-dependent state (equity, peak, drawdown, calendar day) is warp-uniform and lives in registers; what
+    // is a plain sum / max / xor over the records is accumulated PER LANE and reduced once at the end of the chunk.
+    const double size = iv.position_size;
+    const double fee1 = __dmul_rn(size, 0.001), fee2 = __dmul_rn(size, 0.002);
+    double equity = e0, peak = p0, maxdd = 0.0;
+    DayAcc da{0.0, 0.0, 0.0, 0u, 0};
+    int day_valid = 0, day_cur = 0, first_done = 0, first_id = 0;
+    double day_sum = 0.0, first_sum = 0.0;
+    unsigned index = first_index;
+    double l_gain = 0.0, l_loss = 0.0, l_maxp = 0.0, l_minl = 0.0;
+    unsigned l_win = 0, l_los = 0;
+    long long l_dur = 0;
+    unsigned long long l_hash = 0ull;
+    uint32_t* const ev_out = events ? events + ((int64_t)item.individual * S + sym) * ev_cap : nullptr;
+    const unsigned minute0 = (unsigned)cfg.minute0, bar_minutes = (unsigned)cfg.bar_minutes;
+    auto finish_day = [&](int id, double x) {     // the chunk's first day may continue the previous chunk's last one
+        if (!first_done) { first_done = 1; first_id = id; first_sum = x; }
+        else day_complete(da, x);
+    };
+
     unsigned left = seg_count[seg];
     if (left == 0xffffffffu) left = 0;
     const unsigned count = left;
     unsigned w_carry; float p_carry;
     chunk_carry(seg_in[seg], price + (int64_t)sym * ld_price, w_carry, p_carry);
     int b = left ? seg_first[seg] : -1, off = 0;
+    if ((unsigned)b >= (unsigned)pool_blocks) left = 0;
     while (left) {
         const int cnt = (int)min(32u, left);
-        const uint2 ev = lane < cnt ? pool[(int64_t)b * CK_BLOCK + off + lane] : make_uint2(0u, 0u);
-        batch_core(acc, cnt, ev.x, __uint_as_float(ev.y), w_carry, p_carry, cfg.minute0, cfg.bar_minutes, ev_cap);
-        w_carry = __shfl_sync(FULL, ev.x, cnt - 1);
-        p_carry = __shfl_sync(FULL, __uint_as_float(ev.y), cnt - 1);
+        const bool active = lane < cnt;
+        const uint2 ev = active ? pool[(int64_t)b * CK_BLOCK + off + lane] : make_uint2(0u, 0u);
+        const unsigned w = ev.x;
+        const float pf = __uint_as_float(ev.y);
+        float p_prev = __shfl_up_sync(FULL, pf, 1);
+        unsigned w_prev = __shfl_up_sync(FULL, w, 1);
+        if (lane == 0) { p_prev = p_carry; w_prev = w_carry; }
+        int dur;
+        const double pnl = record_pnl(active, w, pf, w_prev, p_prev, size, fee1, fee2, dur);
+        if (pnl > 0.0) { l_gain += pnl; ++l_win; l_maxp = fmax(l_maxp, pnl); }
+        else if (pnl < 0.0) { l_loss += pnl; ++l_los; l_minl = fmin(l_minl, pnl); }
+        l_dur += dur;
+        if (active) {
+            l_hash ^= event_hash(index + lane, w);
+            if (ev_out && (int64_t)index + lane < ev_cap) ev_out[index + lane] = w;
+        }
+
+        // equity curve: inclusive scan of pnl, running peak, drawdown (as batch_core, sweep_dev.cuh)
+        double cs = pnl;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double up = shfl_up_d(cs, d);
+            if (lane >= d) cs += up;
+        }
+        const double eq = equity + cs;
+        double pk = peak;
+        if (__any_sync(FULL, active && eq > peak)) {
+            pk = active ? eq : -INFINITY;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double up = shfl_up_d(pk, d);
+                if (lane >= d) pk = fmax(pk, up);
+            }
+            pk = fmax(pk, peak);
+        }
+        {
+            const double gap = __dsub_rn(pk, eq);
+            const bool cand = active && gap > 0.0 && gap >= maxdd * pk * (1.0 - 1e-12);
+            if (__any_sync(FULL, cand)) maxdd = fmax(maxdd, warp_max_d(cand ? __ddiv_rn(gap, pk) : 0.0));
+        }
+        const double batch_sum = shfl_d(cs, 31);
+        equity += batch_sum;
+        peak = shfl_d(pk, cnt - 1);
+
+        // calendar-day buckets (as batch_core)
+        const int day = active ? (int)((minute0 + (w & 0x3fffffffu) * bar_minutes) / 1440u) : 0;
+        const int first_day = __shfl_sync(FULL, day, 0);
+        const int last_day = __shfl_sync(FULL, day, cnt - 1);
+        if (first_day == last_day && (!day_valid || first_day == day_cur)) {
+            day_sum = (day_valid ? day_sum : 0.0) + batch_sum;
+        } else {
+            const int day_prev = __shfl_up_sync(FULL, day, 1);
+            const int day_next = __shfl_down_sync(FULL, day, 1);
+            const bool head = active && (lane == 0 || day != day_prev);
+            const bool tail = active && (lane == cnt - 1 || day != day_next);
+            double sg = pnl;
+            bool flag = head;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double up = shfl_up_d(sg, d);
+                const int fup = __shfl_up_sync(FULL, (int)flag, d);
+                if (lane >= d && !flag) { sg += up; flag = fup; }
+            }
+            const bool merge_carry = day_valid && (first_day == day_cur);
+            if (tail && merge_carry && day == first_day) sg += day_sum;
+            const bool last_seg_tail = tail && (lane == cnt - 1);
+            const double x = (tail && !last_seg_tail) ? sg : 0.0;
+            unsigned done = __ballot_sync(FULL, tail && !last_seg_tail);
+            if (day_valid && !merge_carry) finish_day(day_cur, day_sum);
+            while (done) {
+                const int j = __ffs(done) - 1;
+                done &= done - 1;
+                finish_day(__shfl_sync(FULL, day, j), shfl_d(x, j));
+            }
+            day_sum = shfl_d(sg, cnt - 1);
+        }
+        day_cur = last_day;
+        day_valid = 1;
+
+        index += cnt;
+        w_carry = __shfl_sync(FULL, w, cnt - 1);
+        p_carry = __shfl_sync(FULL, pf, cnt - 1);
         left -= cnt;
         off += 32;
-        if (off == CK_BLOCK && left) { b = next[b]; off = 0; if (b < 0) break; }
+        if (off == CK_BLOCK && left) { b = next[b]; off = 0; if ((unsigned)b >= (unsigned)pool_blocks) break; }
     }
+    // per-lane accumulators -> chunk totals
+    const double tot_profit = warp_sum_d(l_gain), tot_loss = warp_sum_d(l_loss);
+    const double largest_p = warp_max_d(l_maxp), largest_l = warp_min_d(l_minl);
+    const unsigned n_win = __reduce_add_sync(FULL, l_win), n_loss = __reduce_add_sync(FULL, l_los);
+    long long sum_dur = l_dur;
+    unsigned hlo = (unsigned)l_hash, hhi = (unsigned)(l_hash >> 32);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) sum_dur += __shfl_xor_sync(FULL, sum_dur, m);
+    hlo = __reduce_xor_sync(FULL, hlo);
+    hhi = __reduce_xor_sync(FULL, hhi);
     if (lane == 0) {
-        const WarpAcc& a = *acc;
         ChunkPartial q;
-        q.tot_profit = a.tot_profit; q.tot_loss = a.tot_loss; q.largest_p = a.largest_p; q.largest_l = a.largest_l;
-        q.maxdd = a.maxdd; q.first_sum = a.first_sum; q.pivot = a.pivot; q.s1 = a.s1; q.s2 = a.s2; q.day_sum = a.day_sum;
-        q.sum_dur = a.sum_dur; q.hash = a.hash;
-        q.n_win = a.n_win; q.n_loss = a.n_loss; q.n_days = a.n_days; q.count = count;
-        q.first_done = a.first_done; q.first_day = a.first_day; q.day_cur = (int)a.day_cur; q.pad = 0;
+        q.tot_profit = tot_profit; q.tot_loss = tot_loss; q.largest_p = largest_p; q.largest_l = largest_l;
+        q.maxdd = maxdd; q.first_sum = first_sum; q.pivot = da.pivot; q.s1 = da.s1; q.s2 = da.s2; q.day_sum = day_sum;
+        q.sum_dur = sum_dur; q.hash = ((unsigned long long)hhi << 32) | hlo;
+        q.n_win = n_win; q.n_loss = n_loss; q.n_days = da.n_days; q.count = count;
+        q.first_done = first_done; q.first_day = first_id; q.day_cur = day_cur; q.pad = 0;
         partial[seg] = q;
     }
 }
@@ -782,11 +883,11 @@ int finish_chunks(const ChunkScanArgs& A, const ChunkWorkspace& w, const b200bt_
     };
     auto metrics = [&](const b200bt_chunk_item* its, const int* n_dev) -> int {
         chunk_sums_kernel<<<(unsigned)mblocks, 128, 0, st>>>(A.price, A.ld_price, A.indiv, its, n_items, S, n_seg, w.pool, w.next,
-                                                              w.seg_first, w.seg_count, w.seg_in, w.seg_sum, w.seg_max, n_dev);
+                                                              w.seg_first, w.seg_count, w.seg_in, w.seg_sum, w.seg_max, n_dev, A.pool_blocks);
         B200BT_LAUNCH_CHECK("chunk_sums launch");
         chunk_partial_kernel<<<(unsigned)mblocks, 128, 0, st>>>(A.price, A.ld_price, A.indiv, its, n_items, S, n_seg, w.pool, w.next,
                                                                  w.seg_first, w.seg_count, w.seg_in, w.seg_sum, w.seg_max,
-                                                                 *cfg_host, events, event_cap, w.partial, n_dev);
+                                                                 *cfg_host, events, event_cap, w.partial, n_dev, A.pool_blocks);
         B200BT_LAUNCH_CHECK("chunk_partial launch");
         return B200BT_OK;
     };
