@@ -488,26 +488,36 @@ chunk_sums_kernel(const float* __restrict__ price, int64_t ld_price, const b200b
     int b = left ? seg_first[seg] : -1, off = 0;
     if ((unsigned)b >= (unsigned)pool_blocks) left = 0;   // (a segment being re-scanned on the side stream)
     double run = 0.0, best = -INFINITY;
+    // 64 records per step, two consecutive ones per lane (one 16-byte load): half the shuffles per record
     while (left) {
-        const int cnt = (int)min(32u, left);
-        const uint2 ev = lane < cnt ? pool[(int64_t)b * CK_BLOCK + off + lane] : make_uint2(0u, 0u);
-        const float pf = __uint_as_float(ev.y);
-        float p_prev = __shfl_up_sync(FULL, pf, 1);
-        unsigned w_prev = __shfl_up_sync(FULL, ev.x, 1);
+        const int cnt = (int)min(64u, left);
+        const bool a0 = 2 * lane < cnt, a1 = 2 * lane + 1 < cnt;
+        uint4 ev = make_uint4(0u, 0u, 0u, 0u);
+        if (a0) ev = *reinterpret_cast<const uint4*>(pool + (int64_t)b * CK_BLOCK + off + 2 * lane);   // (slot 2l+1 may be unused: in-block)
+        const float pf0 = __uint_as_float(ev.y), pf1 = __uint_as_float(ev.w);
+        float p_prev = __shfl_up_sync(FULL, pf1, 1);
+        unsigned w_prev = __shfl_up_sync(FULL, ev.z, 1);
         if (lane == 0) { p_prev = p_carry; w_prev = w_carry; }
         int dur;
-        double cs = record_pnl(lane < cnt, ev.x, pf, w_prev, p_prev, size, fee1, fee2, dur);
+        const double pnl0 = record_pnl(a0, ev.x, pf0, w_prev, p_prev, size, fee1, fee2, dur);
+        const double pnl1 = record_pnl(a1, ev.z, pf1, ev.x, pf0, size, fee1, fee2, dur);
+        const double s2 = pnl0 + pnl1;
+        double cs = s2;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const double up = shfl_up_d(cs, d);
             if (lane >= d) cs += up;
         }
-        best = fmax(best, warp_max_d(lane < cnt ? run + cs : -INFINITY));
+        const double after0 = run + (cs - s2) + pnl0, after1 = run + cs;
+        best = fmax(best, warp_max_d(fmax(a0 ? after0 : -INFINITY, a1 ? after1 : -INFINITY)));
         run += shfl_d(cs, 31);
-        w_carry = __shfl_sync(FULL, ev.x, cnt - 1);
-        p_carry = __shfl_sync(FULL, pf, cnt - 1);
+        const int last = (cnt - 1) >> 1;
+        const unsigned wl = (cnt & 1) ? ev.x : ev.z;
+        const float pl = (cnt & 1) ? pf0 : pf1;
+        w_carry = __shfl_sync(FULL, wl, last);
+        p_carry = __shfl_sync(FULL, pl, last);
         left -= cnt;
-        off += 32;
+        off += 64;
         if (off == CK_BLOCK && left) { b = next[b]; off = 0; if ((unsigned)b >= (unsigned)pool_blocks) break; }
     }
     if (lane == 0) { seg_sum[seg] = run; seg_max[seg] = best; }
@@ -579,92 +589,123 @@ chunk_partial_kernel(const float* __restrict__ price, int64_t ld_price, const b2
     chunk_carry(seg_in[seg], price + (int64_t)sym * ld_price, w_carry, p_carry);
     int b = left ? seg_first[seg] : -1, off = 0;
     if ((unsigned)b >= (unsigned)pool_blocks) left = 0;
+    // 64 records per step, two consecutive ones per lane (record 2l and 2l+1 of the step: one 16-byte load)
     while (left) {
-        const int cnt = (int)min(32u, left);
-        const bool active = lane < cnt;
-        const uint2 ev = active ? pool[(int64_t)b * CK_BLOCK + off + lane] : make_uint2(0u, 0u);
-        const unsigned w = ev.x;
-        const float pf = __uint_as_float(ev.y);
-        float p_prev = __shfl_up_sync(FULL, pf, 1);
-        unsigned w_prev = __shfl_up_sync(FULL, w, 1);
+        const int cnt = (int)min(64u, left);
+        const bool a0 = 2 * lane < cnt, a1 = 2 * lane + 1 < cnt;
+        uint4 ev = make_uint4(0u, 0u, 0u, 0u);
+        if (a0) ev = *reinterpret_cast<const uint4*>(pool + (int64_t)b * CK_BLOCK + off + 2 * lane);
+        const unsigned w0 = ev.x, w1 = ev.z;
+        const float pf0 = __uint_as_float(ev.y), pf1 = __uint_as_float(ev.w);
+        float p_prev = __shfl_up_sync(FULL, pf1, 1);
+        unsigned w_prev = __shfl_up_sync(FULL, w1, 1);
         if (lane == 0) { p_prev = p_carry; w_prev = w_carry; }
-        int dur;
-        const double pnl = record_pnl(active, w, pf, w_prev, p_prev, size, fee1, fee2, dur);
-        if (pnl > 0.0) { l_gain += pnl; ++l_win; l_maxp = fmax(l_maxp, pnl); }
-        else if (pnl < 0.0) { l_loss += pnl; ++l_los; l_minl = fmin(l_minl, pnl); }
-        l_dur += dur;
-        if (active) {
-            l_hash ^= event_hash(index + lane, w);
-            if (ev_out && (int64_t)index + lane < ev_cap) ev_out[index + lane] = w;
+        int dur0, dur1;
+        const double pnl0 = record_pnl(a0, w0, pf0, w_prev, p_prev, size, fee1, fee2, dur0);
+        const double pnl1 = record_pnl(a1, w1, pf1, w0, pf0, size, fee1, fee2, dur1);
+        if (pnl0 > 0.0) { l_gain += pnl0; ++l_win; l_maxp = fmax(l_maxp, pnl0); }
+        else if (pnl0 < 0.0) { l_loss += pnl0; ++l_los; l_minl = fmin(l_minl, pnl0); }
+        if (pnl1 > 0.0) { l_gain += pnl1; ++l_win; l_maxp = fmax(l_maxp, pnl1); }
+        else if (pnl1 < 0.0) { l_loss += pnl1; ++l_los; l_minl = fmin(l_minl, pnl1); }
+        l_dur += dur0 + dur1;
+        const unsigned i0 = index + 2 * lane;
+        if (a0) {
+            l_hash ^= event_hash(i0, w0);
+            if (ev_out && (int64_t)i0 < ev_cap) ev_out[i0] = w0;
+        }
+        if (a1) {
+            l_hash ^= event_hash(i0 + 1, w1);
+            if (ev_out && (int64_t)i0 + 1 < ev_cap) ev_out[i0 + 1] = w1;
         }
 
-        // equity curve: inclusive scan of pnl, running peak, drawdown (as batch_core, sweep_dev.cuh)
-        double cs = pnl;
+        // equity curve: inclusive scan of the lane sums, running peak, drawdown (cf. batch_core, sweep_dev.cuh)
+        const double s2 = pnl0 + pnl1;
+        double cs = s2;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const double up = shfl_up_d(cs, d);
             if (lane >= d) cs += up;
         }
-        const double eq = equity + cs;
-        double pk = peak;
-        if (__any_sync(FULL, active && eq > peak)) {
-            pk = active ? eq : -INFINITY;
+        const double eq0 = equity + (cs - s2) + pnl0, eq1 = equity + cs;
+        const double m2 = fmax(a0 ? eq0 : -INFINITY, a1 ? eq1 : -INFINITY);
+        double pk0 = peak, pk1 = peak;
+        if (__any_sync(FULL, m2 > peak)) {
+            double pk = m2;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const double up = shfl_up_d(pk, d);
                 if (lane >= d) pk = fmax(pk, up);
             }
-            pk = fmax(pk, peak);
+            double before = shfl_up_d(pk, 1);          // peak over the records of the lanes in front
+            before = fmax(lane == 0 ? peak : before, peak);
+            pk0 = fmax(before, eq0);
+            pk1 = fmax(pk0, eq1);
+            peak = fmax(peak, shfl_d(pk, 31));
         }
         {
-            const double gap = __dsub_rn(pk, eq);
-            const bool cand = active && gap > 0.0 && gap >= maxdd * pk * (1.0 - 1e-12);
-            if (__any_sync(FULL, cand)) maxdd = fmax(maxdd, warp_max_d(cand ? __ddiv_rn(gap, pk) : 0.0));
+            const double gap0 = __dsub_rn(pk0, eq0), gap1 = __dsub_rn(pk1, eq1);
+            const double lim = maxdd * (1.0 - 1e-12);
+            const bool c0 = a0 && gap0 > 0.0 && gap0 >= lim * pk0, c1 = a1 && gap1 > 0.0 && gap1 >= lim * pk1;
+            if (__any_sync(FULL, c0 || c1))
+                maxdd = fmax(maxdd, warp_max_d(fmax(c0 ? __ddiv_rn(gap0, pk0) : 0.0, c1 ? __ddiv_rn(gap1, pk1) : 0.0)));
         }
         const double batch_sum = shfl_d(cs, 31);
         equity += batch_sum;
-        peak = shfl_d(pk, cnt - 1);
 
-        // calendar-day buckets (as batch_core)
-        const int day = active ? (int)((minute0 + (w & 0x3fffffffu) * bar_minutes) / 1440u) : 0;
-        const int first_day = __shfl_sync(FULL, day, 0);
-        const int last_day = __shfl_sync(FULL, day, cnt - 1);
+        // calendar-day buckets
+        const int last_lane = (cnt - 1) >> 1;
+        const int d0 = a0 ? (int)((minute0 + (w0 & 0x3fffffffu) * bar_minutes) / 1440u) : 0;
+        const int d1 = a1 ? (int)((minute0 + (w1 & 0x3fffffffu) * bar_minutes) / 1440u) : d0;
+        const int first_day = __shfl_sync(FULL, d0, 0);
+        const int last_day = __shfl_sync(FULL, d1, last_lane);
         if (first_day == last_day && (!day_valid || first_day == day_cur)) {
-            day_sum = (day_valid ? day_sum : 0.0) + batch_sum;
+            day_sum = (day_valid ? day_sum : 0.0) + batch_sum;      // the whole step falls into the open day
         } else {
-            const int day_prev = __shfl_up_sync(FULL, day, 1);
-            const int day_next = __shfl_down_sync(FULL, day, 1);
-            const bool head = active && (lane == 0 || day != day_prev);
-            const bool tail = active && (lane == cnt - 1 || day != day_next);
-            double sg = pnl;
-            bool flag = head;
+            // a record is a HEAD if it opens a day within the step; running day sum = segmented scan by heads.
+            // As a function of the running sum it receives, a lane is either additive (no head) or constant.
+            const bool merge_carry = day_valid && (first_day == day_cur);
+            const int d_before = __shfl_up_sync(FULL, d1, 1);
+            const bool head0 = a0 && (lane == 0 ? !merge_carry : d0 != d_before);
+            const bool head1 = a1 && d1 != d0;
+            double sg = head1 ? pnl1 : s2;
+            bool flag = head0 || head1;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const double up = shfl_up_d(sg, d);
                 const int fup = __shfl_up_sync(FULL, (int)flag, d);
                 if (lane >= d && !flag) { sg += up; flag = fup; }
             }
-            const bool merge_carry = day_valid && (first_day == day_cur);
-            if (tail && merge_carry && day == first_day) sg += day_sum;
-            const bool last_seg_tail = tail && (lane == cnt - 1);
-            const double x = (tail && !last_seg_tail) ? sg : 0.0;
-            unsigned done = __ballot_sync(FULL, tail && !last_seg_tail);
+            // (the open day carried in is part of lane 0's chain when it continues)
+            if (merge_carry && !flag) sg += day_sum;          // lanes whose chain reaches back to the step's start
+            double carry_in = shfl_up_d(sg, 1);
+            if (lane == 0) carry_in = merge_carry ? day_sum : 0.0;
+            const double run0 = head0 ? pnl0 : carry_in + pnl0;     // running day sum after record 2l
+            const double run1 = sg;                                  // ... after record 2l+1 (== run0 if inactive)
+            // TAIL = last record of its day within the step, except the step's last record (its day stays open)
+            const int d_after = __shfl_down_sync(FULL, d0, 1);
+            const bool tail0 = a0 && (a1 ? head1 : false);
+            const bool tail1 = a1 && lane < last_lane && d_after != d1;
+            const bool tail0_odd = a0 && !a1 && false;              // an unpaired last record is the step's last: open
+            (void)tail0_odd;
+            unsigned t0m = __ballot_sync(FULL, tail0), t1m = __ballot_sync(FULL, tail1);
             if (day_valid && !merge_carry) finish_day(day_cur, day_sum);
-            while (done) {
-                const int j = __ffs(done) - 1;
-                done &= done - 1;
-                finish_day(__shfl_sync(FULL, day, j), shfl_d(x, j));
+            while (t0m | t1m) {
+                const int j = __ffs(t0m | t1m) - 1;
+                const unsigned bit = 1u << j;
+                if (t0m & bit) finish_day(__shfl_sync(FULL, d0, j), shfl_d(run0, j));
+                if (t1m & bit) finish_day(__shfl_sync(FULL, d1, j), shfl_d(run1, j));
+                t0m &= ~bit; t1m &= ~bit;
             }
-            day_sum = shfl_d(sg, cnt - 1);
+            day_sum = (cnt & 1) ? shfl_d(run0, last_lane) : shfl_d(run1, last_lane);
         }
         day_cur = last_day;
         day_valid = 1;
 
         index += cnt;
-        w_carry = __shfl_sync(FULL, w, cnt - 1);
-        p_carry = __shfl_sync(FULL, pf, cnt - 1);
+        w_carry = __shfl_sync(FULL, (cnt & 1) ? w0 : w1, last_lane);
+        p_carry = __shfl_sync(FULL, (cnt & 1) ? pf0 : pf1, last_lane);
         left -= cnt;
-        off += 32;
+        off += 64;
         if (off == CK_BLOCK && left) { b = next[b]; off = 0; if ((unsigned)b >= (unsigned)pool_blocks) break; }
     }
     // per-lane accumulators -> chunk totals
