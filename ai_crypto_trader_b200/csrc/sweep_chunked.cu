@@ -234,14 +234,42 @@ constexpr int LS_STRIDE = LS_T + 4;     // row stride in floats (16-byte aligned
 #endif
 constexpr int LS_THREADS = B200BT_LS_THREADS;
 
+constexpr int LS_ZONE = 32;             // bars per zone-map block
+
+// Zone map: (min, max) of every 32-bar block of the price row and of each RSI row, NaNs ignored.  A machine whose
+// thresholds lie outside a block's range cannot fire in it, so the scan skips the block after four compares.
+// Layout [S][P + 1][ceil(N / 32)] float2, row 0 = price.
+__global__ void __launch_bounds__(256)
+zone_map_kernel(const float* __restrict__ price, int64_t ld_price, const float* __restrict__ rsi, int64_t ld_rsi, int P,
+                int64_t N, int64_t n_blocks, float2* __restrict__ zones) {
+    const int row = blockIdx.y % (P + 1), sym = blockIdx.y / (P + 1);
+    const float* __restrict__ src = row == 0 ? price + (int64_t)sym * ld_price : rsi + ((int64_t)sym * P + row - 1) * ld_rsi;
+    float2* __restrict__ dst = zones + ((int64_t)sym * (P + 1) + row) * n_blocks;
+    const int lane = threadIdx.x & 31;
+    for (int64_t blk = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); blk < n_blocks; blk += (int64_t)gridDim.x * 8) {
+        const int64_t t = blk * LS_ZONE + lane;
+        const float v = t < N ? __ldg(src + t) : __int_as_float(0x7fc00000);
+        float lo = v, hi = v;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(FULL, lo, m));
+            hi = fmaxf(hi, __shfl_xor_sync(FULL, hi, m));
+        }
+        if (lane == 0) dst[blk] = make_float2(lo, hi);    // all-NaN block: (NaN, NaN), every compare false
+    }
+}
+
 struct LaneScanArgs {
     const float* price; int64_t ld_price;
     const float* rsi; int64_t ld_rsi;
+    const float2* zones; int64_t n_zone_blocks;   // zone map or NULL
     int P, S; int64_t N;
     const b200bt_individual* indiv; const int32_t* order; int pop; int K; int warm;
     uint2* pool; int pool_blocks; int* next; unsigned* alloc;
     int* seg_first; unsigned* seg_count; int2* seg_in; int2* seg_out; int* overflow;
 };
+
+__device__ __forceinline__ int sym_of_block(unsigned bx, int S) { return (int)(bx % (unsigned)S); }
 
 // device-side tables the shared kernels expect: uniform K chunks per individual
 __global__ void lane_tables_kernel(int pop, int K, b200bt_chunk_item* __restrict__ items, int32_t* __restrict__ seg_base,
@@ -261,8 +289,11 @@ __global__ void lane_tables_kernel(int pop, int K, b200bt_chunk_item* __restrict
 template <bool VEC16>
 __global__ void __launch_bounds__(LS_THREADS, B200BT_LS_MIN_BLOCKS)
 lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (see sweep.cu)
-    extern __shared__ __align__(16) float ls_tile[];   // [2][P + 1][LS_STRIDE]
+    extern __shared__ __align__(16) float ls_tile[];   // [2][P + 1][LS_STRIDE], then zone stages [2][P + 1][LS_T / 32] float2
     const int rows = A.P + 1;
+    constexpr int ZB = LS_T / LS_ZONE;                  // zone blocks per tile
+    float2* const ls_zone = reinterpret_cast<float2*>(ls_tile + (size_t)2 * rows * LS_STRIDE);
+    const float2* __restrict__ zsym = A.zones ? A.zones + (int64_t)sym_of_block(blockIdx.x, A.S) * rows * A.n_zone_blocks : nullptr;
     const int sym = (int)(blockIdx.x % (unsigned)A.S);
     const int c = (int)((blockIdx.x / (unsigned)A.S) % (unsigned)A.K);
     const int blk = (int)(blockIdx.x / ((unsigned)A.S * (unsigned)A.K));
@@ -308,6 +339,15 @@ lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (s
                 const int row = e / LS_T, col = e - row * LS_T;
                 const float* src = (row == 0 ? pr : rb + (int64_t)(row - 1) * A.ld_rsi) + t0 + col;
                 dst0[row * LS_STRIDE + col] = (t0 + col < n) ? __ldg(src) : qnan;
+            }
+        }
+        if (zsym) {
+            float2* zdst = ls_zone + (size_t)stage * rows * ZB;
+            for (int e = threadIdx.x; e < rows * ZB; e += LS_THREADS) {
+                const int row = e / ZB, zb = e - row * ZB;
+                const int64_t blk = (int64_t)tl * ZB + zb;
+                if (blk < A.n_zone_blocks) cp_async8(zdst + e, zsym + (int64_t)row * A.n_zone_blocks + blk);
+                else zdst[e] = make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
             }
         }
         cp_async_commit();
@@ -378,18 +418,28 @@ lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (s
             if (t0 == T0) { A.seg_in[seg] = make_int2(pos, pos != 0 ? entry_bar : -1); rec = true; }
             const float4* __restrict__ pp = reinterpret_cast<const float4*>(ls_tile + (size_t)stage * rows * LS_STRIDE);
             const float4* __restrict__ rr = reinterpret_cast<const float4*>(ls_tile + ((size_t)stage * rows + 1 + iv.rsi_row) * LS_STRIDE);
+            const float2* __restrict__ zp = ls_zone + (size_t)stage * rows * ZB;
+            const float2* __restrict__ zr = zp + (1 + iv.rsi_row) * ZB;
+#pragma unroll 1
+            for (int zb = 0; zb < ZB; ++zb) {
+                if (zsym) {
+                    // nothing can fire in a block whose (min, max) stay inside the machine's thresholds
+                    const float2 rz = zr[zb], pz = zp[zb];
+                    if (!((rz.x < rlo) | (rz.y > rhi) | (pz.x <= plo) | (pz.y >= phi))) continue;
+                }
 #pragma unroll 2
-            for (int g = 0; g < LS_T / 4; ++g) {
-                const float4 p = pp[g], r = rr[g];
-                // any bar of the four beyond a threshold?  (fminf / fmaxf drop NaNs, as the per-bar compares do)
-                const float r_min = fminf(fminf(r.x, r.y), fminf(r.z, r.w)), r_max = fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w));
-                const float p_min = fminf(fminf(p.x, p.y), fminf(p.z, p.w)), p_max = fmaxf(fmaxf(p.x, p.y), fmaxf(p.z, p.w));
-                if ((r_min < rlo) | (r_max > rhi) | (p_min <= plo) | (p_max >= phi)) {
-                    const int t = t0 + g * 4;
-                    step(p.x, r.x, t);
-                    step(p.y, r.y, t + 1);
-                    step(p.z, r.z, t + 2);
-                    step(p.w, r.w, t + 3);
+                for (int g = zb * (LS_ZONE / 4); g < (zb + 1) * (LS_ZONE / 4); ++g) {
+                    const float4 p = pp[g], r = rr[g];
+                    // any bar of the four beyond a threshold?  (fminf / fmaxf drop NaNs, as the per-bar compares do)
+                    const float r_min = fminf(fminf(r.x, r.y), fminf(r.z, r.w)), r_max = fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w));
+                    const float p_min = fminf(fminf(p.x, p.y), fminf(p.z, p.w)), p_max = fmaxf(fmaxf(p.x, p.y), fmaxf(p.z, p.w));
+                    if ((r_min < rlo) | (r_max > rhi) | (p_min <= plo) | (p_max >= phi)) {
+                        const int t = t0 + g * 4;
+                        step(p.x, r.x, t);
+                        step(p.y, r.y, t + 1);
+                        step(p.z, r.z, t + 2);
+                        step(p.w, r.w, t + 3);
+                    }
                 }
             }
         }
@@ -523,7 +573,10 @@ chunk_sums_kernel(const float* __restrict__ price, int64_t ld_price, const b200b
     if (lane == 0) { seg_sum[seg] = run; seg_max[seg] = best; }
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef B200BT_M2_MIN_BLOCKS
+#define B200BT_M2_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, B200BT_M2_MIN_BLOCKS)
 chunk_partial_kernel(const float* __restrict__ price, int64_t ld_price, const b200bt_individual* __restrict__ indiv,
                      const b200bt_chunk_item* __restrict__ items, int n_items, int S, int n_seg,
                      const uint2* __restrict__ pool, const int* __restrict__ next, const int* __restrict__ seg_first,
@@ -1033,14 +1086,34 @@ extern "C" int b200bt_sweep_chunked(const float* price, int64_t ld_price, const 
                          lane_invalid, overflow_host_or_null, st);
 }
 
+extern "C" int64_t b200bt_zone_map_floats(int P, int S, int64_t N) {
+    if (P <= 0 || S <= 0 || N <= 0) return 0;
+    return (int64_t)S * (P + 1) * ((N + LS_ZONE - 1) / LS_ZONE) * 2;
+}
+
+extern "C" int b200bt_zone_map(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S, int64_t N,
+                               float* zones, b200bt_stream_t stream) {
+    B200BT_REQUIRE(price && rsi && zones, B200BT_EINVAL, "zone_map: null pointer");
+    B200BT_REQUIRE(P > 0 && S > 0 && N > 0 && ld_price >= N && ld_rsi >= N, B200BT_EINVAL, "zone_map: bad sizes");
+    B200BT_REQUIRE(((uintptr_t)zones & 7) == 0, B200BT_EINVAL, "zone_map: output must be 8-byte aligned");
+    int rc = check_device();
+    if (rc) return rc;
+    const int64_t nb = (N + LS_ZONE - 1) / LS_ZONE;
+    const unsigned gx = (unsigned)min((int64_t)1024, (nb + 7) / 8);
+    zone_map_kernel<<<dim3(gx, (unsigned)(S * (P + 1))), 256, 0, (cudaStream_t)stream>>>(price, ld_price, rsi, ld_rsi, P, N, nb,
+                                                                                       (float2*)zones);
+    B200BT_LAUNCH_CHECK("zone_map launch");
+    return B200BT_OK;
+}
+
 extern "C" int64_t b200bt_sweep_tiled_workspace_bytes(int pool_blocks, int S, int pop, int K) {
     const int64_t n_seg = (int64_t)pop * K;
     return chunk_workspace_bytes(pool_blocks, S * n_seg, (int)n_seg, pop) + 16 + n_seg * 16 + (int64_t)pop * 8;
 }
 
 extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S,
-                                  int64_t N, const b200bt_individual* indiv, const int32_t* order, int pop, int K, int warm,
-                                  int max_repair_rounds, int pool_blocks, void* workspace, int64_t workspace_bytes,
+                                  int64_t N, const float* zones_or_null, const b200bt_individual* indiv, const int32_t* order,
+                                  int pop, int K, int warm, int max_repair_rounds, int pool_blocks, void* workspace, int64_t workspace_bytes,
                                   const b200bt_sweep_config* cfg_host, b200bt_lane_stats* stats, uint32_t* events,
                                   int64_t event_cap, unsigned char* lane_invalid, int* overflow_host_or_null,
                                   b200bt_stream_t stream) {
@@ -1050,7 +1123,7 @@ extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const fl
     if (rc) return rc;
     B200BT_REQUIRE((int64_t)pop * K * S < (1ll << 31), B200BT_ELIMIT, "sweep_tiled: too many chunks");
     B200BT_REQUIRE(K == 1 || N / K >= SW_GROUP, B200BT_EINVAL, "sweep_tiled: chunks shorter than %d bars", SW_GROUP);
-    const size_t smem = (size_t)2 * (P + 1) * LS_STRIDE * sizeof(float);
+    const size_t smem = (size_t)2 * (P + 1) * (LS_STRIDE * sizeof(float) + (LS_T / LS_ZONE) * sizeof(float2));
     B200BT_REQUIRE(smem <= 72 * 1024, B200BT_ELIMIT, "sweep_tiled: RSI bank of %d periods exceeds the shared-memory tile", P);
     B200BT_REQUIRE(workspace_bytes >= b200bt_sweep_tiled_workspace_bytes(pool_blocks, S, pop, K), B200BT_EINVAL,
                    "sweep_tiled: workspace too small");
@@ -1071,6 +1144,7 @@ extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const fl
 
     LaneScanArgs L;
     L.price = price; L.ld_price = ld_price; L.rsi = rsi; L.ld_rsi = ld_rsi; L.P = P; L.S = S; L.N = N;
+    L.zones = (const float2*)zones_or_null; L.n_zone_blocks = (N + LS_ZONE - 1) / LS_ZONE;
     L.indiv = indiv; L.order = order; L.pop = pop; L.K = K; L.warm = warm;
     L.pool = w.pool; L.pool_blocks = pool_blocks; L.next = w.next; L.alloc = w.alloc;
     L.seg_first = w.seg_first; L.seg_count = w.seg_count; L.seg_in = w.seg_in; L.seg_out = w.seg_out; L.overflow = w.overflow;

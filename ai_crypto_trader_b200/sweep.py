@@ -152,7 +152,7 @@ def lane_cost(p: Dict) -> float:
 
 
 EVENTS_PER_COST_BAR = 0.27
-TILED_MAX_PERIODS = 68      # shared-memory tile of the thread-per-lane sweep: 2 (P + 1) 528 B <= 72 KB
+TILED_MAX_PERIODS = 64      # shared-memory tile of the thread-per-lane sweep: 2 (P + 1) 560 B <= 72 KB
 
 
 def predicted_events(population: List[Dict], n_bars: int) -> np.ndarray:
@@ -410,7 +410,8 @@ class PopulationSweep:
         with torch.cuda.device(m.device):
             st = _lib.current_stream()
             _lib.call("b200bt_sweep_tiled", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
-                      len(self.periods), m.S, m.N, indiv_dev.data_ptr() + lo * C.sizeof(_lib.Individual),
+                      len(self.periods), m.S, m.N, _lib.ptr(self.zone_map()) if self.use_zones else None,
+                      indiv_dev.data_ptr() + lo * C.sizeof(_lib.Individual),
                       plan.order_dev.data_ptr(), n, plan.K, plan.warm, plan.max_repair_rounds, plan.pool_blocks,
                       plan.workspace.data_ptr(), plan.workspace.numel(), C.byref(self.cfg), stats.data_ptr(),
                       _lib.ptr(events), self.event_cap, plan.invalid.data_ptr(), plan.overflow.data_ptr(), st)
@@ -422,6 +423,20 @@ class PopulationSweep:
                 _lib.call("b200bt_sweep", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
                           len(self.periods), m.S, m.N, indiv_dev.data_ptr(), redo.data_ptr(), int(redo.numel()),
                           C.byref(self.cfg), self._stats.data_ptr(), _lib.ptr(self._events), self.event_cap, st)
+
+    def zone_map(self) -> torch.Tensor:
+        """(min, max) per 32-bar block of the price rows and of the RSI bank (b200bt_zone_map), built on first use."""
+        if getattr(self, "_zones", None) is None:
+            m = self.market
+            n = int(_lib.load().b200bt_zone_map_floats(len(self.periods), m.S, m.N))
+            z = torch.empty(n, dtype=torch.float32, device=m.device)
+            with torch.cuda.device(m.device):
+                _lib.call("b200bt_zone_map", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
+                          len(self.periods), m.S, m.N, z.data_ptr(), _lib.current_stream())
+            self._zones = z
+        return self._zones
+
+    use_zones = True
 
     def plan(self, population: List[Dict]) -> Optional[List]:
         """The kernel path `evaluate` takes for this population under self.mode: None = fused kernel, else the

@@ -248,10 +248,15 @@ int b200bt_sweep_chunked(const float* price, int64_t ld_price, const float* rsi,
  * and each thread steps its own state machine through shared-memory tiles of the price row and the RSI bank.
  * Verification, in-place repair, metrics and the lane_invalid / overflow outputs are those of b200bt_sweep_chunked.
  * order: device int32[pop] dispatch order (NULL = identity; same-period, similar-cost neighbours are cheapest).
- * Requires 2 (P + 1) 528 B of shared memory <= 72 KB, i.e. P <= 68 RSI periods. */
+ * zones: optional zone map of the same price / RSI arrays (b200bt_zone_map), NULL = none: (min, max) per 32-bar
+ * block of every row, which lets a machine skip blocks in which none of its thresholds can be crossed.
+ * Requires 2 (P + 1) 560 B of shared memory <= 72 KB, i.e. P <= 64 RSI periods. */
+int64_t b200bt_zone_map_floats(int P, int S, int64_t N);     /* floats in the zone map: [S][P+1][ceil(N/32)][2] */
+int b200bt_zone_map(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S, int64_t N,
+                    float* zones, b200bt_stream_t stream);
 int64_t b200bt_sweep_tiled_workspace_bytes(int pool_blocks, int S, int pop, int K);
 int b200bt_sweep_tiled(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S,
-                       int64_t N, const b200bt_individual* indiv, const int32_t* order, int pop, int K, int warm,
+                       int64_t N, const float* zones, const b200bt_individual* indiv, const int32_t* order, int pop, int K, int warm,
                        int max_repair_rounds, int pool_blocks, void* workspace, int64_t workspace_bytes,
                        const b200bt_sweep_config* cfg, b200bt_lane_stats* stats, uint32_t* events,
                        int64_t event_cap, unsigned char* lane_invalid, int* overflow_host_or_null,
