@@ -65,16 +65,41 @@ class MarketData:
             host = torch.from_numpy(np.ascontiguousarray(ohlcv, dtype=np.float32))
         if host.dim() != 3 or host.shape[0] != 5:
             raise ValueError("ohlcv must have shape [5][S][N] (open, high, low, close, volume)")
-        self.ohlcv = host.to(self.device, non_blocking=True).contiguous()
-        self.S = int(self.ohlcv.shape[1])
-        self.N = int(self.ohlcv.shape[2])
+        self.S = int(host.shape[1])
+        self.N = int(host.shape[2])
+        self._others_ready = None
+        if host.is_cuda or not host.is_pinned():
+            self._ohlcv = host.to(self.device, non_blocking=True).contiguous()
+        else:
+            # pinned host source: the close prices (all the sweep and the RSI bank read) go first on the caller's
+            # stream; open / high / low / volume follow on a copy stream and are waited for on first use
+            host = host.contiguous()
+            self._ohlcv = torch.empty(host.shape, dtype=torch.float32, device=self.device)
+            self._ohlcv[3].copy_(host[3], non_blocking=True)
+            side = _copy_stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))       # (allocation order)
+            with torch.cuda.stream(side):
+                for f in (0, 1, 2, 4):
+                    self._ohlcv[f].copy_(host[f], non_blocking=True)
+                self._others_ready = side.record_event()
+            self._ohlcv.record_stream(side)
         self.symbols = list(symbols) if symbols is not None else [f"SYN{i:03d}USDT" for i in range(self.S)]
         self.minute0 = int(minute0)
         self.bar_minutes = int(bar_minutes)
 
+    def _wait_others(self) -> None:
+        if self._others_ready is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._others_ready)
+            self._others_ready = None
+
+    @property
+    def ohlcv(self) -> torch.Tensor:
+        self._wait_others()
+        return self._ohlcv
+
     @property
     def close(self) -> torch.Tensor:
-        return self.ohlcv[3]
+        return self._ohlcv[3]
 
     @property
     def high(self) -> torch.Tensor:
@@ -91,6 +116,16 @@ class MarketData:
     @property
     def volume(self) -> torch.Tensor:
         return self.ohlcv[4]
+
+
+_COPY_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _copy_stream(device: torch.device) -> "torch.cuda.Stream":
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _COPY_STREAMS:
+        _COPY_STREAMS[idx] = torch.cuda.Stream(device=device)
+    return _COPY_STREAMS[idx]
 
 
 def rsi_bank(close: torch.Tensor, periods: Sequence[int], fill: bool = True,
