@@ -445,7 +445,7 @@ class PopulationSweep:
         with torch.cuda.device(m.device):
             st = _lib.current_stream()
             _lib.call("b200bt_sweep_tiled", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
-                      len(self.periods), m.S, m.N, _lib.ptr(self.zone_map()) if self.use_zones else None,
+                      len(self.periods), m.S, m.N, _lib.ptr(self._zones_if_amortised()),
                       indiv_dev.data_ptr() + lo * C.sizeof(_lib.Individual),
                       plan.order_dev.data_ptr(), n, plan.K, plan.warm, plan.max_repair_rounds, plan.pool_blocks,
                       plan.workspace.data_ptr(), plan.workspace.numel(), C.byref(self.cfg), stats.data_ptr(),
@@ -472,6 +472,14 @@ class PopulationSweep:
         return self._zones
 
     use_zones = True
+
+    def _zones_if_amortised(self) -> Optional[torch.Tensor]:
+        """The zone map costs about as much as it saves in ONE sweep (0.8 ms against ~0.2 ms at C2): it is built
+        when this bank is swept a second time (a GA sweeps it every generation), not for a one-off evaluation."""
+        self._tiled_sweeps = getattr(self, "_tiled_sweeps", 0) + 1
+        if not self.use_zones or (self._tiled_sweeps < 2 and getattr(self, "_zones", None) is None):
+            return None
+        return self.zone_map()
 
     def plan(self, population: List[Dict]) -> Optional[List]:
         """The kernel path `evaluate` takes for this population under self.mode: None = fused kernel, else the

@@ -286,6 +286,11 @@ def test_tiled_sweep_is_exact_and_self_repairing(torch_cuda, n_bars, opts):
     fused = PopulationSweep(market, event_cap=cap, mode="fused")
     f_t = tiled.evaluate(population)
     f_f = fused.evaluate(population)
+    hash_first = tiled.lane_stats()["trade_hash"].copy()
+    f_t2 = tiled.evaluate(population)          # the second sweep of a bank goes through the zone map (block skipping)
+    assert tiled._zones is not None
+    np.testing.assert_array_equal(f_t2, f_t)
+    np.testing.assert_array_equal(tiled.lane_stats()["trade_hash"], hash_first)
     plan = tiled.plan_tiles(population, **opts)
     if "chunks" in opts:
         assert plan.K == opts["chunks"]
