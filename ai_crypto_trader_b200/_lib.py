@@ -55,8 +55,10 @@ class SweepConfig(C.Structure):
 LANE_STATS_FIELDS = (
     "n_records", "n_wins", "n_losses", "total_profit", "total_loss", "net_profit",
     "max_drawdown", "sharpe_ratio", "n_days", "largest_profit", "largest_loss",
-    "sum_duration_bars", "score", "win_rate", "profit_factor", "trade_hash",
+    "sum_duration_bars", "score", "win_rate", "profit_factor",
+    "sortino_ratio", "n_negative_days", "downside_deviation", "mean_daily_pnl", "trade_hash",
 )
+LANE_STATS_WORDS = len(LANE_STATS_FIELDS)
 
 EVENT_EXIT = 0x40000000
 EVENT_SELL = 0x80000000

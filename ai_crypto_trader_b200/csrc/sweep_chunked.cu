@@ -503,9 +503,11 @@ struct ChunkPartial {
     long long sum_dur;
     unsigned long long hash;
     unsigned n_win, n_loss, n_days, count;
-    int first_done, first_day, day_cur, pad;
+    int first_done, first_day, day_cur;
+    unsigned n_neg;
+    double npivot, ns1, ns2, pad;     // the chunk's finished negative days (DayAcc)
 };
-static_assert(sizeof(ChunkPartial) == 128, "ChunkPartial layout");
+static_assert(sizeof(ChunkPartial) == 160, "ChunkPartial layout");
 
 // entry record a chunk's first exit is priced against, from the chunk's (verified) start state
 __device__ __forceinline__ void chunk_carry(const int2 in, const float* __restrict__ pr, unsigned& w_carry, float& p_carry) {
@@ -777,7 +779,8 @@ chunk_partial_kernel(const float* __restrict__ price, int64_t ld_price, const b2
         q.maxdd = maxdd; q.first_sum = first_sum; q.pivot = da.pivot; q.s1 = da.s1; q.s2 = da.s2; q.day_sum = day_sum;
         q.sum_dur = sum_dur; q.hash = ((unsigned long long)hhi << 32) | hlo;
         q.n_win = n_win; q.n_loss = n_loss; q.n_days = da.n_days; q.count = count;
-        q.first_done = first_done; q.first_day = first_id; q.day_cur = day_cur; q.pad = 0;
+        q.first_done = first_done; q.first_day = first_id; q.day_cur = day_cur;
+        q.n_neg = da.n_neg; q.npivot = da.npivot; q.ns1 = da.ns1; q.ns2 = da.ns2; q.pad = 0.0;
         partial[seg] = q;
     }
 }
@@ -851,9 +854,17 @@ __global__ void lane_combine_kernel(const b200bt_individual* __restrict__ indiv,
             da.s2 += q.s2 + 2.0 * d * q.s1 + n * d * d;
             da.n_days += q.n_days;
         }
+        if (q.n_neg) {
+            if (da.n_neg == 0) da.npivot = q.npivot;
+            const double d = q.npivot - da.npivot, n = (double)q.n_neg;
+            da.ns1 += q.ns1 + n * d;
+            da.ns2 += q.ns2 + 2.0 * d * q.ns1 + n * d * d;
+            da.n_neg += q.n_neg;
+        }
         open = true; open_day = q.day_cur; open_sum = q.day_sum;
     }
     a.pivot = da.pivot; a.s1 = da.s1; a.s2 = da.s2; a.n_days = da.n_days; a.pivot_set = da.pivot_set;
+    a.npivot = da.npivot; a.ns1 = da.ns1; a.ns2 = da.ns2; a.n_neg = da.n_neg;
     a.day_valid = open ? 1 : 0; a.day_sum = open_sum; a.day_cur = open_day;
     b200bt_lane_stats o;
     finalize_lane(a, cfg, o);

@@ -49,6 +49,8 @@ struct WarpAcc {
     // last day, so its sum is kept aside instead of being counted as a finished day
     int hold_first, first_done, first_day;
     double first_sum;
+    double npivot, ns1, ns2;     // negative days (DayAcc)
+    unsigned n_neg;
 };
 
 // Per-warp shared-memory working set.
@@ -63,6 +65,9 @@ struct DayAcc {
     double pivot, s1, s2;
     unsigned n_days;
     int pivot_set;
+    // the negative days alone (Sortino's downside deviation), same shifted accumulation
+    double npivot = 0.0, ns1 = 0.0, ns2 = 0.0;
+    unsigned n_neg = 0;
 };
 
 __device__ __forceinline__ void day_complete(DayAcc& a, double x) {
@@ -72,6 +77,13 @@ __device__ __forceinline__ void day_complete(DayAcc& a, double x) {
     a.s1 += y;
     a.s2 += y * y;
     a.n_days += 1;
+    if (x < 0.0) {
+        if (a.n_neg == 0) a.npivot = x;
+        const double z = x - a.npivot;
+        a.ns1 += z;
+        a.ns2 += z * z;
+        a.n_neg += 1;
+    }
 }
 
 // PnL of one trade record (strategy_evaluation.py:798,:819,:836): an entry record costs the entry fee,
@@ -156,7 +168,7 @@ static __device__ __noinline__ void batch_core(WarpAcc* __restrict__ acc, int cn
     // daily buckets: segmented sum by calendar day over the batch, merged with the carry day
     // calendar day of a record, relative to bar 0's day (32-bit: the host checks N*bar_minutes < 2^31 - 1440)
     const int day = active ? (int)(((unsigned)minute0 + bar * (unsigned)bar_minutes) / 1440u) : 0;
-    DayAcc da{acc->pivot, acc->s1, acc->s2, acc->n_days, acc->pivot_set};
+    DayAcc da{acc->pivot, acc->s1, acc->s2, acc->n_days, acc->pivot_set, acc->npivot, acc->ns1, acc->ns2, acc->n_neg};
     const int hold_first = acc->hold_first;
     int first_done = acc->first_done, first_id = acc->first_day;
     double first_sum = acc->first_sum;
@@ -221,6 +233,7 @@ static __device__ __noinline__ void batch_core(WarpAcc* __restrict__ acc, int cn
         acc->sum_dur = sum_dur;
         acc->equity = equity_out; acc->peak = peak_out; acc->maxdd = maxdd;
         acc->pivot = da.pivot; acc->s1 = da.s1; acc->s2 = da.s2; acc->n_days = da.n_days; acc->pivot_set = da.pivot_set;
+        acc->npivot = da.npivot; acc->ns1 = da.ns1; acc->ns2 = da.ns2; acc->n_neg = da.n_neg;
         acc->day_sum = day_sum; acc->day_cur = last_day; acc->day_valid = 1;
         acc->first_done = first_done; acc->first_day = first_id; acc->first_sum = first_sum;
         acc->hash ^= ((unsigned long long)hhi << 32) | hlo;
@@ -238,7 +251,7 @@ __device__ __forceinline__ void process_batch(WarpShared* __restrict__ ws, unsig
 
 // Metrics -> calculate_metrics' scalars and _calculate_strategy_score (strategy_evaluation.py:97-228,:579-633).
 __device__ __forceinline__ void finalize_lane(const WarpAcc& a, const b200bt_sweep_config& cfg, b200bt_lane_stats& o) {
-    DayAcc da{a.pivot, a.s1, a.s2, a.n_days, a.pivot_set};
+    DayAcc da{a.pivot, a.s1, a.s2, a.n_days, a.pivot_set, a.npivot, a.ns1, a.ns2, a.n_neg};
     if (a.day_valid) day_complete(da, a.day_sum);
     const double n_rec = (double)a.n_events;
     o.n_records = n_rec;
@@ -270,6 +283,21 @@ __device__ __forceinline__ void finalize_lane(const WarpAcc& a, const b200bt_swe
     o.sharpe_ratio = sharpe;
     o.win_rate = win_rate;
     o.profit_factor = pf;
+    // calculate_advanced_metrics (:250-263, :307-312): only a lane with >= 2 records has daily buckets
+    double mean_daily = 0.0, downside = 0.0, sortino = 0.0;
+    if (a.n_events >= 2 && da.n_days > 0) {
+        mean_daily = da.pivot + da.s1 / (double)da.n_days;
+        if (da.n_neg > 0) {
+            const double nn = (double)da.n_neg, my = da.ns1 / nn;
+            double var = da.ns2 / nn - my * my;
+            downside = sqrt(var < 0.0 ? 0.0 : var);
+        }
+        sortino = downside > 0.0 ? (mean_daily / downside) * sqrt(252.0) : INFINITY;
+    }
+    o.sortino_ratio = sortino;
+    o.n_negative_days = (a.n_events >= 2) ? (double)da.n_neg : 0.0;
+    o.downside_deviation = downside;
+    o.mean_daily_pnl = mean_daily;
     double primary;
     switch (cfg.primary) {
         case B200BT_PRIMARY_RETURN_PCT: primary = (o.net_profit / cfg.initial_capital) * 100.0; break;
@@ -298,6 +326,8 @@ __device__ __forceinline__ void init_acc(WarpAcc& a, const b200bt_individual& iv
     a.day_valid = a.pivot_set = 0;
     a.hold_first = a.first_done = a.first_day = 0;
     a.first_sum = 0.0;
+    a.npivot = a.ns1 = a.ns2 = 0.0;
+    a.n_neg = 0;
 }
 
 __device__ __forceinline__ void init_scan_const(ScanConst& c, const b200bt_individual& iv) {

@@ -104,6 +104,43 @@ class StrategyPerformanceMetrics:
         }
 
 
+    @staticmethod
+    def calculate_advanced_metrics(metrics: Dict) -> Dict:
+        """calculate_advanced_metrics (:231-319): Calmar, Sortino, recovery factor, expectancy, profit per day
+        from a calculate_metrics dict; the streak fields appear only when the caller added a 'trades' list (:267-288)."""
+        import numpy as np
+        out = dict(metrics)
+        dd = metrics.get("max_drawdown", 0)
+        out["calmar_ratio"] = (metrics.get("return_pct", 0) / 100) / dd if dd > 0 else float("inf")
+        daily = list(metrics.get("daily_returns", {}).values())
+        if daily:
+            neg = [r for r in daily if r < 0]
+            downside = np.std(neg) if neg else 0
+            out["sortino_ratio"] = (np.mean(daily) / downside) * np.sqrt(252) if downside > 0 else float("inf")
+        else:
+            out["sortino_ratio"] = 0
+        trades = metrics.get("trades", []) if metrics.get("total_trades", 0) > 0 else []
+        if trades:
+            win = loss = best_win = best_loss = 0
+            for t in sorted(trades, key=lambda x: x.get("timestamp", "")):
+                if t.get("pnl", 0) > 0:
+                    win, loss = win + 1, 0
+                    best_win = max(best_win, win)
+                else:
+                    loss, win = loss + 1, 0
+                    best_loss = max(best_loss, loss)
+            out["max_consecutive_wins"], out["max_consecutive_losses"] = best_win, best_loss
+        out["recovery_factor"] = (metrics.get("net_profit", 0) / (dd * metrics.get("initial_capital", 10000))
+                                  if dd > 0 else float("inf"))
+        if metrics.get("total_trades", 0) > 0:
+            wr = metrics.get("win_rate", 0)
+            out["expectancy"] = wr * metrics.get("average_profit", 0) - (1 - wr) * abs(metrics.get("average_loss", 0))
+        else:
+            out["expectancy"] = 0
+        out["profit_per_day"] = np.mean(daily) if daily else 0
+        return out
+
+
 class StrategyEvaluationSystem:
     def __init__(self, config_path: Optional[str] = "config.json", config: Optional[Dict] = None):
         if config is None:

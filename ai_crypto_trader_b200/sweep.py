@@ -391,7 +391,7 @@ class PopulationSweep:
             return
         m = self.market
         if self._stats is None or self._pop != pop:
-            self._stats = torch.empty((pop, m.S, 16), dtype=torch.float64, device=m.device)
+            self._stats = torch.empty((pop, m.S, _lib.LANE_STATS_WORDS), dtype=torch.float64, device=m.device)
             self._events = (torch.zeros((pop, m.S, self.event_cap), dtype=torch.int32, device=m.device)
                             if self.event_cap else None)
             self._pop = pop
@@ -406,7 +406,7 @@ class PopulationSweep:
     def _ensure_buffers(self, pop: int) -> None:
         m = self.market
         if self._stats is None or self._pop != pop:
-            self._stats = torch.empty((pop, m.S, 16), dtype=torch.float64, device=m.device)
+            self._stats = torch.empty((pop, m.S, _lib.LANE_STATS_WORDS), dtype=torch.float64, device=m.device)
             self._events = (torch.zeros((pop, m.S, self.event_cap), dtype=torch.int32, device=m.device)
                             if self.event_cap else None)
             self._pop = pop
@@ -583,8 +583,26 @@ class PopulationSweep:
         if getattr(self, "_inverse", None) is not None:
             raw = raw[self._inverse]
         out = {name: raw[:, :, i] for i, name in enumerate(_lib.LANE_STATS_FIELDS[:-1])}
-        out["trade_hash"] = np.ascontiguousarray(raw[:, :, 15]).view(np.uint64)
+        out["trade_hash"] = np.ascontiguousarray(raw[:, :, _lib.LANE_STATS_WORDS - 1]).view(np.uint64)
         return out
+
+    def advanced_stats(self) -> Dict[str, np.ndarray]:
+        """calculate_advanced_metrics (strategy_evaluation.py:231-319) for every lane of the last evaluation,
+        [pop][S] arrays: the Sortino ingredients come out of the kernels' daily buckets, the rest is arithmetic on
+        the lane stats (same expressions as the reference, including its fixed 10 000 in the recovery factor)."""
+        st = self.lane_stats()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dd, net, n = st["max_drawdown"], st["net_profit"], st["n_records"]
+            ret_pct = net / self.cfg.initial_capital * 100
+            avg_p = np.where(st["n_wins"] > 0, st["total_profit"] / st["n_wins"], 0.0)
+            avg_l = np.where(st["n_losses"] > 0, st["total_loss"] / st["n_losses"], 0.0)
+            return {
+                "calmar_ratio": np.where(dd > 0, (ret_pct / 100) / dd, np.inf),
+                "sortino_ratio": st["sortino_ratio"],
+                "recovery_factor": np.where(dd > 0, net / (dd * 10000), np.inf),
+                "expectancy": np.where(n > 0, st["win_rate"] * avg_p - (1 - st["win_rate"]) * np.abs(avg_l), 0.0),
+                "profit_per_day": st["mean_daily_pnl"],
+            }
 
     def events(self) -> Optional[np.ndarray]:
         """First `event_cap` event words per lane, uint32 [pop][S][cap] (see B200BT_EVENT_*)."""

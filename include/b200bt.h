@@ -148,7 +148,7 @@ typedef struct b200bt_individual {
     double position_size;
 } b200bt_individual; /* 40 bytes */
 
-/* Per-lane result, 16 x 8 bytes.  Field meaning follows calculate_metrics
+/* Per-lane result, 20 x 8 bytes.  Field meaning follows calculate_metrics
  * (strategy_evaluation.py:187-225) on the lane's trade RECORDS (an entry and
  * an exit record per round trip, as the reference emits them). */
 typedef struct b200bt_lane_stats {
@@ -167,8 +167,14 @@ typedef struct b200bt_lane_stats {
     double score;          /* _calculate_strategy_score                      */
     double win_rate;
     double profit_factor;  /* +inf when total_loss == 0 (reference :113)     */
-    uint64_t trade_hash;   /* xor of mix64(event_index, bar, side) over all events */
-} b200bt_lane_stats; /* 128 bytes */
+    /* ingredients of calculate_advanced_metrics (strategy_evaluation.py:231-319) that need the daily buckets */
+    double sortino_ratio;  /* mean(daily) / std(negative dailies, ddof 0) * sqrt(252); +inf without a negative
+                              spread, 0 without daily buckets (:250-263)      */
+    double n_negative_days;
+    double downside_deviation; /* np.std of the negative daily sums           */
+    double mean_daily_pnl; /* profit_per_day (:307-312)                       */
+    uint64_t trade_hash;   /* xor of event_hash(event_index, event word) over all events */
+} b200bt_lane_stats; /* 160 bytes */
 
 /* Scoring rule (config.json evolution.optimization_goals). */
 #define B200BT_PRIMARY_SHARPE 0

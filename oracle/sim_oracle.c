@@ -41,6 +41,8 @@ typedef struct {
     double n_records, n_wins, n_losses, total_profit, total_loss, net_profit, max_drawdown,
         sharpe_ratio, n_days, largest_profit, largest_loss, sum_duration_bars, score, win_rate,
         profit_factor;
+    /* calculate_advanced_metrics :250-263, :307-312 */
+    double sortino_ratio, n_negative_days, downside_deviation, mean_daily_pnl;
     uint64_t trade_hash;
 } oracle_stats;
 
@@ -201,6 +203,28 @@ int oracle_lane(const float* price, const float* rsi, int64_t n, const oracle_pa
     out->sharpe_ratio = sharpe;
     out->win_rate = win_rate;
     out->profit_factor = pf;
+    if (a.n_rec >= 2 && a.n_days > 0) {
+        /* np.mean(daily); np.std of the negative ones (ddof 0, two-pass) */
+        double s = 0.0, sn = 0.0;
+        size_t nn = 0;
+        for (size_t i = 0; i < a.n_days; ++i) {
+            s += a.days[i];
+            if (a.days[i] < 0) { sn += a.days[i]; ++nn; }
+        }
+        const double mean = s / (double)a.n_days;
+        double sd = 0.0;
+        if (nn) {
+            const double mn = sn / (double)nn;
+            double v = 0.0;
+            for (size_t i = 0; i < a.n_days; ++i)
+                if (a.days[i] < 0) v += (a.days[i] - mn) * (a.days[i] - mn);
+            sd = sqrt(v / (double)nn);
+        }
+        out->mean_daily_pnl = mean;
+        out->n_negative_days = (double)nn;
+        out->downside_deviation = sd;
+        out->sortino_ratio = sd > 0.0 ? (mean / sd) * sqrt(252.0) : INFINITY;
+    }
     double primary;
     switch (cfg->primary) {
         case 1: primary = (out->net_profit / cfg->initial_capital) * 100.0; break;

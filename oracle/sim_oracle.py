@@ -24,7 +24,8 @@ class Config(C.Structure):
 
 STATS_FIELDS = ("n_records", "n_wins", "n_losses", "total_profit", "total_loss", "net_profit", "max_drawdown",
                 "sharpe_ratio", "n_days", "largest_profit", "largest_loss", "sum_duration_bars", "score",
-                "win_rate", "profit_factor", "trade_hash")
+                "win_rate", "profit_factor", "sortino_ratio", "n_negative_days", "downside_deviation", "mean_daily_pnl",
+                "trade_hash")
 STATS_DTYPE = np.dtype([(n, "<f8") for n in STATS_FIELDS[:-1]] + [("trade_hash", "<u8")])
 
 

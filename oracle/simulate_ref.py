@@ -160,6 +160,34 @@ def calculate_metrics(trades: List[Dict], initial_capital: float = 10000.0) -> D
                 daily_returns=daily, equity_curve=equity)
 
 
+ADVANCED_KEYS = ("calmar_ratio", "sortino_ratio", "recovery_factor", "expectancy", "profit_per_day")
+
+
+def calculate_advanced_metrics(metrics: Dict) -> Dict:
+    """calculate_advanced_metrics (:231-319) on the dict calculate_metrics returns.  That dict carries neither
+    'trades' nor 'initial_capital', so the reference never produces the streak fields and always divides the
+    recovery factor by 10 000."""
+    out = dict(metrics)
+    dd = metrics.get("max_drawdown", 0)
+    out["calmar_ratio"] = (metrics.get("return_pct", 0) / 100) / dd if dd > 0 else float("inf")            # :244-250
+    daily = list(metrics.get("daily_returns", {}).values())
+    if daily:                                                                                               # :253-263
+        neg = [r for r in daily if r < 0]
+        downside = np.std(neg) if neg else 0
+        out["sortino_ratio"] = (np.mean(daily) / downside) * np.sqrt(252) if downside > 0 else float("inf")
+    else:
+        out["sortino_ratio"] = 0
+    out["recovery_factor"] = (metrics.get("net_profit", 0) / (dd * metrics.get("initial_capital", 10000))
+                              if dd > 0 else float("inf"))                                                  # :291-296
+    if metrics.get("total_trades", 0) > 0:                                                                  # :298-306
+        wr = metrics.get("win_rate", 0)
+        out["expectancy"] = wr * metrics.get("average_profit", 0) - (1 - wr) * abs(metrics.get("average_loss", 0))
+    else:
+        out["expectancy"] = 0
+    out["profit_per_day"] = np.mean(daily) if daily else 0                                                  # :308-313
+    return out
+
+
 def strategy_score(metrics: Dict, goals: Dict) -> float:
     """:579-633.  `trades_per_day` is never produced by calculate_metrics, so the
     min_trades_per_day constraint never penalises; mirrored."""

@@ -85,6 +85,7 @@ def make_sim():
             trades = ses._simulate_trades(name, dict(params), points)            # REFERENCE
             m = metrics_cls.calculate_metrics(trades)                            # REFERENCE
             score = ses._calculate_strategy_score(m)                             # REFERENCE
+            adv = metrics_cls.calculate_advanced_metrics(m)                      # REFERENCE (:231-319)
             key = f"{name}_{sym}"
             arrays[f"bar_{key}"] = np.array([ts_to_bar[t["timestamp"]] for t in trades], dtype=np.int64)
             arrays[f"sell_{key}"] = np.array([t["side"] == "sell" for t in trades], dtype=np.bool_)
@@ -96,6 +97,7 @@ def make_sim():
             arrays[f"daily_{key}"] = np.array([daily[k] for k in sorted(daily)], dtype=np.float64)
             cases.append({"key": key, "name": name, "symbol": sym, "params": params,
                           "metrics": {k: jsonable(m[k]) for k in SCALARS}, "score": jsonable(score),
+                          "advanced": {k: jsonable(adv[k]) for k in simulate_ref.ADVANCED_KEYS},
                           "n_records": len(trades)})
             print(f"{key:28s} records={len(trades):5d} score={float(score):.6g}")
     np.savez_compressed(OUT / "sim_cases.npz", **arrays)

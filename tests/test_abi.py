@@ -24,7 +24,7 @@ def test_struct_layouts_match_header(native_lib):
     from ai_crypto_trader_b200 import _lib
     assert C.sizeof(_lib.Individual) == 40
     assert C.sizeof(_lib.SweepConfig) == 32
-    assert len(_lib.LANE_STATS_FIELDS) * 8 == 128
+    assert len(_lib.LANE_STATS_FIELDS) * 8 == 160
 
 
 def test_no_cpu_fallback(native_lib):

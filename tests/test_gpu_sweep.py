@@ -81,10 +81,13 @@ def test_sweep_matches_reference_fixtures(torch_cuda, sim_golden):
     population = [dict(by_name[nm]) for nm in names]
     fitness = sweep.evaluate(population)
     stats = sweep.lane_stats()
+    advanced = sweep.advanced_stats()
     events = sweep.events()
     for c in meta["cases"]:
         i, j, key = names.index(c["name"]), syms.index(c["symbol"]), c["key"]
         nrec = c["n_records"]
+        for name, want in c["advanced"].items():      # the reference's calculate_advanced_metrics (:231-319)
+            assert advanced[name][i, j] == pytest.approx(unjson(want), rel=1e-9, abs=1e-12), (key, name)
         assert int(stats["n_records"][i, j]) == nrec, key
         ev = events[i, j, :nrec]
         assert (ev & _lib.EVENT_BAR_MASK).tolist() == arrays[f"bar_{key}"].tolist(), key
@@ -130,8 +133,10 @@ def test_sweep_vs_c_oracle_random_populations(torch_cuda, n_bars, pop, n_sym):
             for f in ("n_wins", "n_losses", "n_days", "sum_duration_bars"):
                 assert stats[f][i, s] == want[f], (i, s, f)
             for f in ("total_profit", "total_loss", "net_profit", "max_drawdown", "sharpe_ratio", "largest_profit",
-                      "largest_loss", "win_rate", "profit_factor", "score"):
+                      "largest_loss", "win_rate", "profit_factor", "score", "sortino_ratio", "downside_deviation",
+                      "mean_daily_pnl"):
                 assert stats[f][i, s] == pytest.approx(float(want[f]), rel=1e-9, abs=1e-11), (i, s, f)
+            assert stats["n_negative_days"][i, s] == want["n_negative_days"], (i, s)
             scores[i, s] = want["score"]
     np.testing.assert_allclose(fitness, scores.mean(axis=1), rtol=1e-9, atol=1e-11)
 
@@ -194,8 +199,10 @@ def _check_lanes_vs_oracle(sweep, population, ohlcv, cap):
             for f in ("n_wins", "n_losses", "n_days", "sum_duration_bars"):
                 assert stats[f][i, s] == want[f], (i, s, f)
             for f in ("total_profit", "total_loss", "net_profit", "max_drawdown", "sharpe_ratio", "largest_profit",
-                      "largest_loss", "win_rate", "profit_factor", "score"):
+                      "largest_loss", "win_rate", "profit_factor", "score", "sortino_ratio", "downside_deviation",
+                      "mean_daily_pnl"):
                 assert stats[f][i, s] == pytest.approx(float(want[f]), rel=1e-9, abs=1e-11), (i, s, f)
+            assert stats["n_negative_days"][i, s] == want["n_negative_days"], (i, s)
 
 
 @pytest.mark.parametrize("n_bars,opts", [
@@ -287,6 +294,7 @@ def test_tiled_sweep_is_exact_and_self_repairing(torch_cuda, n_bars, opts):
     f_t = tiled.evaluate(population)
     f_f = fused.evaluate(population)
     hash_first = tiled.lane_stats()["trade_hash"].copy()
+    first_invalid, first_overflow = tiled.last_invalid_lanes, tiled.last_pool_overflow
     f_t2 = tiled.evaluate(population)          # the second sweep of a bank goes through the zone map (block skipping)
     assert tiled._zones is not None
     np.testing.assert_allclose(f_t2, f_t, rtol=1e-12, atol=0)   # (lanes may switch between the chunked and the fused arithmetic)
@@ -295,11 +303,12 @@ def test_tiled_sweep_is_exact_and_self_repairing(torch_cuda, n_bars, opts):
     if "chunks" in opts:
         assert plan.K == opts["chunks"]
     if opts.get("max_repair_rounds", 8) == 0:
-        assert tiled.last_invalid_lanes > 0            # the fallback path really ran
+        assert first_invalid > 0                       # the fallback path really ran
     if opts.get("max_repair_rounds", 8) == 64:
-        assert tiled.last_invalid_lanes == 0           # every wrong boundary was repaired in place
+        assert first_invalid == 0                      # every wrong boundary was repaired in place
     if "pool_blocks" in opts:
-        assert tiled.last_pool_overflow and tiled.last_invalid_lanes > 0
+        assert first_overflow and first_invalid > 0    # (the second sweep planned a larger pool)
+        assert not tiled.last_pool_overflow
     np.testing.assert_array_equal(tiled.lane_stats()["trade_hash"], fused.lane_stats()["trade_hash"])
     np.testing.assert_array_equal(tiled.lane_stats()["n_records"], fused.lane_stats()["n_records"])
     ev_t, ev_f, n_rec = tiled.events(), fused.events(), fused.lane_stats()["n_records"]

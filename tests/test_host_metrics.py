@@ -22,5 +22,12 @@ def test_metrics_and_score_match_reference(sim_golden):
         if recs:
             assert np.array_equal(np.array(m["equity_curve"]), arrays[f"equity_{key}"])
         assert float(ses._calculate_strategy_score(m)) == unjson(c["score"]), key
+        adv = StrategyPerformanceMetrics.calculate_advanced_metrics(m)
+        for name, want in c["advanced"].items():
+            assert float(adv[name]) == unjson(want), (key, name)
+        assert "max_consecutive_wins" not in adv              # the metrics dict carries no 'trades' (:267)
+        streaks = StrategyPerformanceMetrics.calculate_advanced_metrics(dict(m, trades=recs))
+        if recs and m["total_trades"] > 0:
+            assert streaks["max_consecutive_wins"] <= 1 and streaks["max_consecutive_losses"] >= 1   # entries always lose the fee
     one = StrategyPerformanceMetrics.calculate_metrics([{"timestamp": "2024-01-01T00:00:00", "pnl": 3.0}])
     assert one["total_trades"] == 1 and one["win_rate"] == 1.0 and one["net_profit"] == 3.0

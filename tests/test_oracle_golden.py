@@ -35,6 +35,10 @@ def test_python_restatement_matches_reference_records(sim_golden):
             got = float(m[name])
             assert got == want or (np.isnan(got) and np.isnan(want)), (key, name, got, want)
         assert np.array_equal(np.array(m["equity_curve"]), arrays[f"equity_{key}"]), key
+        adv = simulate_ref.calculate_advanced_metrics(m)
+        for name, want in case["advanced"].items():
+            want, got = unjson(want), float(adv[name])
+            assert got == want or (np.isnan(got) and np.isnan(want)), (key, name, got, want)
         got_score = float(simulate_ref.strategy_score(m, meta["goals"]))
         assert got_score == unjson(case["score"]), key
 
@@ -61,6 +65,10 @@ def test_c_oracle_matches_reference(sim_golden):
             want = unjson(want)
             assert got == pytest.approx(want, rel=1e-11, abs=1e-12), (key, got, want)
         assert int(st["n_days"]) == len(arrays[f"daily_{key}"]), key
+        adv = case["advanced"]
+        assert st["sortino_ratio"] == pytest.approx(unjson(adv["sortino_ratio"]), rel=1e-10, abs=1e-12), key
+        assert st["mean_daily_pnl"] == pytest.approx(unjson(adv["profit_per_day"]), rel=1e-11, abs=1e-12), key
+        assert int(st["n_negative_days"]) == int((arrays[f"daily_{key}"] < 0).sum()) * (case["n_records"] >= 2), key
         if case["n_records"]:
             dur = m["avg_trade_duration"] * (case["n_records"] // 2)
             assert st["sum_duration_bars"] == pytest.approx(dur, rel=1e-12), key
