@@ -204,6 +204,7 @@ def lane_costs(population: List[Dict]) -> np.ndarray:
 
 
 _PINNED_FLAG = None
+DEFERRED = torch.empty(0, dtype=torch.uint8)      # sentinel: the caller assigns plan.workspace (plan_batches)
 
 
 def _pinned_flag() -> torch.Tensor:
@@ -249,11 +250,11 @@ class ChunkPlan:
         self.seg_base_dev = torch.from_numpy(self.seg_base).to(device)
         self.n_chunks_dev = torch.from_numpy(self.n_chunks).to(device)
         self.order_dev = torch.from_numpy(self.order).to(device)
-        ws_bytes = int(_lib.load().b200bt_sweep_chunked_workspace_bytes(self.pool_blocks, n_symbols, self.n_seg))
-        if workspace is not None and workspace.numel() >= ws_bytes:
+        self.ws_bytes = int(_lib.load().b200bt_sweep_chunked_workspace_bytes(self.pool_blocks, n_symbols, self.n_seg))
+        if workspace is not None and workspace.numel() >= self.ws_bytes:
             self.workspace = workspace
         else:
-            self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+            self.workspace = None if workspace is DEFERRED else torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
         self.invalid = torch.zeros((pop, n_symbols), dtype=torch.uint8, device=device)
         self.overflow = _pinned_flag()
         self.pop = pop
@@ -298,11 +299,11 @@ class TilePlan:
         if pool_blocks is not None:
             self.pool_blocks = int(pool_blocks)
         self.order_dev = torch.from_numpy(self.order).to(device)
-        ws_bytes = int(_lib.load().b200bt_sweep_tiled_workspace_bytes(self.pool_blocks, n_symbols, pop, self.K))
-        if workspace is not None and workspace.numel() >= ws_bytes:
+        self.ws_bytes = int(_lib.load().b200bt_sweep_tiled_workspace_bytes(self.pool_blocks, n_symbols, pop, self.K))
+        if workspace is not None and workspace.numel() >= self.ws_bytes:
             self.workspace = workspace
         else:
-            self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+            self.workspace = None if workspace is DEFERRED else torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
         self.invalid = torch.zeros((pop, n_symbols), dtype=torch.uint8, device=device)
         self.overflow = _pinned_flag()
 
@@ -527,11 +528,11 @@ class PopulationSweep:
         cuts.append(len(population))
         if len(cuts) == 2:
             return [cls(population, self.market.N, self.market.S, self.market.device, **kw)]
-        plans, shared = [], None
-        for lo, hi in sorted(zip(cuts[:-1], cuts[1:]), key=lambda c: -float(pred[c[0]:c[1]].sum())):
-            pl = cls(population[lo:hi], self.market.N, self.market.S, self.market.device, lo=lo, workspace=shared, **kw)
-            shared = shared if shared is not None else pl.workspace     # the largest slice is planned first
-            plans.append(pl)
+        plans = [cls(population[lo:hi], self.market.N, self.market.S, self.market.device, lo=lo, workspace=DEFERRED, **kw)
+                 for lo, hi in zip(cuts[:-1], cuts[1:])]
+        shared = torch.empty(max(pl.ws_bytes for pl in plans), dtype=torch.uint8, device=self.market.device)
+        for pl in plans:
+            pl.workspace = shared        # the slices run one after the other on the same stream
         return sorted(plans, key=lambda pl: pl.lo)
 
     # -- host-facing evaluation --------------------------------------------

@@ -242,9 +242,9 @@ def main():
     path_kernels = {"fused": "sweep_kernel", "chunked": "chunk_scan_kernel + chunk_sums/partial/lane_combine",
                     "tiled": "lane_scan_kernel + chunk_sums/partial/lane_combine"}[path]
     # DRAM bytes (read + write) of the dominant kernel per launch on THIS workload, from the committed
-    # `ncu --set full` captures (profiles/r1_lane_scan_ncu.txt, r1_chunk_scan_ncu.txt, r1_sweep_v2_ncu.txt);
+    # `ncu --set full` captures (profiles/r1_tiled_final_ncu.txt, r1_chunk_scan_ncu.txt, r1_sweep_v2_ncu.txt);
     # null for any other workload size
-    ncu_traffic = {"tiled": 4.581e9 + 1.032e9, "chunked": 45.6e9, "fused": 3.3e9}[path] \
+    ncu_traffic = {"tiled": 5.222e9 + 1.006e9, "chunked": 45.6e9, "fused": 3.3e9}[path] \
         if (pop_local, S, N) == (POP_PER_GPU, N_SYMBOLS, N_BARS) else None
 
     def step():
