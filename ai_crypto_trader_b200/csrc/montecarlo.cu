@@ -51,12 +51,14 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
 // round-to-even, so the top value rounds to exactly 1; never 0).
 __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
-// Box-Muller: two uniforms -> two standard normals (r cos 2*pi*v, r sin 2*pi*v).  The radius uses the
-// accurate logf (the fast __logf has an ABSOLUTE error of 2^-21, which for u -> 1 exceeds -ln u itself
-// and can even flip its sign); rsqrt / sin / cos use the MUFU units: the angle is taken in (-pi, pi)
-// where __sincosf is accurate to 2^-21, the half-turn shift is undone by the sign flip.
+// Box-Muller: two uniforms -> two standard normals (r cos 2*pi*v, r sin 2*pi*v), all on the MUFU units.
+// Radius: t = -2 ln u with the fast __logf (absolute error 2^-21 in ln u).  For u -> 1 that error exceeds -ln u
+// itself and can make t slightly negative: t is clamped at 0, i.e. a radius below ~1e-3 (probability ~5e-7 per
+// draw) is only known to ~1e-3 absolute -- far below the Monte-Carlo error of any statistic reported here, and
+// checked against the float64 NumPy restatement (oracle/mc_ref.py) at 3e-5 relative on the final prices.
+// Angle: taken in (-pi, pi) where __sincosf is accurate to 2^-21; the half-turn shift is undone by the sign flip.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-    const float t = -2.0f * logf(u01(a));                 // >= 0; exactly 0 when the uniform rounds to 1
+    const float t = fmaxf(-2.0f * __logf(u01(a)), 0.0f);
     const float r = t * rsqrtf(fmaxf(t, 1e-30f));
     float s, c;
     __sincosf(6.283185307179586f * u01(b) - 3.14159265358979f, &s, &c);
