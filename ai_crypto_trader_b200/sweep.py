@@ -269,12 +269,12 @@ class TilePlan:
 
     @classmethod
     def chunks_for(cls, pop: int, n_bars: int, n_symbols: int, device, warm: int = 8192, max_chunks: int = 64) -> int:
-        """About 1.5 resident sets of CTAs (measured optimum on the C2 workload: heavy CTAs run longer, so whole
-        "waves" do not exist), chunks at least 4 warm-ups long."""
+        """About 1.75 resident sets of CTAs (measured optimum on the C2 workload, flat from 1.6 to 1.9: heavy CTAs
+        run longer, so whole "waves" do not exist), chunks at least 4 warm-ups long."""
         kmax = max(1, min(max_chunks, n_bars // max(4 * warm, 2048)))
         slots = torch.cuda.get_device_properties(device).multi_processor_count * cls.CTAS_PER_SM
         groups = -(-pop // cls.THREADS) * n_symbols
-        return min(kmax, max(1, round(1.5 * slots / groups)))
+        return min(kmax, max(1, round(1.75 * slots / groups)))
 
     def __init__(self, population: List[Dict], n_bars: int, n_symbols: int, device, warm: int = 8192,
                  max_chunks: int = 64, chunks: Optional[int] = None, pool_scale: float = 1.5,
