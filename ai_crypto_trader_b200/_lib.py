@@ -49,6 +49,8 @@ class SweepConfig(C.Structure):
         ("primary", C.c_int32),
         ("secondary_mask", C.c_int32),
         ("variant", C.c_int32),
+        ("gap_bar", C.c_int32),
+        ("gap_minutes", C.c_int32),
     ]
 
 

@@ -54,7 +54,7 @@ sweep_kernel(const float* __restrict__ price, int64_t ld_price,
         init_scan_const(sc0, iv);
         ws->sc = sc0;
         WarpAcc a0;
-        init_acc(a0, iv, cfg.initial_capital, events ? events + ((int64_t)ind * S + sym) * ev_cap : nullptr);
+        init_acc(a0, iv, cfg, events ? events + ((int64_t)ind * S + sym) * ev_cap : nullptr);
         ws->acc = a0;
     }
     __syncwarp();
@@ -188,7 +188,9 @@ extern "C" int b200bt_sweep(const float* price, int64_t ld_price, const float* r
     B200BT_REQUIRE(ld_price >= N && ld_rsi >= N, B200BT_EINVAL, "sweep: row stride shorter than N");
     B200BT_REQUIRE(N < (1ll << 30), B200BT_ELIMIT, "sweep: N must be < 2^30 bars");
     B200BT_REQUIRE(cfg_host->bar_minutes > 0, B200BT_EINVAL, "sweep: bar_minutes must be > 0");
-    B200BT_REQUIRE(cfg_host->minute0 >= 0 && cfg_host->minute0 + N * (int64_t)cfg_host->bar_minutes < (1ll << 32) - 1440,
+    B200BT_REQUIRE(cfg_host->gap_minutes >= 0, B200BT_EINVAL, "sweep: negative gap_minutes");
+    B200BT_REQUIRE(cfg_host->minute0 >= 0 &&
+                       cfg_host->minute0 + N * (int64_t)cfg_host->bar_minutes + cfg_host->gap_minutes < (1ll << 32) - 1440,
                    B200BT_ELIMIT, "sweep: minute0 + N*bar_minutes must stay below 2^32 minutes");
     B200BT_REQUIRE(events == nullptr || event_cap > 0, B200BT_EINVAL, "sweep: event buffer without capacity");
     int rc = check_device();

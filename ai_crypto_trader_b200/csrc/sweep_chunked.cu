@@ -632,6 +632,11 @@ chunk_partial_kernel(const float* __restrict__ price, int64_t ld_price, const b2
     unsigned long long l_hash = 0ull;
     uint32_t* const ev_out = events ? events + ((int64_t)item.individual * S + sym) * ev_cap : nullptr;
     const unsigned minute0 = (unsigned)cfg.minute0, bar_minutes = (unsigned)cfg.bar_minutes;
+    const unsigned gap_bar = cfg.gap_bar > 0 ? (unsigned)cfg.gap_bar : 0xffffffffu, gap_minutes = (unsigned)cfg.gap_minutes;
+    auto day_of = [&](unsigned w) {   // calendar day of a record (a glued series jumps gap_minutes at gap_bar)
+        const unsigned bar = w & 0x3fffffffu;
+        return (int)((minute0 + bar * bar_minutes + (bar >= gap_bar ? gap_minutes : 0u)) / 1440u);
+    };
     auto finish_day = [&](int id, double x) {     // the chunk's first day may continue the previous chunk's last one
         if (!first_done) { first_done = 1; first_id = id; first_sum = x; }
         else day_complete(da, x);
@@ -709,8 +714,8 @@ chunk_partial_kernel(const float* __restrict__ price, int64_t ld_price, const b2
 
         // calendar-day buckets
         const int last_lane = (cnt - 1) >> 1;
-        const int d0 = a0 ? (int)((minute0 + (w0 & 0x3fffffffu) * bar_minutes) / 1440u) : 0;
-        const int d1 = a1 ? (int)((minute0 + (w1 & 0x3fffffffu) * bar_minutes) / 1440u) : d0;
+        const int d0 = a0 ? day_of(w0) : 0;
+        const int d1 = a1 ? day_of(w1) : d0;
         const int first_day = __shfl_sync(FULL, d0, 0);
         const int last_day = __shfl_sync(FULL, d1, last_lane);
         if (first_day == last_day && (!day_valid || first_day == day_cur)) {
@@ -818,7 +823,7 @@ __global__ void lane_combine_kernel(const b200bt_individual* __restrict__ indiv,
     invalid[t] = ok ? 0 : 1;
     if (!ok) return;
     WarpAcc a;
-    init_acc(a, indiv[ind], cfg.initial_capital, nullptr);
+    init_acc(a, indiv[ind], cfg, nullptr);
     DayAcc da{0.0, 0.0, 0.0, 0u, 0};
     bool open = false;      // the lane's open (last, not yet finished) calendar day
     int open_day = 0;
@@ -1040,8 +1045,8 @@ int check_sweep_args(const char* who, const float* price, int64_t ld_price, cons
     B200BT_REQUIRE(S > 0 && N > 0 && P > 0, B200BT_EINVAL, "%s: bad sizes", who);
     B200BT_REQUIRE(ld_price >= N && ld_rsi >= N, B200BT_EINVAL, "%s: row stride shorter than N", who);
     B200BT_REQUIRE(N < (1ll << 30), B200BT_ELIMIT, "%s: N must be < 2^30 bars", who);
-    B200BT_REQUIRE(cfg_host->bar_minutes > 0 && cfg_host->minute0 >= 0 &&
-                       cfg_host->minute0 + N * (int64_t)cfg_host->bar_minutes < (1ll << 32) - 1440,
+    B200BT_REQUIRE(cfg_host->bar_minutes > 0 && cfg_host->minute0 >= 0 && cfg_host->gap_minutes >= 0 &&
+                       cfg_host->minute0 + N * (int64_t)cfg_host->bar_minutes + cfg_host->gap_minutes < (1ll << 32) - 1440,
                    B200BT_ELIMIT, "%s: minute0 + N*bar_minutes must stay below 2^32 minutes", who);
     B200BT_REQUIRE(events == nullptr || event_cap > 0, B200BT_EINVAL, "%s: event buffer without capacity", who);
     return B200BT_OK;

@@ -51,6 +51,7 @@ struct WarpAcc {
     double first_sum;
     double npivot, ns1, ns2;     // negative days (DayAcc)
     unsigned n_neg;
+    unsigned gap_bar, gap_minutes;   // calendar clock of a glued series (b200bt_sweep_config); gap_bar = ~0u: none
 };
 
 // Per-warp shared-memory working set.
@@ -167,7 +168,7 @@ static __device__ __noinline__ void batch_core(WarpAcc* __restrict__ acc, int cn
 
     // daily buckets: segmented sum by calendar day over the batch, merged with the carry day
     // calendar day of a record, relative to bar 0's day (32-bit: the host checks N*bar_minutes < 2^31 - 1440)
-    const int day = active ? (int)(((unsigned)minute0 + bar * (unsigned)bar_minutes) / 1440u) : 0;
+    const int day = active ? (int)(((unsigned)minute0 + bar * (unsigned)bar_minutes + (bar >= acc->gap_bar ? acc->gap_minutes : 0u)) / 1440u) : 0;
     DayAcc da{acc->pivot, acc->s1, acc->s2, acc->n_days, acc->pivot_set, acc->npivot, acc->ns1, acc->ns2, acc->n_neg};
     const int hold_first = acc->hold_first;
     int first_done = acc->first_done, first_id = acc->first_day;
@@ -314,7 +315,10 @@ __device__ __forceinline__ void finalize_lane(const WarpAcc& a, const b200bt_swe
 }
 
 // Initial metrics state of a lane.
-__device__ __forceinline__ void init_acc(WarpAcc& a, const b200bt_individual& iv, double initial_capital, uint32_t* ev_out) {
+__device__ __forceinline__ void init_acc(WarpAcc& a, const b200bt_individual& iv, const b200bt_sweep_config& cfg, uint32_t* ev_out) {
+    const double initial_capital = cfg.initial_capital;
+    a.gap_bar = cfg.gap_bar > 0 ? (unsigned)cfg.gap_bar : 0xffffffffu;
+    a.gap_minutes = (unsigned)cfg.gap_minutes;
     a.tp = iv.take_profit; a.sl = iv.stop_loss; a.size = iv.position_size;
     a.fee1 = __dmul_rn(a.size, 0.001); a.fee2 = __dmul_rn(a.size, 0.002);
     a.equity = initial_capital; a.peak = initial_capital; a.maxdd = 0.0;

@@ -186,6 +186,120 @@ class StrategyEvaluationSystem:
                         "quantity": qty, "fees": size * 0.001, "pnl": pnl})
         return out
 
+    # -- k-fold cross-validation (:635-744) -----------------------------------------------------------
+    CV_METRICS = ("sharpe_ratio", "win_rate", "max_drawdown", "profit_factor", "return_pct")
+
+    def cross_validate_population(self, population: List[Dict], close: torch.Tensor, bank: torch.Tensor, periods,
+                                  minute0: int, bar_minutes: int = 1, k_folds: int = 5,
+                                  initial_capital: float = 10000.0) -> Dict[str, np.ndarray]:
+        """The numeric core of cross_validate_strategy for a whole population at once.
+
+        close [S][N] fp32 and bank [S][P][N] (RSI rows for `periods`) are device tensors.  The bars are cut into
+        k contiguous folds (:659-666); for each fold every individual is simulated on the fold ("test") and on
+        the other folds glued together ("train", :674-682 -- the state machine runs straight across the seam,
+        as the reference's does, and the records keep their own calendar days).  Returns arrays [k][pop][S] for
+        the lane metrics `CV_METRICS` and `score`, prefixed train_ / test_."""
+        S, N = close.shape
+        if N < k_folds:
+            k_folds = N
+        fold = N // k_folds
+        bounds = [(i * fold, (i + 1) * fold if i < k_folds - 1 else N) for i in range(k_folds)]
+        out = {f"{side}_{m}": np.zeros((k_folds, len(population), S)) for side in ("train", "test")
+               for m in self.CV_METRICS + ("score", "n_records")}
+
+        def run(side, f, c, bk, m0, gap_bar=0, gap_minutes=0):
+            market = MarketData.from_close(c.contiguous(), minute0=m0, bar_minutes=bar_minutes)
+            sweep = PopulationSweep.from_bank(market, bk.contiguous(), periods, self.optimization_goals,
+                                              initial_capital=initial_capital, mode="auto")
+            sweep.set_gap(gap_bar, gap_minutes)
+            sweep.evaluate(population)
+            st = sweep.lane_stats()
+            for m in ("sharpe_ratio", "win_rate", "max_drawdown", "profit_factor", "score", "n_records"):
+                out[f"{side}_{m}"][f] = st[m]
+            out[f"{side}_return_pct"][f] = st["net_profit"] / initial_capital * 100
+
+        for f, (a, b) in enumerate(bounds):
+            run("test", f, close[:, a:b], bank[:, :, a:b], minute0 + a * bar_minutes)
+            if a == 0 and b == N:
+                continue                                               # k = 1: nothing to train on (:672 gives [])
+            if a == 0:
+                run("train", f, close[:, b:], bank[:, :, b:], minute0 + b * bar_minutes)
+            elif b == N:
+                run("train", f, close[:, :a], bank[:, :, :a], minute0)
+            else:
+                run("train", f, torch.cat([close[:, :a], close[:, b:]], dim=1), torch.cat([bank[:, :, :a], bank[:, :, b:]], dim=2),
+                    minute0, gap_bar=a, gap_minutes=(b - a) * bar_minutes)
+        out["fold_bounds"] = np.array(bounds)
+        return out
+
+    @staticmethod
+    def _summarize_market_conditions(market_data: List[Dict]) -> Dict:
+        """:880-935 (host; a fold's worth of points)."""
+        if not market_data:
+            return {"trend": "unknown", "volatility": 0, "volume": 0, "period_start": None, "period_end": None}
+        prices = [d.get("price", 0) for d in market_data if d.get("price", 0) > 0]
+        volumes = [d.get("volume", 0) for d in market_data if d.get("volume", 0) > 0]
+        trend, volatility = "unknown", 0
+        if len(prices) >= 2:
+            change = (prices[-1] - prices[0]) / prices[0] if prices[0] > 0 else 0
+            trend = "uptrend" if change > 0.05 else "downtrend" if change < -0.05 else "ranging"
+            p = np.asarray(prices, dtype=np.float64)
+            volatility = np.std((p[1:] - p[:-1]) / p[:-1])
+        return {"trend": trend, "volatility": float(volatility), "volume": float(np.mean(volumes) if volumes else 0),
+                "period_start": market_data[0].get("timestamp"), "period_end": market_data[-1].get("timestamp")}
+
+    @staticmethod
+    def _calculate_cv_summary(fold_results: List[Dict], test_metric: str, normalize: bool) -> Dict:
+        """:937-990."""
+        tr = [f["train_score"] for f in fold_results]
+        te = [f["test_score"] for f in fold_results]
+        summary = {"mean_train_score": float(np.mean(tr)), "std_train_score": float(np.std(tr)),
+                   "mean_test_score": float(np.mean(te)), "std_test_score": float(np.std(te)),
+                   "train_test_gap": float(np.mean(tr) - np.mean(te)),
+                   "relative_overfitting": float((np.mean(tr) - np.mean(te)) / np.mean(tr)) if np.mean(tr) > 0 else 0}
+        for side in ("train", "test"):
+            for metric in (fold_results[0][f"{side}_metrics"] if fold_results else {}):
+                vals = [f[f"{side}_metrics"][metric] for f in fold_results]
+                summary[f"mean_{side}_{metric}"] = float(np.mean(vals))
+                summary[f"std_{side}_{metric}"] = float(np.std(vals))
+        summary["consistency"] = (1.0 - min(1.0, summary["std_test_score"] / summary["mean_test_score"])
+                                  if summary["mean_test_score"] > 0 else 0.0)
+        return summary
+
+    def cross_validate_strategy(self, strategy_id: str, parameters: Dict, market_data_periods: List[Dict],
+                                k_folds: int = 5, test_metric: str = "sharpe_ratio",
+                                normalize_results: bool = True) -> Dict:
+        """Drop-in for cross_validate_strategy (:635-744) on a flat list of market-data points (keys timestamp,
+        symbol, price, rsi[, volume]) on a uniform time grid.  JSON dump and plots (:732-739) are out of scope."""
+        pts = market_data_periods
+        if len(pts) < k_folds:
+            k_folds = len(pts)
+        n = len(pts)
+        t0 = datetime.fromisoformat(pts[0]["timestamp"].replace("Z", "+00:00"))
+        minute0 = int((t0.replace(tzinfo=None) - datetime(1970, 1, 1)).total_seconds() // 60)   # calendar days as written (:151)
+        step = 1
+        if n > 1:
+            t1 = datetime.fromisoformat(pts[1]["timestamp"].replace("Z", "+00:00"))
+            step = max(1, int(round((t1 - t0).total_seconds() / 60)))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        close = torch.from_numpy(np.array([d.get("price", 50000) for d in pts], dtype=np.float32)).to(dev).view(1, n)
+        bank = torch.from_numpy(np.array([d.get("rsi", 50) for d in pts], dtype=np.float32)).to(dev).view(1, 1, n)
+        period = int(parameters.get("rsi_period", 14))
+        cv = self.cross_validate_population([dict(parameters)], close, bank, [period], minute0, step, k_folds)
+        fold_results = []
+        for f, (a, b) in enumerate(cv["fold_bounds"].tolist()):
+            block = {}
+            for side in ("train", "test"):
+                m = {k: float(cv[f"{side}_{k}"][f, 0, 0]) for k in self.CV_METRICS}
+                m["test_metric"] = m.get(test_metric, 0)
+                block[f"{side}_metrics"] = m
+                block[f"{side}_score"] = float(cv[f"{side}_score"][f, 0, 0])
+            fold_results.append({"fold": f + 1, **block, "market_conditions": self._summarize_market_conditions(pts[a:b])})
+        return {"strategy_id": strategy_id, "parameters": parameters, "k_folds": len(fold_results),
+                "test_metric": test_metric,
+                "cv_summary": self._calculate_cv_summary(fold_results, test_metric, normalize_results),
+                "fold_results": fold_results, "timestamp": datetime.now().isoformat()}
+
     def _calculate_strategy_score(self, metrics: Dict) -> float:
         goals = self.optimization_goals
         score = metrics.get(goals.get("primary", "sharpe_ratio"), 0)

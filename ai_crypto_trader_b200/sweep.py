@@ -48,6 +48,7 @@ def _f32_down(x: float) -> np.float32:
 
 class MarketData:
     """Device-resident fp32 OHLCV, field-major SoA [5][S][N] (open, high, low, close, volume).
+    `MarketData.from_close(close_dev, ...)` wraps device close prices alone (other fields zero).
 
     Mirrors the role of HistoricalDataManager.market_data_cache
     (backtesting/data_manager.py:218-220): load once, reuse across calls.
@@ -86,6 +87,14 @@ class MarketData:
         self.symbols = list(symbols) if symbols is not None else [f"SYN{i:03d}USDT" for i in range(self.S)]
         self.minute0 = int(minute0)
         self.bar_minutes = int(bar_minutes)
+
+    @classmethod
+    def from_close(cls, close: torch.Tensor, minute0: int = EPOCH_2024_MINUTES, bar_minutes: int = 1,
+                   symbols: Optional[Sequence[str]] = None) -> "MarketData":
+        assert close.is_cuda and close.dtype == torch.float32 and close.dim() == 2
+        ohlcv = torch.zeros((5,) + tuple(close.shape), dtype=torch.float32, device=close.device)
+        ohlcv[3] = close
+        return cls(ohlcv, symbols=symbols, minute0=minute0, bar_minutes=bar_minutes, device=close.device)
 
     def _wait_others(self) -> None:
         if self._others_ready is not None:
@@ -353,7 +362,7 @@ class PopulationSweep:
 
     @classmethod
     def from_bank(cls, market: MarketData, bank: torch.Tensor, periods, optimization_goals=None,
-                  initial_capital: float = 10000.0, event_cap: int = 0) -> "PopulationSweep":
+                  initial_capital: float = 10000.0, event_cap: int = 0, mode: str = "fused") -> "PopulationSweep":
         """Sweep over a caller-supplied RSI bank [S][P][N] (e.g. the 'rsi' field of the reference's
         market-data points) instead of one computed from the close prices."""
         self = cls.__new__(cls)
@@ -368,7 +377,7 @@ class PopulationSweep:
         self.event_cap = int(event_cap)
         assert bank.is_cuda and bank.dtype == torch.float32 and tuple(bank.shape) == (market.S, len(self.periods), market.N)
         self.bank = bank.contiguous()
-        self.mode, self.chunk_min_bars, self.chunk_options = "fused", 131072, {}
+        self.mode, self.chunk_min_bars, self.chunk_options = mode, 131072, {}
         self._stats = self._events = None
         self._pop = 0
         self._pinned_in = self._pinned_out = None
@@ -459,6 +468,11 @@ class PopulationSweep:
                 _lib.call("b200bt_sweep", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
                           len(self.periods), m.S, m.N, indiv_dev.data_ptr(), redo.data_ptr(), int(redo.numel()),
                           C.byref(self.cfg), self._stats.data_ptr(), _lib.ptr(self._events), self.event_cap, st)
+
+    def set_gap(self, gap_bar: int, gap_minutes: int) -> None:
+        """Declare the series as two pieces glued at `gap_bar`, the second one `gap_minutes` later on the calendar
+        (training folds of cross_validate_strategy): only the daily buckets of the metrics see it."""
+        self.cfg.gap_bar, self.cfg.gap_minutes = int(gap_bar), int(gap_minutes)
 
     def zone_map(self) -> torch.Tensor:
         """(min, max) per 32-bar block of the price rows and of the RSI bank (b200bt_zone_map), built on first use."""

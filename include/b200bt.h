@@ -193,7 +193,9 @@ typedef struct b200bt_sweep_config {
     int32_t primary;         /* B200BT_PRIMARY_*                              */
     int32_t secondary_mask;  /* B200BT_SEC_* bits                             */
     int32_t variant;         /* kernel variant selector, 0 = default          */
-} b200bt_sweep_config;
+    int32_t gap_bar;         /* > 0: the series is two pieces glued at this bar (training folds of            */
+    int32_t gap_minutes;     /*      cross_validate_strategy :674-682): bars >= gap_bar lie gap_minutes later  */
+} b200bt_sweep_config;   /* 40 bytes */
 
 /* Event word written to the optional trade buffer: bits 0..29 bar index,
  * bit 30 = 1 for an exit record, bit 31 = 1 for side "sell"

@@ -35,6 +35,8 @@ typedef struct {
     int32_t primary;        /* 0 sharpe, 1 return_pct, 2 profit_factor, 3 win_rate, 4 net_profit */
     int32_t secondary_mask; /* 1 max_drawdown, 2 win_rate, 4 profit_factor */
     int32_t reserved;
+    int32_t gap_bar;        /* > 0: bars >= gap_bar carry timestamps gap_minutes later (glued training folds) */
+    int32_t gap_minutes;
 } oracle_config;
 
 typedef struct {
@@ -112,7 +114,8 @@ static void record(acc_t* a, int64_t bar, uint32_t flags, double pnl) {
         if (!a->have_dd || dd > a->maxdd) a->maxdd = dd;
         a->have_dd = 1;
     }
-    int64_t day = (a->cfg->minute0 + bar * (int64_t)a->cfg->bar_minutes) / 1440;
+    int64_t day = (a->cfg->minute0 + bar * (int64_t)a->cfg->bar_minutes +
+                   ((a->cfg->gap_bar > 0 && bar >= a->cfg->gap_bar) ? a->cfg->gap_minutes : 0)) / 1440;
     if (a->day_open && day == a->cur_day) {
         a->day_sum += pnl;
     } else {

@@ -19,7 +19,8 @@ class Params(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("initial_capital", C.c_double), ("minute0", C.c_int64), ("bar_minutes", C.c_int32),
-                ("primary", C.c_int32), ("secondary_mask", C.c_int32), ("reserved", C.c_int32)]
+                ("primary", C.c_int32), ("secondary_mask", C.c_int32), ("reserved", C.c_int32),
+                ("gap_bar", C.c_int32), ("gap_minutes", C.c_int32)]
 
 
 STATS_FIELDS = ("n_records", "n_wins", "n_losses", "total_profit", "total_loss", "net_profit", "max_drawdown",
@@ -61,11 +62,12 @@ def params_of(p: dict) -> Params:
                   10000 * (min(p.get("max_position_size", 5), 20) / 100))
 
 
-def config_of(minute0: int, bar_minutes: int = 1, goals: dict | None = None, initial_capital: float = 10000.0) -> Config:
+def config_of(minute0: int, bar_minutes: int = 1, goals: dict | None = None, initial_capital: float = 10000.0,
+              gap_bar: int = 0, gap_minutes: int = 0) -> Config:
     goals = goals or {"primary": "sharpe_ratio", "secondary": ["max_drawdown", "win_rate", "profit_factor"]}
     prim = {"sharpe_ratio": 0, "return_pct": 1, "profit_factor": 2, "win_rate": 3, "net_profit": 4}[goals.get("primary", "sharpe_ratio")]
     sec = sum({"max_drawdown": 1, "win_rate": 2, "profit_factor": 4}.get(m, 0) for m in goals.get("secondary", []))
-    return Config(float(initial_capital), int(minute0), int(bar_minutes), prim, sec, 0)
+    return Config(float(initial_capital), int(minute0), int(bar_minutes), prim, sec, 0, int(gap_bar), int(gap_minutes))
 
 
 def lane(price32: np.ndarray, rsi32: np.ndarray, p: dict, cfg: Config, event_cap: int = 0):

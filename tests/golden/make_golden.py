@@ -11,6 +11,7 @@ Writes (all small, committed):
     tests/golden/mc_reference.*   MonteCarloService results + its own paths (NumPy seed fixed)
     tests/golden/bt_reference.*   StrategyTester.backtest_strategy runs (LLM stubbed, `ta` shimmed)
     tests/golden/pf_reference.json PortfolioRiskService VaR / CVaR / correlation / portfolio VaR
+    tests/golden/cv_reference.json StrategyEvaluationSystem.cross_validate_strategy on flat data points
 Inputs are the fp32 synthetic series of ai_crypto_trader_b200.synth; the RSI
 bank is oracle.indicators_ref.rsi_bank (float64 pandas, rounded to fp32).
 The reference functions executed are
@@ -287,8 +288,40 @@ def make_pf():
     print("PF: var95", out["var"]["0.95"][:3], "corr01", out["correlation"][0][1], "pvar", out["portfolio_var"])
 
 
+CV_BARS, CV_SYMBOL, CV_FOLDS = 30000, 2, 5
+CV_CASES = [
+    ("cv_typical", {"rsi_period": 14, "rsi_overbought": 70, "rsi_oversold": 30, "take_profit": 3, "stop_loss": 2}),
+    ("cv_fast", {"rsi_period": 6, "rsi_overbought": 66, "rsi_oversold": 34, "take_profit": 1, "stop_loss": 1}),
+    ("cv_holder", {"rsi_period": 21, "rsi_overbought": 80, "rsi_oversold": 20, "take_profit": 10, "stop_loss": 5}),
+]
+
+
+def make_cv():
+    """Reference StrategyEvaluationSystem.cross_validate_strategy (services/strategy_evaluation.py:635-744) on a
+    FLAT list of market-data points (what its type hint says; with its own caller's list of periods it raises).
+    The plotting hook (:739) is switched off on the instance; nothing else is touched."""
+    ses, _ = ref_runner.strategy_evaluation()
+    ses._visualize_cv_results = lambda results: None
+    d = synth.synth_symbol(CV_SYMBOL, CV_BARS)
+    out = {"n_bars": CV_BARS, "symbol": CV_SYMBOL, "k_folds": CV_FOLDS, "minute0": synth.EPOCH_2024_MINUTES, "cases": []}
+    for name, params in CV_CASES:
+        rsi = indicators_ref.rsi_bank(d["close"], [params["rsi_period"]])[0]
+        pts = simulate_ref.market_points(d["close"], rsi, f"SYN{CV_SYMBOL:03d}USDT", synth.EPOCH_2024_MINUTES)
+        for p, v in zip(pts, d["volume"]):
+            p["volume"] = float(v)
+        res = ses.cross_validate_strategy(name, dict(params), pts, k_folds=CV_FOLDS)          # REFERENCE
+        folds = [{k: (v if k == "market_conditions" else
+                      ({m: jsonable(x) for m, x in v.items()} if isinstance(v, dict) else jsonable(v)))
+                  for k, v in f.items()} for f in res["fold_results"]]
+        out["cases"].append({"name": name, "params": params, "fold_results": folds,
+                             "cv_summary": {k: jsonable(v) for k, v in res["cv_summary"].items()}})
+        print(f"CV {name}: mean_test_score={res['cv_summary']['mean_test_score']:.6g} "
+              f"mean_train_score={res['cv_summary']['mean_train_score']:.6g}")
+    (OUT / "cv_reference.json").write_text(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sim", "ga", "mc", "bt", "pf"]
+    which = sys.argv[1:] or ["sim", "ga", "mc", "bt", "pf", "cv"]
     if "sim" in which:
         make_sim()
     if "ga" in which:
@@ -299,3 +332,5 @@ if __name__ == "__main__":
         make_bt()
     if "pf" in which:
         make_pf()
+    if "cv" in which:
+        make_cv()

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(native_lib):
 def test_struct_layouts_match_header(native_lib):
     from ai_crypto_trader_b200 import _lib
     assert C.sizeof(_lib.Individual) == 40
-    assert C.sizeof(_lib.SweepConfig) == 32
+    assert C.sizeof(_lib.SweepConfig) == 40
     assert len(_lib.LANE_STATS_FIELDS) * 8 == 160
 
 

@@ -83,3 +83,22 @@ def test_c_oracle_event_cap_and_hash_are_consistent(sim_golden):
     st_b, ev_b, _ = sim_oracle.lane(close, rsi, case["params"], cfg, event_cap=4096)
     assert st_a["trade_hash"] == st_b["trade_hash"] != 0
     assert len(ev_a) == 16 and np.array_equal(ev_a, ev_b[:16])
+
+
+def test_c_oracle_calendar_gap_matches_python_restatement(sim_golden):
+    """A series glued from two pieces (training folds of the cross-validation): the C oracle with gap_bar / gap_minutes
+    equals the Python restatement fed the glued points with their own timestamps."""
+    meta, arrays = sim_golden
+    case = next(c for c in meta["cases"] if c["name"] == "fast_rsi_tight")
+    close, rsi = _case_inputs(meta, arrays, case)
+    a, b = 1500, 4400                       # cut [a, b) out: the seam jumps ~2 days
+    pts = simulate_ref.market_points(close, rsi, "X", meta["minute0"])
+    glued = pts[:a] + pts[b:]
+    recs = simulate_ref.simulate_trades(dict(case["params"]), glued)
+    m = simulate_ref.calculate_metrics(recs)
+    cfg = sim_oracle.config_of(meta["minute0"], 1, meta["goals"], gap_bar=a, gap_minutes=b - a)
+    st, _, _ = sim_oracle.lane(np.concatenate([close[:a], close[b:]]), np.concatenate([rsi[:a], rsi[b:]]), case["params"], cfg)
+    assert int(st["n_records"]) == len(recs)
+    assert int(st["n_days"]) == len(m["daily_returns"])
+    assert st["sharpe_ratio"] == pytest.approx(float(m["sharpe_ratio"]), rel=1e-10)
+    assert st["score"] == pytest.approx(float(simulate_ref.strategy_score(m, meta["goals"])), rel=1e-10)
