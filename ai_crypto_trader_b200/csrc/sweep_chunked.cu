@@ -9,8 +9,14 @@
 // bars early in the flat state without recording, and records from T_c on.  Two trajectories that
 // are ever flat at the same bar coincide from then on, so after the warm-up the chunk's assumed
 // state (position side + entry bar) is almost always the true one.  It is VERIFIED, not trusted:
-//   scan kernel     one warp per (individual, symbol, chunk): events -> blocks of a global pool
-//                   (bump allocator, singly linked per chunk), assumed state at T_c and end state.
+//   scan kernels    chunk_scan_kernel: one WARP per (individual, symbol, chunk) of the expensive lanes
+//                   (b200bt_sweep_chunked), or lane_scan_kernel: every lane cut into the same K chunks and one
+//                   THREAD per (individual, symbol, chunk) (b200bt_sweep_tiled, see "thread-per-lane scan").
+//                   Events -> blocks of a global pool (bump allocator, singly linked per chunk), plus the
+//                   chunk's assumed state at T_c and its end state.
+//   verify / repair chunk_verify_kernel lists chunks whose assumed state differs from the predecessor's end state;
+//                   chunk_scan_kernel<REPAIR> re-scans them from the true state.  The first rounds are on the
+//                   critical path, later ones run on a side stream beside the metrics kernels (finish_chunks).
 //   metrics kernels one warp per (individual, symbol, chunk) again (see "metrics, chunk-parallel" below), then
 //                   one thread per (individual, symbol) checks end state of chunk c-1 == assumed state
 //                   of chunk c for every boundary and merges the chunks' partial metrics.
@@ -745,8 +751,7 @@ chunk_partial_kernel(const float* __restrict__ price, int64_t ld_price, const b2
             const int d_after = __shfl_down_sync(FULL, d0, 1);
             const bool tail0 = a0 && (a1 ? head1 : false);
             const bool tail1 = a1 && lane < last_lane && d_after != d1;
-            const bool tail0_odd = a0 && !a1 && false;              // an unpaired last record is the step's last: open
-            (void)tail0_odd;
+            // (an unpaired last record 2l is the step's last record: its day stays open)
             unsigned t0m = __ballot_sync(FULL, tail0), t1m = __ballot_sync(FULL, tail1);
             if (day_valid && !merge_carry) finish_day(day_cur, day_sum);
             while (t0m | t1m) {
