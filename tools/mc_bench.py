@@ -23,7 +23,6 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     a = ap.parse_args()
     from ai_crypto_trader_b200.monte_carlo import PathEngine, risk_statistics
-    from oracle import mc_ref
     eng = PathEngine()
     mu, sigma = 0.08, 0.35            # annualised drift / volatility; horizon = steps/252 years at dt = 1/252
     def timed(fn, reps):
