@@ -553,6 +553,8 @@ class PopulationSweep:
     def evaluate(self, population: List[Dict]) -> np.ndarray:
         """fitness (float64[pop]) of a list of parameter dicts; H2D of the decoded
         population and D2H of the fitness vector happen inside this call."""
+        if not population:
+            return np.zeros(0, dtype=np.float64)
         dev = self.market.device
         packed = decode_population(population, self.period_row)
         # individuals that decode to the same kernel parameters (the reference rule reads 6 of the 18 genes,

@@ -316,3 +316,22 @@ def test_tiled_sweep_is_exact_and_self_repairing(torch_cuda, n_bars, opts):
     np.testing.assert_array_equal(ev_t[live], ev_f[live])
     np.testing.assert_allclose(f_t, f_f, rtol=1e-9, atol=1e-11)
     _check_lanes_vs_oracle(tiled, population[:24], ohlcv, cap)
+
+
+def test_evaluate_edge_populations(torch_cuda):
+    """Empty population, one individual, one symbol, a series shorter than one tile -- through the default mode."""
+    from ai_crypto_trader_b200 import synth
+    from ai_crypto_trader_b200.sweep import MarketData, PopulationSweep
+    from oracle import indicators_ref, sim_oracle
+    for n_bars in (7, 200_001):
+        ohlcv = synth.synth_ohlcv(1, n_bars, first_symbol=6)
+        market = MarketData(ohlcv)
+        sweep = PopulationSweep(market)
+        assert sweep.evaluate([]).shape == (0,)
+        one = synth.random_population(1, seed=n_bars)
+        f = sweep.evaluate(one)
+        bank = indicators_ref.rsi_bank(ohlcv[3, 0], sweep.periods)
+        want, _, _ = sim_oracle.lane(ohlcv[3, 0], bank[sweep.period_row[one[0]["rsi_period"]]], one[0],
+                                     sim_oracle.config_of(market.minute0, 1))
+        assert f.shape == (1,) and f[0] == pytest.approx(float(want["score"]), rel=1e-9, abs=1e-12)
+        assert int(sweep.lane_stats()["n_records"][0, 0]) == int(want["n_records"])
