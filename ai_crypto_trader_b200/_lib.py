@@ -109,6 +109,11 @@ _SIGNATURES = {
     "b200bt_select_workspace_bytes": (C.c_int64, [_i]),
     "b200bt_select": (C.c_int, [_vp, _i64, _vp, _i, _vp, _vp, _i64, _vp]),
     "b200bt_mc_moments": (C.c_int, [_vp, _vp, _i64, C.c_double, C.c_double, _vp, _vp]),
+    "b200bt_ga_init": (C.c_int, [_vp, _i, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                 C.c_uint64, _vp]),
+    "b200bt_ga_next_generation": (C.c_int, [_vp, _vp, _vp, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                            C.POINTER(C.c_int), C.c_double, _i, C.c_double, C.c_double, C.c_uint64,
+                                            C.c_uint32, _vp, _vp, _vp]),
     "b200bt_pct_change": (C.c_int, [_vp, _i64, _i, _i64, _vp, _i64, _vp]),
     "b200bt_tail_stats_workspace_bytes": (C.c_int64, [_i64]),
     "b200bt_tail_stats": (C.c_int, [_vp, _i64, C.c_double, _vp, _vp, _i64, _vp]),

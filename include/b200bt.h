@@ -367,6 +367,28 @@ int64_t b200bt_correlation_workspace_bytes(int S, int64_t N);
 int b200bt_correlation(const float* x, int64_t ld, int S, int64_t N, double* out, void* workspace,
                        int64_t workspace_bytes, b200bt_stream_t stream);
 
+/* ---- GA operators on the device -------------------------------------------------------
+ * The operators of services/genetic_algorithm.py:83-252 over a device matrix params [pop][genes] float64 (integer
+ * genes hold integral values).  Ranges: host arrays lo / hi / is_int of length genes (<= 64).  Randomness is
+ * Philox4x32-10 keyed by (seed; generation, slot): parity with the reference's Mersenne-twister stream is
+ * DISTRIBUTIONAL (same operators and probabilities), results are a pure function of (seed, generation, inputs). */
+
+/* initialize_population (:83-117): rows >= n_seeded are drawn uniformly from the ranges (randint / uniform),
+ * rows < n_seeded (already written by the caller) are clamped to the ranges. */
+int b200bt_ga_init(double* params, int pop, int genes, int n_seeded, const double* lo, const double* hi,
+                   const int* is_int, uint64_t seed, b200bt_stream_t stream);
+
+/* selection + crossover + mutation (:135-252) -> params_out (must not alias params).
+ * ranked: device int32[pop], indices by descending fitness (stable); selected_workspace: device int32[pop].
+ * elites = max(1, int(elitism_pct * pop)) best, copied unchanged to the first rows; every other selected slot is the
+ * winner of a tournament of `tournament` (<= 8) distinct contenders; offspring pairs come from two uniform draws
+ * of the selected list, uniform crossover with probability crossover_rate, per-gene mutation with mutation_rate. */
+int b200bt_ga_next_generation(const double* params, const double* fitness, const int32_t* ranked, int pop, int genes,
+                              const double* lo, const double* hi, const int* is_int, double elitism_pct,
+                              int tournament, double crossover_rate, double mutation_rate, uint64_t seed,
+                              uint32_t generation, int32_t* selected_workspace, double* params_out,
+                              b200bt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import numpy as np, torch
 from ai_crypto_trader_b200 import synth
 from ai_crypto_trader_b200.dist import ShardedFitness
-from ai_crypto_trader_b200.genetic_algorithm import GeneticAlgorithm
+from ai_crypto_trader_b200.genetic_algorithm import DeviceGeneticAlgorithm, GeneticAlgorithm
 from ai_crypto_trader_b200.sweep import MarketData, PopulationSweep
 
 ap = argparse.ArgumentParser()
@@ -22,6 +22,7 @@ ap.add_argument("--symbols", type=int, default=50)
 ap.add_argument("--bars", type=int, default=1_000_000)
 ap.add_argument("--generations", type=int, default=3)
 ap.add_argument("--mode", default="auto")
+ap.add_argument("--device-ga", action="store_true", help="GA operators on the GPU (DeviceGeneticAlgorithm)")
 a = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", 1)); rank = int(os.environ.get("RANK", 0))
@@ -47,7 +48,10 @@ def batch(population):
     return out
 def one(ind): return batch([ind])[0]
 one.batch = batch
-ga = GeneticAlgorithm(synth.param_ranges(False), one, population_size=a.pop, generations=a.generations, random_seed=42)
+if a.device_ga:
+    ga = DeviceGeneticAlgorithm(synth.param_ranges(False), batch, population_size=a.pop, generations=a.generations, random_seed=42)
+else:
+    ga = GeneticAlgorithm(synth.param_ranges(False), one, population_size=a.pop, generations=a.generations, random_seed=42)
 w = time.perf_counter()
 best = ga.run()
 total = time.perf_counter() - w
@@ -61,6 +65,7 @@ if rank == 0:
                       "bar_strategy_evals_per_generation": a.pop * a.symbols * a.bars,
                       "evals_per_s_in_sweep": a.pop * a.symbols * a.bars / (np.median(dev) * 1e-3),
                       "setup_s": {"synthetic_data": t1 - t0, "upload_and_rsi_bank": t2 - t1},
-                      "per_evaluation": diag, "best_fitness": ga.best_fitness, "mode": a.mode}))
+                      "per_evaluation": diag, "best_fitness": ga.best_fitness, "mode": a.mode,
+                      "ga_operators": "device (csrc/ga_ops.cu)" if a.device_ga else "host (reference random stream)"}))
 if world > 1:
     torch.distributed.destroy_process_group()
