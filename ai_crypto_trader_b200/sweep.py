@@ -83,7 +83,8 @@ class MarketData:
                 for f in (0, 1, 2, 4):
                     self._ohlcv[f].copy_(host[f], non_blocking=True)
                 self._others_ready = side.record_event()
-            self._ohlcv.record_stream(side)
+            # (no record_stream: it would keep the allocator from reusing this block for the next MarketData and cost a
+            # cudaMalloc per upload; __del__ orders the release after the side-stream copies instead)
         self.symbols = list(symbols) if symbols is not None else [f"SYN{i:03d}USDT" for i in range(self.S)]
         self.minute0 = int(minute0)
         self.bar_minutes = int(bar_minutes)
@@ -95,6 +96,12 @@ class MarketData:
         ohlcv = torch.zeros((5,) + tuple(close.shape), dtype=torch.float32, device=close.device)
         ohlcv[3] = close
         return cls(ohlcv, symbols=symbols, minute0=minute0, bar_minutes=bar_minutes, device=close.device)
+
+    def __del__(self):
+        try:
+            self._wait_others()      # the block returns to the allocator on the current stream: after the copies
+        except Exception:
+            pass
 
     def _wait_others(self) -> None:
         if self._others_ready is not None:
@@ -212,6 +219,25 @@ def lane_costs(population: List[Dict]) -> np.ndarray:
     return ndtr((g("rsi_oversold", 30) - 50.0) / sd) + 1.0 - ndtr((g("rsi_overbought", 70) - 50.0) / sd)
 
 
+def costs_from_packed(packed: np.ndarray, periods: Sequence[int]) -> np.ndarray:
+    """lane_cost of already decoded individuals (b200bt_individual records): no second pass over the dicts."""
+    from scipy.special import ndtr
+    w = np.asarray(periods, dtype=np.float64)[packed["rsi_row"]]
+    sd = 44.0 / np.sqrt(np.maximum(w, 1.0))
+    return ndtr((packed["rsi_lo"].astype(np.float64) - 50.0) / sd) + 1.0 - ndtr((packed["rsi_hi"].astype(np.float64) - 50.0) / sd)
+
+
+_SM_COUNT: Dict[int, int] = {}
+
+
+def _sm_count(device) -> int:
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
 _PINNED_FLAG = None
 DEFERRED = torch.empty(0, dtype=torch.uint8)      # sentinel: the caller assigns plan.workspace (plan_batches)
 
@@ -230,18 +256,20 @@ class ChunkPlan:
 
     def __init__(self, population: List[Dict], n_bars: int, n_symbols: int, device, target_events: int = 16384,
                  warm: int = 8192, max_chunks: int = 64, pool_scale: float = 1.5, pool_blocks: Optional[int] = None,
-                 max_repair_rounds: int = 8, lo: int = 0, workspace: Optional[torch.Tensor] = None):
+                 max_repair_rounds: int = 8, lo: int = 0, workspace: Optional[torch.Tensor] = None,
+                 pred: Optional[np.ndarray] = None):
         """`population` is the slice [lo, lo + len) of the caller's population (individual indices inside the
-        plan are slice-relative); `workspace` may be shared between the plans of successive slices."""
+        plan are slice-relative); `workspace` may be shared between the plans of successive slices; `pred` =
+        predicted_events(population, n_bars) when the caller already has it."""
         pop = len(population)
         self.lo = int(lo)
-        pred = predicted_events(population, n_bars)
+        pred = predicted_events(population, n_bars) if pred is None else np.asarray(pred, dtype=np.float64)
         kmax = max(1, min(max_chunks, n_bars // max(8 * warm, 2048)))
         k = np.clip(np.ceil(pred / target_events), 1, kmax).astype(np.int32)
         self.n_chunks = k
         self.seg_base = np.concatenate([[0], np.cumsum(k)[:-1]]).astype(np.int32)
         self.n_seg = int(k.sum())
-        self.order = evaluation_order(population)
+        self.order = np.argsort(-pred, kind="stable").astype(np.int32)      # (b200bt_sweep_chunked ignores it)
         items = np.zeros((self.n_seg, 4), dtype=np.int32)
         # most expensive work first (per-chunk cost), keeping one individual's chunks together
         per_chunk = pred / k
@@ -281,14 +309,14 @@ class TilePlan:
         """About 1.75 resident sets of CTAs (measured optimum on the C2 workload, flat from 1.6 to 1.9: heavy CTAs
         run longer, so whole "waves" do not exist), chunks at least 4 warm-ups long."""
         kmax = max(1, min(max_chunks, n_bars // max(4 * warm, 2048)))
-        slots = torch.cuda.get_device_properties(device).multi_processor_count * cls.CTAS_PER_SM
+        slots = _sm_count(device) * cls.CTAS_PER_SM
         groups = -(-pop // cls.THREADS) * n_symbols
         return min(kmax, max(1, round(1.75 * slots / groups)))
 
     def __init__(self, population: List[Dict], n_bars: int, n_symbols: int, device, warm: int = 8192,
                  max_chunks: int = 64, chunks: Optional[int] = None, pool_scale: float = 1.5,
                  pool_blocks: Optional[int] = None, max_repair_rounds: Optional[int] = None, lo: int = 0,
-                 workspace: Optional[torch.Tensor] = None, order_by: str = "cost"):
+                 workspace: Optional[torch.Tensor] = None, order_by: str = "cost", pred: Optional[np.ndarray] = None):
         pop = len(population)
         self.lo, self.pop = int(lo), pop
         self.warm = int(warm)
@@ -298,7 +326,7 @@ class TilePlan:
         # a lane that holds one position across many chunks needs one repair round per boundary
         self.max_repair_rounds = int(max_repair_rounds) if max_repair_rounds is not None else min(self.K, 24)
         self.n_seg = pop * self.K
-        pred = predicted_events(population, n_bars)
+        pred = predicted_events(population, n_bars) if pred is None else np.asarray(pred, dtype=np.float64)
         # threads of a CTA wait for each other at every tile: neighbours should cost the same ("cost"), which
         # matters more than sharing RSI rows ("period": the fused kernel's order)
         self.order = (np.argsort(-pred, kind="stable").astype(np.int32) if order_by == "cost"
@@ -496,9 +524,10 @@ class PopulationSweep:
             return None
         return self.zone_map()
 
-    def plan(self, population: List[Dict]) -> Optional[List]:
+    def plan(self, population: List[Dict], pred: Optional[np.ndarray] = None) -> Optional[List]:
         """The kernel path `evaluate` takes for this population under self.mode: None = fused kernel, else the
-        list of TilePlan / ChunkPlan slices to pass to evaluate_device(plan=...)."""
+        list of TilePlan / ChunkPlan slices to pass to evaluate_device(plan=...).  `pred`: predicted_events of the
+        population when the caller already has it (evaluate derives it from the decoded records)."""
         long_enough = self.market.N >= self.chunk_min_bars
         tiled = self.mode == "tiled"
         if self.mode == "auto" and long_enough and len(self.periods) <= TILED_MAX_PERIODS:
@@ -515,7 +544,7 @@ class PopulationSweep:
         if getattr(self, "last_pool_overflow", False):      # the previous sweep ran out of event pool: plan larger
             options["pool_scale"] = 4.0 * options.get("pool_scale", 1.5)
             options.pop("pool_blocks", None)
-        return self.plan_batches(population, tiled=tiled, **options)
+        return self.plan_batches(population, tiled=tiled, pred=pred, **options)
 
     def plan_tiles(self, population: List[Dict], **kw) -> "TilePlan":
         return TilePlan(population, self.market.N, self.market.S, self.market.device, **kw)
@@ -523,27 +552,30 @@ class PopulationSweep:
     def plan_chunks(self, population: List[Dict], **kw) -> "ChunkPlan":
         return ChunkPlan(population, self.market.N, self.market.S, self.market.device, **kw)
 
-    def plan_batches(self, population: List[Dict], max_pool_bytes: int = 8 << 30, tiled: bool = False, **kw) -> List:
+    def plan_batches(self, population: List[Dict], max_pool_bytes: int = 8 << 30, tiled: bool = False,
+                     pred: Optional[np.ndarray] = None, **kw) -> List:
         """Plans for contiguous slices of the population whose event pools each stay below `max_pool_bytes`
         and share one workspace: large populations (BASELINE configs[4]: 10 000 x 50 symbols) record more
         events than fit in HBM at once, so they go through the chunked kernels slice by slice."""
         cls = TilePlan if tiled else ChunkPlan
         accepted = inspect.signature(cls.__init__).parameters     # chunk_options may carry the other path's knobs
         kw = {k: v for k, v in kw.items() if k in accepted}
+        if pred is None:
+            pred = predicted_events(population, self.market.N)
         if kw.get("pool_blocks") is not None:
-            return [cls(population, self.market.N, self.market.S, self.market.device, **kw)]
-        pred = predicted_events(population, self.market.N) * self.market.S * 8 * kw.get("pool_scale", 1.5)
+            return [cls(population, self.market.N, self.market.S, self.market.device, pred=pred, **kw)]
+        pool_bytes = pred * (self.market.S * 8 * kw.get("pool_scale", 1.5))
+        if float(pool_bytes.sum()) <= max_pool_bytes:
+            return [cls(population, self.market.N, self.market.S, self.market.device, pred=pred, **kw)]
         cuts, acc = [0], 0.0
-        for i, b in enumerate(pred):
+        for i, b in enumerate(pool_bytes):
             if acc + b > max_pool_bytes and i > cuts[-1]:
                 cuts.append(i)
                 acc = 0.0
             acc += b
         cuts.append(len(population))
-        if len(cuts) == 2:
-            return [cls(population, self.market.N, self.market.S, self.market.device, **kw)]
-        plans = [cls(population[lo:hi], self.market.N, self.market.S, self.market.device, lo=lo, workspace=DEFERRED, **kw)
-                 for lo, hi in zip(cuts[:-1], cuts[1:])]
+        plans = [cls(population[lo:hi], self.market.N, self.market.S, self.market.device, lo=lo, workspace=DEFERRED,
+                     pred=pred[lo:hi], **kw) for lo, hi in zip(cuts[:-1], cuts[1:])]
         shared = torch.empty(max(pl.ws_bytes for pl in plans), dtype=torch.uint8, device=self.market.device)
         for pl in plans:
             pl.workspace = shared        # the slices run one after the other on the same stream
@@ -570,7 +602,12 @@ class PopulationSweep:
             population = [population[i] for i in keep]
         self.last_unique = len(population)
         pop = len(population)
-        order = evaluation_order(population)
+        pred = EVENTS_PER_COST_BAR * costs_from_packed(packed, self.periods) * self.market.N
+        plan = self.plan(population, pred=pred)
+        if plan is None:       # the fused kernel dispatches in this order: same RSI period adjacent, most expensive first
+            order = np.lexsort((np.arange(pop), -pred, packed["rsi_row"])).astype(np.int32)
+        else:
+            order = np.zeros(0, dtype=np.int32)
         nbytes = packed.nbytes
         if self._pinned_in is None or self._pinned_in.numel() < nbytes + order.nbytes:
             self._pinned_in = torch.empty(nbytes + order.nbytes, dtype=torch.uint8, pin_memory=True)
@@ -581,9 +618,8 @@ class PopulationSweep:
         hin[nbytes:nbytes + order.nbytes] = order.view(np.uint8)
         staged = self._pinned_in[:nbytes + order.nbytes].to(dev, non_blocking=True)
         indiv_dev = staged[:nbytes]
-        order_dev = staged[nbytes:].view(torch.int32)
+        order_dev = staged[nbytes:].view(torch.int32) if order.size else None
         fit = torch.empty(pop, dtype=torch.float64, device=dev)
-        plan = self.plan(population)
         self.evaluate_device(indiv_dev, order_dev, pop, fit, plan=plan)
         self._inverse = expand
         out = self._pinned_out[:pop]
