@@ -1,7 +1,8 @@
 """Population-fitness sweep: the GA hot path on the GPU.
 
-Host side of `b200bt_sweep` (include/b200bt.h).  For every (individual, symbol)
-lane it evaluates what the reference evaluates serially in Python:
+Host side of `b200bt_sweep`, `b200bt_sweep_chunked` and `b200bt_sweep_tiled` (include/b200bt.h): three schedules of
+the same computation, chosen by `PopulationSweep.plan`.  For every (individual, symbol) lane they evaluate what the
+reference evaluates serially in Python:
 
     trades  = StrategyEvaluationSystem._simulate_trades(id, params, bars)   strategy_evaluation.py:746
     metrics = StrategyPerformanceMetrics.calculate_metrics(trades)          :32
