@@ -61,3 +61,23 @@ class ShardedFitness:
 
     def __call__(self, individual: Dict) -> float:
         return float(self.evaluate_local([individual])[0])
+
+
+def gather_paths(local_finals: torch.Tensor, local_maxdd: torch.Tensor, n_total: int, group=None):
+    """All-gather the per-rank shards of a Monte-Carlo run (paths sharded contiguously by shard_bounds, the kernels
+    keyed by the GLOBAL path index, so the gathered arrays equal a single-GPU run bit for bit).  One collective of
+    8 bytes per path; every rank then holds all finals / drawdowns and computes the same order statistics."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local_finals, local_maxdd
+    world = dist.get_world_size(group)
+    per = -(-n_total // world)
+    send = torch.full((2 * per,), float("nan"), dtype=torch.float32, device=local_finals.device)
+    send[:local_finals.numel()] = local_finals
+    send[per:per + local_maxdd.numel()] = local_maxdd
+    recv = torch.empty((world * 2 * per,), dtype=torch.float32, device=local_finals.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.view(world, 2, per)
+    counts = [shard_bounds(n_total, world, r)[1] - shard_bounds(n_total, world, r)[0] for r in range(world)]
+    finals = torch.cat([recv[r, 0, :counts[r]] for r in range(world)])
+    maxdd = torch.cat([recv[r, 1, :counts[r]] for r in range(world)])
+    return finals, maxdd

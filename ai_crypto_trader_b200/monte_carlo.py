@@ -77,6 +77,9 @@ class PathEngine:
 
     def gbm(self, s0, mu, sigma, dt, n_paths, steps, seed, path_offset=0, store_paths=False):
         dev = self.device
+        if n_paths == 0:          # a rank without paths (more ranks than paths)
+            e = torch.empty(0, dtype=torch.float32, device=dev)
+            return e, e.clone(), None
         finals = torch.empty(n_paths, dtype=torch.float32, device=dev)
         maxdd = torch.empty(n_paths, dtype=torch.float32, device=dev)
         paths = torch.empty((steps + 1, n_paths), dtype=torch.float32, device=dev) if store_paths else None
@@ -209,16 +212,25 @@ class MonteCarloService:
             seed = self.seed + self._sim_counter
             self._sim_counter += 1
             eng = self.engine
+            # under torch.distributed the paths are sharded over the ranks (Philox is keyed by the global path index:
+            # the result does not depend on the number of GPUs) and gathered once for the statistics
+            from .dist import gather_paths, shard_bounds
+            world, rank = 1, 0
+            if torch.distributed.is_available() and torch.distributed.is_initialized() and not store:
+                world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+            lo, hi, _ = shard_bounds(int(num_simulations), world, rank)
             if method == "geometric_brownian_motion":
-                finals, maxdd, paths = eng.gbm(initial_price, mu, sigma, dt, num_simulations, steps, seed,
+                finals, maxdd, paths = eng.gbm(initial_price, mu, sigma, dt, hi - lo, steps, seed, path_offset=lo,
                                                store_paths=store)
             elif method == "historical":
                 finals, maxdd, paths = eng.bootstrap(returns.to_numpy(), self.mc_params["return_method"] == "log",
-                                                     initial_price, num_simulations, steps, seed,
+                                                     initial_price, hi - lo, steps, seed, path_offset=lo,
                                                      block_len=self.block_len, store_paths=store)
             else:
                 logger.error("Unknown simulation method: %s", method)
                 return {}
+            if world > 1:
+                finals, maxdd = gather_paths(finals, maxdd, int(num_simulations))
             st = risk_statistics(eng, finals, maxdd, initial_price, self.mc_params["confidence_level"])
             results = {
                 "symbol": symbol, "initial_price": initial_price, "time_horizon_days": days,

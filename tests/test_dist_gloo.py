@@ -34,6 +34,13 @@ blob = torch.tensor([ga.best_fitness, float(sum(ga.fitness_scores))], dtype=torc
 out = [torch.zeros_like(blob) for _ in range(world)]
 dist.all_gather(out, blob)
 assert all(torch.equal(o, out[0]) for o in out)
+# Monte-Carlo shards: contiguous path ranges, one gather, every rank ends with the full arrays in path order
+from ai_crypto_trader_b200.dist import gather_paths
+for n in (1, 2, 9, 64):
+    lo, hi, _ = shard_bounds(n, world, rank)
+    full = torch.arange(n, dtype=torch.float32) * 0.5 + 100.0
+    f, d = gather_paths(full[lo:hi].clone(), -full[lo:hi].clone(), n)
+    assert torch.equal(f, full) and torch.equal(d, -full), (n, rank)
 if rank == 0:
     print("GLOO_OK", ga.best_fitness)
 dist.destroy_process_group()

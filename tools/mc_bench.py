@@ -23,8 +23,36 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     a = ap.parse_args()
     from ai_crypto_trader_b200.monte_carlo import PathEngine, risk_statistics
-    eng = PathEngine()
+    import os
+    world, rank = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
     mu, sigma = 0.08, 0.35            # annualised drift / volatility; horizon = steps/252 years at dt = 1/252
+    if world > 1:
+        # BASELINE configs[2] on several GPUs (torchrun): paths sharded by rank, one gather of finals + drawdowns, the
+        # statistics on every rank; STRONG scaling (the 1M paths are fixed), device time = max over ranks
+        import torch.distributed as dist
+        from ai_crypto_trader_b200.dist import gather_paths, shard_bounds
+        dist.init_process_group("nccl")
+        eng = PathEngine()
+        lo, hi, _ = shard_bounds(a.paths, world, rank)
+        def job():
+            f, d, _ = eng.gbm(100.0, mu, sigma, 1 / 252, hi - lo, a.steps, 2024, path_offset=lo)
+            f, d = gather_paths(f, d, a.paths)
+            return risk_statistics(eng, f, d, 100.0, 0.95)
+        job(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.reps): st = job()
+        e1.record(); dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / a.reps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(json.dumps({"workload": f"GBM {a.paths} paths x {a.steps} steps, risk statistics, {world} GPUs (paths sharded, strong scaling)",
+                              "n_gpus": world, "ms": float(t.item()), "path_steps_per_s": a.paths * a.steps / (float(t.item()) * 1e-3),
+                              "var_pct": abs(st["var"]), "mdd_mean": st["mdd_mean"]}))
+        dist.destroy_process_group()
+        return
+    eng = PathEngine()
     def timed(fn, reps):
         fn(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
