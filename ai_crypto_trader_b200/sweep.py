@@ -21,7 +21,7 @@ from __future__ import annotations
 import ctypes as C
 import inspect
 import os
-from typing import Dict, Iterable, List, Optional, Sequence
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -53,6 +53,9 @@ class MarketData:
 
     Mirrors the role of HistoricalDataManager.market_data_cache
     (backtesting/data_manager.py:218-220): load once, reuse across calls.
+
+    From a PINNED host tensor only the close prices are uploaded at construction; open / high / low / volume are
+    uploaded when first read (`materialise()` forces it), so the source must stay unchanged until then.
     """
 
     def __init__(self, ohlcv, symbols: Optional[Sequence[str]] = None,
@@ -69,23 +72,29 @@ class MarketData:
             raise ValueError("ohlcv must have shape [5][S][N] (open, high, low, close, volume)")
         self.S = int(host.shape[1])
         self.N = int(host.shape[2])
-        self._others_ready = None
+        self._pending_host = None       # pinned source whose open / high / low / volume rows are not on the device yet
+        self.h2d_bytes = 0              # bytes this object has copied host -> device so far
         if host.is_cuda or not host.is_pinned():
             self._ohlcv = host.to(self.device, non_blocking=True).contiguous()
+            self.h2d_bytes = 0 if host.is_cuda else host.numel() * 4
         else:
-            # pinned host source: the close prices (all the sweep and the RSI bank read) go first on the caller's
-            # stream; open / high / low / volume follow on a copy stream and are waited for on first use
+            # pinned host source: only the close prices (all the sweep and the RSI bank read) are uploaded now, in four
+            # concurrent quarter copies (one 40 MB copy reaches ~24 GB/s here, four ~33 GB/s: tools/h2d_bandwidth.py);
+            # open / high / low / volume follow on first use (the indicator kernels), so a GA generation does not move them
             host = host.contiguous()
             self._ohlcv = torch.empty(host.shape, dtype=torch.float32, device=self.device)
-            self._ohlcv[3].copy_(host[3], non_blocking=True)
-            side = _copy_stream(self.device)
-            side.wait_stream(torch.cuda.current_stream(self.device))       # (allocation order)
-            with torch.cuda.stream(side):
-                for f in (0, 1, 2, 4):
-                    self._ohlcv[f].copy_(host[f], non_blocking=True)
-                self._others_ready = side.record_event()
-            # (no record_stream: it would keep the allocator from reusing this block for the next MarketData and cost a
-            # cudaMalloc per upload; __del__ orders the release after the side-stream copies instead)
+            cur = torch.cuda.current_stream(self.device)
+            parts = min(4, self.S)
+            lanes = [_copy_stream(self.device, 1 + i) for i in range(parts)]
+            rows = [(i * self.S) // parts for i in range(parts + 1)]
+            for st, lo, hi in zip(lanes, rows[:-1], rows[1:]):
+                st.wait_stream(cur)                                          # (allocation order)
+                with torch.cuda.stream(st):
+                    self._ohlcv[3, lo:hi].copy_(host[3, lo:hi], non_blocking=True)
+            for st in lanes:
+                cur.wait_stream(st)
+            self._pending_host = host
+            self.h2d_bytes = self.S * self.N * 4
         self.symbols = list(symbols) if symbols is not None else [f"SYN{i:03d}USDT" for i in range(self.S)]
         self.minute0 = int(minute0)
         self.bar_minutes = int(bar_minutes)
@@ -98,16 +107,19 @@ class MarketData:
         ohlcv[3] = close
         return cls(ohlcv, symbols=symbols, minute0=minute0, bar_minutes=bar_minutes, device=close.device)
 
-    def __del__(self):
-        try:
-            self._wait_others()      # the block returns to the allocator on the current stream: after the copies
-        except Exception:
-            pass
+    def materialise(self) -> "MarketData":
+        """Make all five fields device-resident now."""
+        self._wait_others()
+        return self
 
     def _wait_others(self) -> None:
-        if self._others_ready is not None:
-            torch.cuda.current_stream(self.device).wait_event(self._others_ready)
-            self._others_ready = None
+        """Upload the fields that are still on the host (current stream)."""
+        host = self._pending_host
+        if host is not None:
+            self._pending_host = None
+            for f in (0, 1, 2, 4):
+                self._ohlcv[f].copy_(host[f], non_blocking=True)
+            self.h2d_bytes += 4 * self.S * self.N * 4
 
     @property
     def ohlcv(self) -> torch.Tensor:
@@ -135,14 +147,14 @@ class MarketData:
         return self.ohlcv[4]
 
 
-_COPY_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+_COPY_STREAMS: Dict[Tuple[int, int], "torch.cuda.Stream"] = {}
 
 
-def _copy_stream(device: torch.device) -> "torch.cuda.Stream":
+def _copy_stream(device: torch.device, which: int = 0) -> "torch.cuda.Stream":
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    if idx not in _COPY_STREAMS:
-        _COPY_STREAMS[idx] = torch.cuda.Stream(device=device)
-    return _COPY_STREAMS[idx]
+    if (idx, which) not in _COPY_STREAMS:
+        _COPY_STREAMS[(idx, which)] = torch.cuda.Stream(device=device)
+    return _COPY_STREAMS[(idx, which)]
 
 
 def rsi_bank(close: torch.Tensor, periods: Sequence[int], fill: bool = True,

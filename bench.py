@@ -304,7 +304,7 @@ def main():
             out = torch.empty(pop_global, dtype=torch.float64, device=dev)
             dist.all_gather_into_tensor(out, g)
             f = out.cpu().numpy()
-        return f, sw.h2d_bytes + ohlcv_host.numel() * 4, sw.d2h_bytes
+        return f, sw.h2d_bytes + mk.h2d_bytes, sw.d2h_bytes    # (the sweep reads close prices: the other OHLCV fields stay on the host)
 
     e2e_steps = max(3, min(args.steps, 5))
     f_e2e, h2d, d2h = e2e_step()
@@ -338,7 +338,7 @@ def main():
                          "traffic": ncu_traffic, "traffic_unit": "bytes per launch of the dominant kernel (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "peak_source": peak_src, "bytes_per_eval": BYTES_PER_EVAL,
                          "kernel_ms": ms_kernel, "sweep_mode": path, "note": "achieved = 8 B x evals per sweep / CUDA-event duration of the sweep kernels (scan, verify/repair, metrics, fitness reduce); lanes sharing a (symbol, period) stream are served from L1/L2, so DRAM traffic is far below the algorithmic bytes (see profiles/)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "path": "MarketData(pinned host OHLCV) -> PopulationSweep (RSI bank) -> evaluate(list of dicts) -> host fitness"},
+                    "steps": e2e_steps, "path": "MarketData(pinned host OHLCV; close prices uploaded, the fields the sweep does not read stay on the host) -> PopulationSweep (RSI bank) -> evaluate(list of dicts) -> host fitness"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
