@@ -73,6 +73,7 @@ class MarketData:
         self.S = int(host.shape[1])
         self.N = int(host.shape[2])
         self._pending_host = None       # pinned source whose open / high / low / volume rows are not on the device yet
+        self._close_parts = []
         self.h2d_bytes = 0              # bytes this object has copied host -> device so far
         if host.is_cuda or not host.is_pinned():
             self._ohlcv = host.to(self.device, non_blocking=True).contiguous()
@@ -87,12 +88,12 @@ class MarketData:
             parts = min(4, self.S)
             lanes = [_copy_stream(self.device, 1 + i) for i in range(parts)]
             rows = [(i * self.S) // parts for i in range(parts + 1)]
+            self._close_parts = []      # (row lo, row hi, stream) of the quarter copies the current stream has not joined yet
             for st, lo, hi in zip(lanes, rows[:-1], rows[1:]):
                 st.wait_stream(cur)                                          # (allocation order)
                 with torch.cuda.stream(st):
                     self._ohlcv[3, lo:hi].copy_(host[3, lo:hi], non_blocking=True)
-            for st in lanes:
-                cur.wait_stream(st)
+                self._close_parts.append((lo, hi, st))
             self._pending_host = host
             self.h2d_bytes = self.S * self.N * 4
         self.symbols = list(symbols) if symbols is not None else [f"SYN{i:03d}USDT" for i in range(self.S)]
@@ -126,8 +127,17 @@ class MarketData:
         self._wait_others()
         return self._ohlcv
 
+    def _join_close(self) -> None:
+        """The current stream waits for the quarter copies of the close prices (once)."""
+        if self._close_parts:
+            cur = torch.cuda.current_stream(self.device)
+            for _, _, st in self._close_parts:
+                cur.wait_stream(st)
+            self._close_parts = []
+
     @property
     def close(self) -> torch.Tensor:
+        self._join_close()
         return self._ohlcv[3]
 
     @property
@@ -393,13 +403,30 @@ class PopulationSweep:
             primary=_lib.PRIMARY[goals.get("primary", "sharpe_ratio")],
             secondary_mask=sum(_lib.SECONDARY.get(m, 0) for m in goals.get("secondary", [])), variant=0)
         self.event_cap = int(event_cap)
-        self.bank = rsi_bank(market.close, self.periods)
+        self.bank = self._bank_behind_the_upload(market)
         self.mode, self.chunk_min_bars, self.chunk_options = mode, 131072, dict(chunk_options or {})
         self._stats = None
         self._events = None
         self._pop = 0
         self._pinned_in = None
         self._pinned_out = None
+
+    def _bank_behind_the_upload(self, market: MarketData) -> torch.Tensor:
+        """RSI bank of the market.  While the close prices are still arriving in quarter copies (MarketData from a
+        pinned host tensor), each quarter's rows are computed on that quarter's copy stream, so the bank is ready one
+        quarter of its kernel time after the last byte instead of one whole kernel."""
+        parts = market._close_parts
+        if not parts:
+            return rsi_bank(market.close, self.periods)
+        P = len(self.periods)
+        bank = torch.empty((market.S, P, market.N), dtype=torch.float32, device=market.device)
+        cur = torch.cuda.current_stream(market.device)
+        for lo, hi, st in parts:
+            st.wait_stream(cur)                        # (the bank's allocation)
+            with torch.cuda.stream(st):
+                rsi_bank(market._ohlcv[3, lo:hi], self.periods, out=bank[lo:hi])
+        market._join_close()                           # the current stream now waits for copies AND bank rows
+        return bank
 
     @classmethod
     def from_bank(cls, market: MarketData, bank: torch.Tensor, periods, optimization_goals=None,
