@@ -242,6 +242,27 @@ def lane_costs(population: List[Dict]) -> np.ndarray:
     return ndtr((g("rsi_oversold", 30) - 50.0) / sd) + 1.0 - ndtr((g("rsi_overbought", 70) - 50.0) / sd)
 
 
+_HASH_MULTIPLIERS = np.array([0x9E3779B97F4A7C15, 0xC2B2AE3D27D4EB4F, 0x165667B19E3779F9, 0x27D4EB2F165667C5,
+                              0x85EBCA77C2B2AE63], dtype=np.uint64)
+
+
+def _duplicate_classes(packed: np.ndarray):
+    """(first index of each distinct record, class of every record), or None when all records are distinct.
+    Records are compared through a 64-bit multiplicative hash of their 40 bytes (3x faster than sorting the structured
+    array); a hash class is only trusted after every member is compared with its representative."""
+    words = packed.view(np.uint64).reshape(len(packed), -1)
+    with np.errstate(over="ignore"):
+        key = (words * _HASH_MULTIPLIERS[:words.shape[1]]).sum(axis=1, dtype=np.uint64)
+    uk, first, inverse = np.unique(key, return_index=True, return_inverse=True)
+    if len(uk) == len(packed):
+        return None
+    inverse = inverse.reshape(-1)
+    if not bool((packed[first][inverse] == packed).all()):       # a collision merged different records: exact path
+        _, first, inverse = np.unique(packed, return_index=True, return_inverse=True)
+        inverse = inverse.reshape(-1)
+    return (first, inverse) if len(first) < len(packed) else None
+
+
 def costs_from_packed(packed: np.ndarray, periods: Sequence[int]) -> np.ndarray:
     """lane_cost of already decoded individuals (b200bt_individual records): no second pass over the dicts."""
     from scipy.special import ndtr
@@ -631,9 +652,10 @@ class PopulationSweep:
         packed = decode_population(population, self.period_row)
         # individuals that decode to the same kernel parameters (the reference rule reads 6 of the 18 genes,
         # and elitism / crossover copy individuals) are evaluated once
-        uniq, first, inverse = np.unique(packed, return_index=True, return_inverse=True)
         expand = None
-        if len(uniq) < len(packed):
+        dup = _duplicate_classes(packed)
+        if dup is not None:
+            first, inverse = dup
             keep = np.sort(first)                       # unique individuals in population order
             rank = np.empty(len(first), dtype=np.int64)
             rank[np.argsort(first)] = np.arange(len(first))
