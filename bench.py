@@ -183,7 +183,30 @@ def cpu_baseline_inline(budget_s: float = 12.0):
     dtc = time.perf_counter() - t0
     py["c_port_single_core"] = {"value": N_BARS * len(pop) / dtc, "unit": UNIT, "cores": 1,
                                 "sample": f"{len(pop)} lanes x {N_BARS} bars, oracle/sim_oracle.c"}
+    # BASELINE configs[0] (the reference's own CPU-runnable case): StrategyTester.backtest_strategy on 10 000 bars of one
+    # symbol, restated in Python with the LLM stubbed (oracle/tester_ref.py), single process like the reference
+    from oracle import tester_ref
+    df = configs0_frame()
+    t0 = time.perf_counter()
+    st = tester_ref.backtest(df)
+    py["configs0_backtest"] = {"cpu_ms": (time.perf_counter() - t0) * 1e3, "bars": len(df), "trades": int(st["total_trades"]),
+                               "sample": "1 strategy x 1 symbol x 10 000 bars, oracle/tester_ref.py, 1 core"}
     return py
+
+
+def configs0_frame():
+    """10 000 synthetic 1-minute bars ending in a sell-off (the constant technical signal then trades, as in the parity
+    fixtures tests/golden/bt_reference.*)."""
+    import numpy as np
+    import pandas as pd
+    from ai_crypto_trader_b200 import synth
+    n = 10_000
+    d = synth.synth_symbol(1, n)
+    f = np.ones(n)
+    f[-60:] = np.linspace(1.0, 0.90, 60)
+    cols = {k: d[k].astype(np.float64) * (f if k in ("open", "high", "low", "close") else 1.0) for k in synth.FIELDS}
+    return pd.DataFrame({k: v.astype(np.float32).astype(np.float64) for k, v in cols.items()},
+                        index=pd.date_range("2024-01-01", periods=n, freq="min"))
 
 
 # --------------------------------------------------------------------------
@@ -343,6 +366,17 @@ def main():
             "clocks": clocks,
         }
         if cpu_baseline is not None:
+            if "configs0_backtest" in cpu_baseline:
+                # the same configs[0] backtest through the GPU path (indicators, backtest_ref kernel, stats dict)
+                import asyncio
+                from ai_crypto_trader_b200.backtesting import StrategyTester
+                df0 = configs0_frame()
+                tester = StrategyTester(config={}, data_manager=None, results_dir="/tmp/b200bt_bench_results", config_path=None)
+                asyncio.run(tester.backtest_frame(df0, "SYNUSDC"))
+                t0 = time.perf_counter()
+                st0 = asyncio.run(tester.backtest_frame(df0, "SYNUSDC"))
+                cpu_baseline["configs0_backtest"]["gpu_path_ms"] = (time.perf_counter() - t0) * 1e3
+                cpu_baseline["configs0_backtest"]["gpu_trades"] = int(st0["total_trades"])
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
     if world > 1:
