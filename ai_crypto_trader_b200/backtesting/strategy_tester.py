@@ -172,23 +172,31 @@ class StrategyTester:
         n_tr, n_eq = int(s[1]), int(s[8])
         tr = trades_dev[:n_tr].cpu().numpy()
         eq = equity_dev[:n_eq].cpu().numpy()
-        times = [t.isoformat() for t in df.index]
+        # host materialisation of the reference's result schema (:320-333, :166-171, :222-236), column-wise
+        idx = df.index
+        if len(idx) and bool((idx.microsecond == 0).all()) and bool((idx.nanosecond == 0).all()):
+            times = np.asarray(idx.strftime("%Y-%m-%dT%H:%M:%S"))        # == Timestamp.isoformat() for whole seconds
+        else:
+            times = np.array([t.isoformat() for t in idx], dtype=object)
         st = self.stats
-        for row in tr:
-            st["trades"].append({"symbol": symbol, "entry_price": float(row[3]), "entry_time": times[int(row[0])],
-                                 "quantity": float(row[4]), "position_size": float(row[5]),
-                                 "stop_loss_pct": tech["stop_loss_pct"], "take_profit_pct": tech["take_profit_pct"],
-                                 "exit_price": float(market_price(df, int(row[1]))), "exit_time": times[int(row[1])],
-                                 "pnl": float(row[6]), "pnl_pct": float(row[7]), "exit_reason": REASONS[int(row[2])]})
-        max_equity = initial_balance
-        for bar, bal in eq:
-            ts = times[int(bar)]
-            bal = float(bal)
-            st["equity_curve"].append({"timestamp": ts, "equity": bal})
-            if bal > max_equity:
-                max_equity = bal
-            dd = max_equity - bal
-            st["drawdown_curve"].append({"timestamp": ts, "drawdown": dd, "drawdown_pct": (dd / max_equity) * 100})
+        e_bar, x_bar = tr[:, 0].astype(np.int64), tr[:, 1].astype(np.int64)
+        exit_price = df["close"].to_numpy().astype(np.float32).astype(np.float64)[x_bar]      # market_price(): the fp32 close
+        sl, tp = tech["stop_loss_pct"], tech["take_profit_pct"]
+        reasons = [REASONS[int(r)] for r in tr[:, 2].astype(np.int64).tolist()]
+        st["trades"].extend(
+            {"symbol": symbol, "entry_price": ep, "entry_time": et, "quantity": q, "position_size": ps,
+             "stop_loss_pct": sl, "take_profit_pct": tp, "exit_price": xp, "exit_time": xt, "pnl": pnl, "pnl_pct": pp,
+             "exit_reason": why}
+            for ep, et, q, ps, xp, xt, pnl, pp, why in zip(tr[:, 3].tolist(), times[e_bar].tolist(), tr[:, 4].tolist(),
+                                                           tr[:, 5].tolist(), exit_price.tolist(), times[x_bar].tolist(),
+                                                           tr[:, 6].tolist(), tr[:, 7].tolist(), reasons))
+        bal = eq[:, 1]
+        peak = np.maximum.accumulate(np.concatenate([[float(initial_balance)], bal]))[1:]     # running max incl. the start
+        dd = peak - bal
+        ts = times[eq[:, 0].astype(np.int64)].tolist()
+        st["equity_curve"].extend({"timestamp": t, "equity": b} for t, b in zip(ts, bal.tolist()))
+        st["drawdown_curve"].extend({"timestamp": t, "drawdown": d, "drawdown_pct": p}
+                                    for t, d, p in zip(ts, dd.tolist(), ((dd / peak) * 100).tolist()))
         st["total_trades"], st["winning_trades"], st["losing_trades"] = int(s[1]), int(s[2]), int(s[3])
         st["total_profit"], st["total_loss"] = float(s[4]), float(s[5])
         st["max_drawdown"], st["max_drawdown_pct"] = float(s[6]), float(s[7])
