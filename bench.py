@@ -371,7 +371,7 @@ def main():
                 import asyncio
                 from ai_crypto_trader_b200.backtesting import StrategyTester
                 df0 = configs0_frame()
-                tester = StrategyTester(config={}, data_manager=None, results_dir="/tmp/b200bt_bench_results", config_path=None)
+                tester = StrategyTester(config={}, data_manager=None, results_dir=os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpurun_out", "bench_results"), config_path=None)
                 asyncio.run(tester.backtest_frame(df0, "SYNUSDC"))
                 t0 = time.perf_counter()
                 st0 = asyncio.run(tester.backtest_frame(df0, "SYNUSDC"))
