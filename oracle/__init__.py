@@ -8,7 +8,8 @@ the timed CPU baseline.  The product package (ai_crypto_trader_b200) never
 imports this package and has no CPU fallback.
 
 Pinning status (see DESIGN.md "Oracle"):
-  * simulate / metrics / score / GA operators / Monte-Carlo statistics are
+  * simulate / metrics / advanced metrics / score / cross-validation / GA operators / Monte-Carlo statistics /
+    StrategyTester backtest / portfolio VaR, CVaR and correlation are
     pinned by golden fixtures produced by EXECUTING the reference's own code
     (tests/golden/make_golden.py, run in the build container where
     /root/reference exists; fixtures committed under tests/golden/).
