@@ -66,8 +66,30 @@ EVENT_EXIT = 0x40000000
 EVENT_SELL = 0x80000000
 EVENT_BAR_MASK = 0x3FFFFFFF
 
-PRIMARY = {"sharpe_ratio": 0, "return_pct": 1, "profit_factor": 2, "win_rate": 3, "net_profit": 4}
+PRIMARY = {"sharpe_ratio": 0, "return_pct": 1, "profit_factor": 2, "win_rate": 3, "net_profit": 4, "total_trades": 5,
+           "max_drawdown": 6, "total_profit": 7, "total_loss": 8, "largest_profit": 9, "largest_loss": 10,
+           "average_profit": 11, "average_loss": 12}
+PRIMARY_ADVANCED = {"sortino_ratio": 13, "expectancy": 14, "calmar_ratio": 15, "profit_per_day": 16, "recovery_factor": 17}
+PRIMARY_ZERO = 99
 SECONDARY = {"max_drawdown": 1, "win_rate": 2, "profit_factor": 4}
+SECONDARY_ADVANCED = {"expectancy": 8}
+
+
+def score_codes(goals: dict, advanced: bool = False):
+    """(primary code, secondary mask) of `_calculate_strategy_score` (strategy_evaluation.py:579-633) for the kernels.
+
+    `advanced` = the score is taken on calculate_advanced_metrics' dict (evaluate_strategy :545-557) instead of the plain
+    calculate_metrics dict (cross_validate_strategy :683-691).  The reference reads `metrics.get(primary, 0)` and walks
+    an if / elif chain over the secondary names, so a key the dict does not hold scores 0 and an unknown secondary
+    name (or `expectancy` on the plain dict, where the key is absent and the factor is 1) changes nothing."""
+    name = goals.get("primary", "sharpe_ratio")
+    table = dict(PRIMARY, **PRIMARY_ADVANCED) if advanced else PRIMARY
+    primary = table.get(name, PRIMARY_ZERO)
+    sec = dict(SECONDARY, **SECONDARY_ADVANCED) if advanced else SECONDARY
+    mask = 0
+    for m in goals.get("secondary", []):
+        mask |= sec.get(m, 0)
+    return primary, mask
 
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
 

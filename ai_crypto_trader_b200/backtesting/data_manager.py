@@ -53,11 +53,30 @@ class HistoricalDataManager:
 
     @staticmethod
     def save_sidecar(csv_path: Path, df: pd.DataFrame) -> Path:
+        """fp32 [5][N] + int64 epoch SECONDS next to the CSV, stamped with the CSV's size and mtime: a CSV that is
+        rewritten afterwards (the reference's fetcher, :191-196) invalidates the sidecar."""
         side = Path(str(csv_path) + ".f32.npz")
-        minutes = (df.index.astype("datetime64[s]").astype(np.int64) // 60).to_numpy()
+        seconds = df.index.astype("datetime64[s]").astype(np.int64).to_numpy()
         ohlcv = np.stack([df[f].to_numpy(dtype=np.float32) for f in FIELDS])
-        np.savez(side, ohlcv=ohlcv, minutes=minutes)
+        st = Path(csv_path).stat()
+        np.savez(side, ohlcv=ohlcv, seconds=seconds, csv_stamp=np.array([st.st_size, st.st_mtime_ns], dtype=np.int64))
         return side
+
+    @staticmethod
+    def _sidecar_if_fresh(csv_path: Path):
+        """The sidecar's arrays when it exists and still describes `csv_path` (same size and mtime), else None."""
+        side = Path(str(csv_path) + ".f32.npz")
+        if not side.exists():
+            return None
+        try:
+            z = np.load(side)
+            st = Path(csv_path).stat()
+            if "csv_stamp" not in z or "seconds" not in z or z["csv_stamp"].tolist() != [st.st_size, st.st_mtime_ns]:
+                return None
+            return z["seconds"], z["ohlcv"]
+        except Exception as e:
+            logger.error("Error loading sidecar %s: %s", side, e)
+            return None
 
     # -- reading ------------------------------------------------------------------
     def load_market_data(self, symbol: str, interval: str, start_date: datetime, end_date: datetime = None) -> pd.DataFrame:
@@ -94,27 +113,27 @@ class HistoricalDataManager:
         return result
 
     def load_ohlcv32(self, symbol: str, interval: str, start_date: datetime, end_date: datetime = None):
-        """(float32 [5][N], int64 minutes[N]) from the binary sidecars when every matching CSV has
-        one; falls back to parsing the CSVs (same values, rounded to fp32)."""
+        """(float32 [5][N], int64 minutes[N]) from the binary sidecars when every matching CSV has a fresh one
+        (`_sidecar_if_fresh`); otherwise the CSVs are parsed (same values, rounded to fp32).  Rows are de-duplicated on
+        their timestamp in seconds (keep first, like load_market_data :258); `minutes` = seconds // 60."""
         symbol_dir = self.market_data_dir / symbol
         files = sorted(symbol_dir.glob(f"{interval}_*.csv")) if symbol_dir.exists() else []
-        sides = [Path(str(p) + ".f32.npz") for p in files]
-        if files and all(s.exists() for s in sides):
+        sides = [self._sidecar_if_fresh(p) for p in files]
+        if files and all(s is not None for s in sides):
             if end_date is None:
                 end_date = datetime.now()
-            lo = int(pd.Timestamp(start_date).timestamp() // 60)
-            hi = int(pd.Timestamp(end_date).timestamp() // 60)
+            lo = int(pd.Timestamp(start_date).timestamp())
+            hi = int(pd.Timestamp(end_date).timestamp())
             chunks = []
-            for s in sides:
-                z = np.load(s)
-                m = (z["minutes"] >= lo) & (z["minutes"] <= hi)
-                chunks.append((z["minutes"][m], z["ohlcv"][:, m]))
-            minutes = np.concatenate([c[0] for c in chunks])
+            for sec, ohlcv in sides:
+                m = (sec >= lo) & (sec <= hi)
+                chunks.append((sec[m], ohlcv[:, m]))
+            seconds = np.concatenate([c[0] for c in chunks])
             ohlcv = np.concatenate([c[1] for c in chunks], axis=1)
-            order = np.argsort(minutes, kind="stable")
-            minutes, ohlcv = minutes[order], ohlcv[:, order]
-            keep = np.concatenate([[True], minutes[1:] != minutes[:-1]])
-            return np.ascontiguousarray(ohlcv[:, keep]), minutes[keep]
+            order = np.argsort(seconds, kind="stable")
+            seconds, ohlcv = seconds[order], ohlcv[:, order]
+            keep = np.concatenate([[True], seconds[1:] != seconds[:-1]]) if len(seconds) else np.zeros(0, dtype=bool)
+            return np.ascontiguousarray(ohlcv[:, keep]), seconds[keep] // 60
         df = self.load_market_data(symbol, interval, start_date, end_date)
         if df.empty:
             return np.zeros((5, 0), dtype=np.float32), np.zeros(0, dtype=np.int64)

@@ -299,18 +299,38 @@ __device__ __forceinline__ void finalize_lane(const WarpAcc& a, const b200bt_swe
     o.n_negative_days = (a.n_events >= 2) ? (double)da.n_neg : 0.0;
     o.downside_deviation = downside;
     o.mean_daily_pnl = mean_daily;
+    // every scalar key of the metrics dict can be the primary metric (:589-590)
+    const double ret_pct = (o.net_profit / cfg.initial_capital) * 100.0;
+    const double avg_p = a.n_win ? a.tot_profit / (double)a.n_win : 0.0, avg_l = a.n_loss ? a.tot_loss / (double)a.n_loss : 0.0;
+    // calculate_advanced_metrics :302-310 (total_trades > 0)
+    const double expectancy = a.n_events ? win_rate * avg_p - (1.0 - win_rate) * fabs(avg_l) : 0.0;
     double primary;
     switch (cfg.primary) {
-        case B200BT_PRIMARY_RETURN_PCT: primary = (o.net_profit / cfg.initial_capital) * 100.0; break;
+        case B200BT_PRIMARY_RETURN_PCT: primary = ret_pct; break;
         case B200BT_PRIMARY_PROFIT_FACTOR: primary = pf; break;
         case B200BT_PRIMARY_WIN_RATE: primary = win_rate; break;
         case B200BT_PRIMARY_NET_PROFIT: primary = o.net_profit; break;
+        case B200BT_PRIMARY_TOTAL_TRADES: primary = n_rec; break;
+        case B200BT_PRIMARY_MAX_DRAWDOWN: primary = a.maxdd; break;
+        case B200BT_PRIMARY_TOTAL_PROFIT: primary = a.tot_profit; break;
+        case B200BT_PRIMARY_TOTAL_LOSS: primary = a.tot_loss; break;
+        case B200BT_PRIMARY_LARGEST_PROFIT: primary = a.largest_p; break;
+        case B200BT_PRIMARY_LARGEST_LOSS: primary = a.largest_l; break;
+        case B200BT_PRIMARY_AVERAGE_PROFIT: primary = avg_p; break;
+        case B200BT_PRIMARY_AVERAGE_LOSS: primary = avg_l; break;
+        case B200BT_PRIMARY_SORTINO: primary = sortino; break;
+        case B200BT_PRIMARY_EXPECTANCY: primary = expectancy; break;
+        case B200BT_PRIMARY_CALMAR: primary = a.maxdd > 0.0 ? (ret_pct / 100.0) / a.maxdd : INFINITY; break;          // :243-249
+        case B200BT_PRIMARY_PROFIT_PER_DAY: primary = mean_daily; break;
+        case B200BT_PRIMARY_RECOVERY_FACTOR: primary = a.maxdd > 0.0 ? o.net_profit / (a.maxdd * 10000.0) : INFINITY; break;   // :296-300
+        case B200BT_PRIMARY_ZERO: primary = 0.0; break;
         default: primary = sharpe; break;
     }
     double score = primary;
     if (cfg.secondary_mask & B200BT_SEC_MAX_DRAWDOWN) score *= (1.0 - a.maxdd);
     if (cfg.secondary_mask & B200BT_SEC_WIN_RATE) score *= (1.0 + win_rate);
     if (cfg.secondary_mask & B200BT_SEC_PROFIT_FACTOR) score *= (pf / 2.0);
+    if (cfg.secondary_mask & B200BT_SEC_EXPECTANCY) score *= (1.0 + fmin(expectancy / 100.0, 1.0));
     o.score = score;
 }
 

@@ -16,7 +16,7 @@ import uuid
 from datetime import datetime
 from typing import Dict, List, Optional
 
-from .dist import ShardedFitness
+from .dist import ShardedFitness, broadcast_seed
 from .genetic_algorithm import GeneticAlgorithm
 from .sweep import DEFAULT_GOALS, MarketData, PopulationSweep
 from .synth import param_ranges
@@ -45,10 +45,16 @@ class StrategyEvolutionService:
     async def optimize_with_genetic_algorithm(self, current_params: Dict, performance_data: Optional[Dict] = None,
                                               historical_trades: Optional[List[Dict]] = None) -> Optional[Dict]:
         try:
+            # under torch.distributed the GA operators run replicated: every rank needs the same seed (rank 0's;
+            # a fresh one is drawn there when none was configured) -- ShardedFitness checks the populations agree
+            import torch.distributed as dist
+            seed = self.random_seed
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                seed = broadcast_seed(seed)
             ga = GeneticAlgorithm(param_ranges=self.param_ranges, fitness_function=self.fitness,
                                   population_size=self.ga_population_size, generations=self.ga_generations,
                                   mutation_rate=0.2, crossover_rate=0.8, elitism_pct=0.1,
-                                  random_seed=self.random_seed)
+                                  random_seed=seed)
             seeds = [dict(current_params)] if current_params else None
             optimized = ga.run(seeded_individuals=seeds)
             history = ga.get_generation_history()

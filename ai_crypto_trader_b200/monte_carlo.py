@@ -92,6 +92,9 @@ class PathEngine:
     def bootstrap(self, returns: np.ndarray, log_returns: bool, s0, n_paths, steps, seed, path_offset=0,
                   block_len=1, store_paths=False):
         dev = self.device
+        if n_paths == 0:          # a rank without paths (more ranks than paths), as in gbm()
+            e = torch.empty(0, dtype=torch.float32, device=dev)
+            return e, e.clone(), None
         r = torch.from_numpy(np.ascontiguousarray(returns, dtype=np.float32)).to(dev)
         finals = torch.empty(n_paths, dtype=torch.float32, device=dev)
         maxdd = torch.empty(n_paths, dtype=torch.float32, device=dev)

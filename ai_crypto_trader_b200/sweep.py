@@ -411,18 +411,21 @@ class PopulationSweep:
 
     def __init__(self, market: MarketData, rsi_periods: Iterable[int] = range(5, 31),
                  optimization_goals: Optional[Dict] = None, initial_capital: float = 10000.0,
-                 event_cap: int = 0, mode: str = "auto", chunk_options: Optional[Dict] = None):
-        """mode: "fused" (one warp per lane, serial in time), "chunked" (expensive lanes split into verified
+                 event_cap: int = 0, mode: str = "auto", chunk_options: Optional[Dict] = None,
+                 score_on_advanced: bool = False):
+        """score_on_advanced: take the strategy score on calculate_advanced_metrics' dict (the composition of
+        evaluate_strategy, strategy_evaluation.py:545-557: `expectancy`, `sortino_ratio`, ... exist as keys) instead of the
+        plain calculate_metrics dict (cross_validate_strategy :683-691, the default).
+        mode: "fused" (one warp per lane, serial in time), "chunked" (expensive lanes split into verified
         time chunks, one warp per chunk), "tiled" (every lane split into the same K verified chunks, one THREAD
         per chunk; csrc/sweep_chunked.cu) or "auto" (tiled from 131072 bars up, fused below)."""
         self.market = market
         self.periods = sorted(set(int(p) for p in rsi_periods))
         self.period_row = {p: i for i, p in enumerate(self.periods)}
         goals = optimization_goals or DEFAULT_GOALS
-        self.cfg = _lib.SweepConfig(
-            initial_capital=float(initial_capital), minute0=market.minute0, bar_minutes=market.bar_minutes,
-            primary=_lib.PRIMARY[goals.get("primary", "sharpe_ratio")],
-            secondary_mask=sum(_lib.SECONDARY.get(m, 0) for m in goals.get("secondary", [])), variant=0)
+        primary, mask = _lib.score_codes(goals, advanced=score_on_advanced)
+        self.cfg = _lib.SweepConfig(initial_capital=float(initial_capital), minute0=market.minute0,
+                                    bar_minutes=market.bar_minutes, primary=primary, secondary_mask=mask, variant=0)
         self.event_cap = int(event_cap)
         self.bank = self._bank_behind_the_upload(market)
         self.mode, self.chunk_min_bars, self.chunk_options = mode, 131072, dict(chunk_options or {})
@@ -451,7 +454,8 @@ class PopulationSweep:
 
     @classmethod
     def from_bank(cls, market: MarketData, bank: torch.Tensor, periods, optimization_goals=None,
-                  initial_capital: float = 10000.0, event_cap: int = 0, mode: str = "fused") -> "PopulationSweep":
+                  initial_capital: float = 10000.0, event_cap: int = 0, mode: str = "fused",
+                  score_on_advanced: bool = False) -> "PopulationSweep":
         """Sweep over a caller-supplied RSI bank [S][P][N] (e.g. the 'rsi' field of the reference's
         market-data points) instead of one computed from the close prices."""
         self = cls.__new__(cls)
@@ -459,10 +463,9 @@ class PopulationSweep:
         self.periods = [int(p) for p in periods]
         self.period_row = {p: i for i, p in enumerate(self.periods)}
         goals = optimization_goals or DEFAULT_GOALS
-        self.cfg = _lib.SweepConfig(
-            initial_capital=float(initial_capital), minute0=market.minute0, bar_minutes=market.bar_minutes,
-            primary=_lib.PRIMARY[goals.get("primary", "sharpe_ratio")],
-            secondary_mask=sum(_lib.SECONDARY.get(m, 0) for m in goals.get("secondary", [])), variant=0)
+        primary, mask = _lib.score_codes(goals, advanced=score_on_advanced)
+        self.cfg = _lib.SweepConfig(initial_capital=float(initial_capital), minute0=market.minute0,
+                                    bar_minutes=market.bar_minutes, primary=primary, secondary_mask=mask, variant=0)
         self.event_cap = int(event_cap)
         assert bank.is_cuda and bank.dtype == torch.float32 and tuple(bank.shape) == (market.S, len(self.periods), market.N)
         self.bank = bank.contiguous()

@@ -182,9 +182,28 @@ typedef struct b200bt_lane_stats {
 #define B200BT_PRIMARY_PROFIT_FACTOR 2
 #define B200BT_PRIMARY_WIN_RATE 3
 #define B200BT_PRIMARY_NET_PROFIT 4
+/* any other scalar key of the metrics dict may be the primary metric (`metrics.get(primary, 0)`, :589-590) */
+#define B200BT_PRIMARY_TOTAL_TRADES 5
+#define B200BT_PRIMARY_MAX_DRAWDOWN 6
+#define B200BT_PRIMARY_TOTAL_PROFIT 7
+#define B200BT_PRIMARY_TOTAL_LOSS 8
+#define B200BT_PRIMARY_LARGEST_PROFIT 9
+#define B200BT_PRIMARY_LARGEST_LOSS 10
+#define B200BT_PRIMARY_AVERAGE_PROFIT 11
+#define B200BT_PRIMARY_AVERAGE_LOSS 12
+/* keys only calculate_advanced_metrics adds (:231-319): present when the score is taken on the advanced dict
+ * (evaluate_strategy :545-557); on the plain dict (cross_validate_strategy :683-691) the host passes ZERO for them */
+#define B200BT_PRIMARY_SORTINO 13
+#define B200BT_PRIMARY_EXPECTANCY 14
+#define B200BT_PRIMARY_CALMAR 15
+#define B200BT_PRIMARY_PROFIT_PER_DAY 16
+#define B200BT_PRIMARY_RECOVERY_FACTOR 17
+#define B200BT_PRIMARY_ZERO 99           /* a key the metrics dict does not hold: metrics.get(key, 0) */
 #define B200BT_SEC_MAX_DRAWDOWN 1
 #define B200BT_SEC_WIN_RATE 2
 #define B200BT_SEC_PROFIT_FACTOR 4
+#define B200BT_SEC_EXPECTANCY 8          /* score *= 1 + min(expectancy / 100, 1) (:615-620); set by the host only when
+                                            the score is taken on the advanced dict (else the key is absent: factor 1) */
 
 typedef struct b200bt_sweep_config {
     double initial_capital;  /* 10000.0 (strategy_evaluation.py:33,761)       */

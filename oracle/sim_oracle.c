@@ -228,18 +228,38 @@ int oracle_lane(const float* price, const float* rsi, int64_t n, const oracle_pa
         out->downside_deviation = sd;
         out->sortino_ratio = sd > 0.0 ? (mean / sd) * sqrt(252.0) : INFINITY;
     }
+    /* _calculate_strategy_score :579-633 on the metrics dict (codes as in include/b200bt.h) */
+    const double ret_pct = (out->net_profit / cfg->initial_capital) * 100.0;
+    const double avg_p = out->n_wins > 0 ? out->total_profit / out->n_wins : 0.0;
+    const double avg_l = out->n_losses > 0 ? out->total_loss / out->n_losses : 0.0;
+    const double expectancy = a.n_rec > 0 ? win_rate * avg_p - (1.0 - win_rate) * fabs(avg_l) : 0.0;   /* :302-310 */
     double primary;
     switch (cfg->primary) {
-        case 1: primary = (out->net_profit / cfg->initial_capital) * 100.0; break;
+        case 1: primary = ret_pct; break;
         case 2: primary = pf; break;
         case 3: primary = win_rate; break;
         case 4: primary = out->net_profit; break;
+        case 5: primary = out->n_records; break;
+        case 6: primary = out->max_drawdown; break;
+        case 7: primary = out->total_profit; break;
+        case 8: primary = out->total_loss; break;
+        case 9: primary = out->largest_profit; break;
+        case 10: primary = out->largest_loss; break;
+        case 11: primary = avg_p; break;
+        case 12: primary = avg_l; break;
+        case 13: primary = out->sortino_ratio; break;
+        case 14: primary = expectancy; break;
+        case 15: primary = out->max_drawdown > 0.0 ? (ret_pct / 100.0) / out->max_drawdown : INFINITY; break;
+        case 16: primary = out->mean_daily_pnl; break;
+        case 17: primary = out->max_drawdown > 0.0 ? out->net_profit / (out->max_drawdown * 10000.0) : INFINITY; break;
+        case 99: primary = 0.0; break;
         default: primary = sharpe; break;
     }
     double score = primary;
     if (cfg->secondary_mask & 1) score *= (1.0 - out->max_drawdown);
     if (cfg->secondary_mask & 2) score *= (1.0 + win_rate);
     if (cfg->secondary_mask & 4) score *= (pf / 2.0);
+    if (cfg->secondary_mask & 8) score *= (1.0 + fmin(expectancy / 100.0, 1.0));
     out->score = score;
     free(a.days);
     return 0;

@@ -62,11 +62,24 @@ def params_of(p: dict) -> Params:
                   10000 * (min(p.get("max_position_size", 5), 20) / 100))
 
 
+_PRIMARY = {"sharpe_ratio": 0, "return_pct": 1, "profit_factor": 2, "win_rate": 3, "net_profit": 4, "total_trades": 5,
+            "max_drawdown": 6, "total_profit": 7, "total_loss": 8, "largest_profit": 9, "largest_loss": 10,
+            "average_profit": 11, "average_loss": 12}
+_PRIMARY_ADV = {"sortino_ratio": 13, "expectancy": 14, "calmar_ratio": 15, "profit_per_day": 16, "recovery_factor": 17}
+
+
 def config_of(minute0: int, bar_minutes: int = 1, goals: dict | None = None, initial_capital: float = 10000.0,
-              gap_bar: int = 0, gap_minutes: int = 0) -> Config:
+              gap_bar: int = 0, gap_minutes: int = 0, advanced: bool = False) -> Config:
+    """`advanced`: score on calculate_advanced_metrics' dict (strategy_evaluation.py:545-557) instead of the plain one."""
     goals = goals or {"primary": "sharpe_ratio", "secondary": ["max_drawdown", "win_rate", "profit_factor"]}
-    prim = {"sharpe_ratio": 0, "return_pct": 1, "profit_factor": 2, "win_rate": 3, "net_profit": 4}[goals.get("primary", "sharpe_ratio")]
-    sec = sum({"max_drawdown": 1, "win_rate": 2, "profit_factor": 4}.get(m, 0) for m in goals.get("secondary", []))
+    table = dict(_PRIMARY, **_PRIMARY_ADV) if advanced else _PRIMARY
+    prim = table.get(goals.get("primary", "sharpe_ratio"), 99)          # metrics.get(primary, 0)
+    secs = {"max_drawdown": 1, "win_rate": 2, "profit_factor": 4}
+    if advanced:
+        secs["expectancy"] = 8
+    sec = 0
+    for m in goals.get("secondary", []):
+        sec |= secs.get(m, 0)
     return Config(float(initial_capital), int(minute0), int(bar_minutes), prim, sec, 0, int(gap_bar), int(gap_minutes))
 
 

@@ -12,6 +12,7 @@ Writes (all small, committed):
     tests/golden/bt_reference.*   StrategyTester.backtest_strategy runs (LLM stubbed, `ta` shimmed)
     tests/golden/pf_reference.json PortfolioRiskService VaR / CVaR / correlation / portfolio VaR
     tests/golden/cv_reference.json StrategyEvaluationSystem.cross_validate_strategy on flat data points
+    tests/golden/ra_reference.json ResultAnalyzer load / filter / generate_summary_report on a set of result files
 Inputs are the fp32 synthetic series of ai_crypto_trader_b200.synth; the RSI
 bank is oracle.indicators_ref.rsi_bank (float64 pandas, rounded to fp32).
 The reference functions executed are
@@ -58,6 +59,25 @@ SCALARS = ["total_trades", "win_rate", "profit_factor", "sharpe_ratio", "max_dra
            "return_pct", "avg_trade_duration", "risk_reward_ratio"]
 
 
+# other optimisation goals (config.json evolution.optimization_goals) x the dict the score is taken on
+# (False: calculate_metrics' dict, the composition of cross_validate_strategy; True: calculate_advanced_metrics' dict,
+# the composition of evaluate_strategy :545-557)
+ALT_GOALS = [
+    ({"primary": "return_pct", "secondary": ["win_rate", "expectancy"]}, True),
+    ({"primary": "return_pct", "secondary": ["win_rate", "expectancy"]}, False),       # expectancy absent: factor 1
+    ({"primary": "sortino_ratio", "secondary": ["max_drawdown"]}, True),
+    ({"primary": "sortino_ratio", "secondary": ["max_drawdown"]}, False),              # unknown key: 0
+    ({"primary": "expectancy", "secondary": ["profit_factor", "no_such_metric"]}, True),
+    ({"primary": "total_trades", "secondary": []}, False),
+    ({"primary": "average_loss", "secondary": ["max_drawdown", "win_rate"]}, False),
+    ({"primary": "calmar_ratio", "secondary": ["expectancy"]}, True),
+    ({"primary": "profit_per_day", "secondary": ["win_rate"], "constraints": {"min_trades_per_day": 20}}, True),
+    ({"primary": "largest_profit", "secondary": ["max_drawdown"]}, False),
+    ({"primary": "recovery_factor", "secondary": []}, True),
+    ({"primary": "not_a_metric", "secondary": ["win_rate"]}, True),
+]
+
+
 def jsonable(x):
     x = float(x)
     if math.isinf(x):
@@ -87,6 +107,11 @@ def make_sim():
             m = metrics_cls.calculate_metrics(trades)                            # REFERENCE
             score = ses._calculate_strategy_score(m)                             # REFERENCE
             adv = metrics_cls.calculate_advanced_metrics(m)                      # REFERENCE (:231-319)
+            alt = []
+            for g, on_advanced in ALT_GOALS:                                     # REFERENCE (:579-633), other goal sets
+                ses.optimization_goals = g
+                alt.append(jsonable(ses._calculate_strategy_score(adv if on_advanced else m)))
+            ses.optimization_goals = goals
             key = f"{name}_{sym}"
             arrays[f"bar_{key}"] = np.array([ts_to_bar[t["timestamp"]] for t in trades], dtype=np.int64)
             arrays[f"sell_{key}"] = np.array([t["side"] == "sell" for t in trades], dtype=np.bool_)
@@ -98,12 +123,13 @@ def make_sim():
             arrays[f"daily_{key}"] = np.array([daily[k] for k in sorted(daily)], dtype=np.float64)
             cases.append({"key": key, "name": name, "symbol": sym, "params": params,
                           "metrics": {k: jsonable(m[k]) for k in SCALARS}, "score": jsonable(score),
-                          "advanced": {k: jsonable(adv[k]) for k in simulate_ref.ADVANCED_KEYS},
+                          "advanced": {k: jsonable(adv[k]) for k in simulate_ref.ADVANCED_KEYS}, "alt_scores": alt,
                           "n_records": len(trades)})
             print(f"{key:28s} records={len(trades):5d} score={float(score):.6g}")
     np.savez_compressed(OUT / "sim_cases.npz", **arrays)
     (OUT / "sim_cases.json").write_text(json.dumps(
         {"n_bars": N_BARS, "periods": PERIODS, "minute0": synth.EPOCH_2024_MINUTES, "goals": goals,
+         "alt_goals": [{"goals": g, "advanced": a} for g, a in ALT_GOALS],
          "cases": cases}, indent=1))
 
 
@@ -320,8 +346,60 @@ def make_cv():
     (OUT / "cv_reference.json").write_text(json.dumps(out, indent=1))
 
 
+def ra_results():
+    """A small set of backtest result documents in the shape StrategyTester.save_results writes
+    (backtesting/strategy_tester.py:432-458): ties, a loss-maker, missing keys, a zero initial balance."""
+    def doc(strategy, symbol, interval, ib, fb, trades, wr, pf, sh, dd):
+        return {"strategy": strategy, "symbol": symbol, "interval": interval, "start_date": "2024-01-01T00:00:00",
+                "end_date": "2024-02-01T00:00:00",
+                "stats": {"initial_balance": ib, "final_balance": fb, "total_trades": trades, "win_rate": wr,
+                          "profit_factor": pf, "sharpe_ratio": sh, "max_drawdown_pct": dd}}
+    docs = [doc("AI_Social_Strategy", "BTCUSDC", "1h", 10000.0, 11234.5, 42, 57.14, 1.62, 1.1, 6.3),
+            doc("AI_Social_Strategy", "ETHUSDC", "1h", 10000.0, 9321.25, 18, 38.9, 0.71, -0.8, 11.2),
+            doc("AI_Social_Strategy", "BTCUSDC", "5m", 10000.0, 11234.5, 310, 51.0, 1.08, 0.4, 9.9),     # return tie with #0
+            doc("Baseline", "SOLUSDC", "1m", 5000.0, 5000.0, 0, 0, 0, 0, 0),
+            doc("Baseline", "BTCUSDC", "1h", 0, 120.0, 3, 66.7, 2.5, 0.2, 1.0),                          # zero initial balance
+            doc("AI_Social_Strategy", "ETHUSDC", "15m", 20000.0, 26000.0, 77, 61.0, 2.2, 1.9, 4.4)]
+    docs.append({"symbol": "XRPUSDC", "stats": {"final_balance": 50.0}})                                  # missing keys
+    docs.append({"strategy": "NoStats", "symbol": "ADAUSDC", "interval": "1d"})                           # no stats at all
+    return docs
+
+
+def make_ra():
+    """Reference ResultAnalyzer (backtesting/result_analyzer.py:23-72, :226-328): the documents above written as
+    result files, then load_results / get_available_results / filter_results / generate_summary_report executed."""
+    import tempfile
+    ref_runner.strategy_tester()          # imports the reference's `backtesting` package behind the ta / plotting stubs
+    from backtesting.result_analyzer import ResultAnalyzer
+    d = Path(tempfile.mkdtemp(prefix="b200bt_ra_"))
+    docs = ra_results()
+    for i, doc in enumerate(docs):
+        (d / f"result_{i:02d}.json").write_text(json.dumps(doc))
+    (d / "broken.json").write_text("{not json")
+    ra = ResultAnalyzer(str(d))
+    avail = sorted(ra.get_available_results(), key=lambda r: r["file_path"])
+    strip = lambda rs: [dict(r, file_path=Path(r["file_path"]).name) for r in rs]
+    by_name = lambda rs: sorted(Path(r["file_path"]).name for r in rs)
+    filters = [dict(symbol="BTCUSDC"), dict(strategy="Baseline"), dict(interval="1h", min_trades=10),
+               dict(symbol="ETHUSDC", interval="15m"), dict(min_trades=1), dict(strategy="nope")]
+    summary = ra.generate_summary_report(avail)
+    for k in ("strategies", "symbols", "intervals"):
+        summary[k] = sorted(summary[k])
+    summary["best_result"] = strip([summary["best_result"]])[0]
+    summary["worst_result"] = strip([summary["worst_result"]])[0]
+    for r in summary["results"]:
+        r["file_path"] = Path(r["file_path"]).name
+    out = {"documents": docs, "available": strip(avail),
+           "filters": [{"criteria": f, "files": by_name(ra.filter_results(**f))} for f in filters],
+           "summary": summary, "summary_empty": ra.generate_summary_report([]),
+           "load_missing": ra.load_results(str(d / "does_not_exist.json")),
+           "load_first": ra.load_results(str(d / "result_00.json"))}
+    (OUT / "ra_reference.json").write_text(json.dumps(out, indent=1))
+    print("RA:", len(avail), "results; best", summary["best_result"]["file_path"], "worst", summary["worst_result"]["file_path"])
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sim", "ga", "mc", "bt", "pf", "cv"]
+    which = sys.argv[1:] or ["sim", "ga", "mc", "bt", "pf", "cv", "ra"]
     if "sim" in which:
         make_sim()
     if "ga" in which:
@@ -334,3 +412,5 @@ if __name__ == "__main__":
         make_pf()
     if "cv" in which:
         make_cv()
+    if "ra" in which:
+        make_ra()

@@ -34,6 +34,29 @@ blob = torch.tensor([ga.best_fitness, float(sum(ga.fitness_scores))], dtype=torc
 out = [torch.zeros_like(blob) for _ in range(world)]
 dist.all_gather(out, blob)
 assert all(torch.equal(o, out[0]) for o in out)
+# ranks that disagree on the population, or a rank whose local evaluation throws, fail TOGETHER (no silent mixing of
+# unrelated fitness values, no rank left waiting in the collective)
+from ai_crypto_trader_b200.dist import PopulationMismatch, broadcast_seed
+try:
+    fit.batch(synth.random_population(6, seed=100 + rank))
+    raise SystemExit("different populations were not detected")
+except PopulationMismatch:
+    pass
+def flaky(pop):
+    if rank == 1:
+        raise ValueError("boom")
+    return np.zeros(len(pop))
+try:
+    ShardedFitness(flaky).batch(synth.random_population(6, seed=1))
+    raise SystemExit("a failing rank was not reported")
+except RuntimeError as e:
+    assert "rank(s) [1]" in str(e), str(e)
+assert fit.batch(synth.random_population(5, seed=3)) == local_eval(synth.random_population(5, seed=3)).tolist()   # still usable
+seeds = [broadcast_seed(None), broadcast_seed(77 + rank)]
+blob = torch.tensor(seeds, dtype=torch.int64)
+out = [torch.zeros_like(blob) for _ in range(world)]
+dist.all_gather(out, blob)
+assert all(torch.equal(o, out[0]) for o in out) and seeds[1] == 77
 # Monte-Carlo shards: contiguous path ranges, one gather, every rank ends with the full arrays in path order
 from ai_crypto_trader_b200.dist import gather_paths
 for n in (1, 2, 9, 64):

@@ -106,6 +106,29 @@ def test_sweep_matches_reference_fixtures(torch_cuda, sim_golden):
     np.testing.assert_allclose(fitness, want_fit, rtol=1e-9, atol=1e-12)
 
 
+def test_sweep_other_optimisation_goals_match_reference_scores(torch_cuda, sim_golden):
+    """The kernels' score rule under other goal sets (any scalar key as the primary metric, `expectancy` as a secondary
+    one, unknown keys) on the plain and on the advanced metrics dict: the reference's own scores (`alt_scores`)."""
+    from ai_crypto_trader_b200.sweep import MarketData, PopulationSweep
+    meta, arrays = sim_golden
+    syms = sorted({c["symbol"] for c in meta["cases"]})
+    ohlcv = np.zeros((5, len(syms), meta["n_bars"]), dtype=np.float32)
+    for j, s in enumerate(syms):
+        ohlcv[3, j] = arrays[f"close_{s}"]
+    market = MarketData(ohlcv, minute0=meta["minute0"])
+    names = list(dict.fromkeys(c["name"] for c in meta["cases"]))
+    by_name = {c["name"]: c["params"] for c in meta["cases"]}
+    population = [dict(by_name[nm]) for nm in names]
+    for g, alt in enumerate(meta["alt_goals"]):
+        sweep = PopulationSweep(market, rsi_periods=meta["periods"], optimization_goals=alt["goals"],
+                                score_on_advanced=alt["advanced"])
+        sweep.evaluate(population)
+        score = sweep.lane_stats()["score"]
+        for c in meta["cases"]:
+            got, want = score[names.index(c["name"]), syms.index(c["symbol"])], unjson(c["alt_scores"][g])
+            assert got == pytest.approx(want, rel=1e-9, abs=1e-12) or (np.isnan(got) and np.isnan(want)), (alt, c["key"], got, want)
+
+
 @pytest.mark.parametrize("n_bars,pop,n_sym", [(1, 4, 1), (31, 8, 2), (33, 8, 1), (1000, 64, 3), (50001, 96, 2)])
 def test_sweep_vs_c_oracle_random_populations(torch_cuda, n_bars, pop, n_sym):
     from ai_crypto_trader_b200 import _lib, synth

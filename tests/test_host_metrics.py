@@ -25,6 +25,10 @@ def test_metrics_and_score_match_reference(sim_golden):
         adv = StrategyPerformanceMetrics.calculate_advanced_metrics(m)
         for name, want in c["advanced"].items():
             assert float(adv[name]) == unjson(want), (key, name)
+        for g, alt in enumerate(meta["alt_goals"]):             # other goal sets, plain / advanced dict
+            ses2 = StrategyEvaluationSystem(config={"evolution": {"optimization_goals": alt["goals"]}})
+            got, want = float(ses2._calculate_strategy_score(adv if alt["advanced"] else m)), unjson(c["alt_scores"][g])
+            assert got == want or (np.isnan(got) and np.isnan(want)), (key, alt)
         assert "max_consecutive_wins" not in adv              # the metrics dict carries no 'trades' (:267)
         streaks = StrategyPerformanceMetrics.calculate_advanced_metrics(dict(m, trades=recs))
         if recs and m["total_trades"] > 0:

@@ -102,3 +102,28 @@ def test_c_oracle_calendar_gap_matches_python_restatement(sim_golden):
     assert int(st["n_days"]) == len(m["daily_returns"])
     assert st["sharpe_ratio"] == pytest.approx(float(m["sharpe_ratio"]), rel=1e-10)
     assert st["score"] == pytest.approx(float(simulate_ref.strategy_score(m, meta["goals"])), rel=1e-10)
+
+
+def _same(got, want):
+    return got == pytest.approx(want, rel=1e-10, abs=1e-12) or (np.isnan(got) and np.isnan(want)) or got == want
+
+
+def test_other_optimisation_goals_match_reference_scores(sim_golden):
+    """_calculate_strategy_score under other goal sets, on the plain and on the advanced metrics dict (fixture
+    `alt_scores` = the reference's own outputs): the C oracle's score rule and the Python restatement."""
+    meta, arrays = sim_golden
+    for g, alt in enumerate(meta["alt_goals"]):
+        cfg = sim_oracle.config_of(meta["minute0"], 1, alt["goals"], advanced=alt["advanced"])
+        for case in meta["cases"]:
+            close, rsi = _case_inputs(meta, arrays, case)
+            want = unjson(case["alt_scores"][g])
+            st, _, _ = sim_oracle.lane(close, rsi, case["params"], cfg)
+            assert _same(float(st["score"]), want), (alt, case["key"], float(st["score"]), want)
+    case = meta["cases"][1]
+    close, rsi = _case_inputs(meta, arrays, case)
+    pts = simulate_ref.market_points(close, rsi, "SYN000USDT", meta["minute0"])
+    m = simulate_ref.calculate_metrics(simulate_ref.simulate_trades(dict(case["params"]), pts))
+    adv = simulate_ref.calculate_advanced_metrics(m)
+    for g, alt in enumerate(meta["alt_goals"]):
+        got = float(simulate_ref.strategy_score(adv if alt["advanced"] else m, alt["goals"]))
+        assert _same(got, unjson(case["alt_scores"][g])), alt

@@ -12,7 +12,7 @@ for tool in memcheck racecheck; do
 done
 # ncu: families 3 and 1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'mc_paths|sel_|mc_moments' -c 12 -o $O/mc -f python tools/mc_bench.py --reps 1 > $O/ncu_mc.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'bank_kernel|macd|bollinger|extrema|vwap|nanfill|sma' -c 40 -o $O/ind -f python tools/indicator_bench.py > $O/ncu_ind.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'bank_kernel|macd|bollinger|extrema|vwap|nanfill|sma' -c 80 -o $O/ind -f python tools/indicator_bench.py --reps 1 --warmup 0 > $O/ncu_ind.log 2>&1
 python tools/mc_bench.py > $O/mc_bench.json 2>&1
 python tools/indicator_bench.py > $O/ind_bench.log 2>&1
 ls -la $O

@@ -14,14 +14,17 @@ from ai_crypto_trader_b200.sweep import MarketData, rsi_bank
 ap = argparse.ArgumentParser()
 ap.add_argument("--symbols", type=int, default=10)
 ap.add_argument("--bars", type=int, default=1_000_000)
+ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--warmup", type=int, default=3)
 a = ap.parse_args()
 m = MarketData(synth.synth_ohlcv(a.symbols, a.bars))
 o, h, l, c, v = m.open, m.high, m.low, m.close, m.volume
 peak = json.loads((Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json").read_text()).get("hbm_gbs", 6583.5) \
     if (Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json").exists() else 6583.5
 
-def timed(fn, reps=10):
-    for _ in range(3): fn()
+def timed(fn, reps=None):
+    reps = reps or a.reps
+    for _ in range(a.warmup): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
