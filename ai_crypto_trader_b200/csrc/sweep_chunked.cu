@@ -242,33 +242,44 @@ constexpr int LS_THREADS = B200BT_LS_THREADS;
 
 constexpr int LS_ZONE = 32;             // bars per zone-map block
 
-// Zone map: (min, max) of every 32-bar block of the price row and of each RSI row, NaNs ignored.  A machine whose
-// thresholds lie outside a block's range cannot fire in it, so the scan skips the block after four compares.
-// Layout [S][P + 1][ceil(N / 32)] float2, row 0 = price.
+// Zone map: (min, max) of every 32-bar block ("coarse") and of every 4-bar group ("fine") of the price row and of each
+// RSI row, NaNs ignored.  A machine whose thresholds lie outside a block's range cannot fire in it: the scan skips a
+// 32-bar block after four compares when no machine of the warp can fire, and inside a block it tests each 4-bar group
+// against the precomputed range (two 8-byte loads, four compares) instead of folding the eight values itself.
+// Layout: coarse [S][P + 1][ceil(N / 32)] float2, then fine [S][P + 1][ceil(N / 128) * 32] float2; row 0 = price.
 __global__ void __launch_bounds__(256)
 zone_map_kernel(const float* __restrict__ price, int64_t ld_price, const float* __restrict__ rsi, int64_t ld_rsi, int P,
-                int64_t N, int64_t n_blocks, float2* __restrict__ zones) {
+                int64_t N, int64_t n_blocks, float2* __restrict__ zones, float2* __restrict__ fine, int64_t n_fine) {
     const int row = blockIdx.y % (P + 1), sym = blockIdx.y / (P + 1);
     const float* __restrict__ src = row == 0 ? price + (int64_t)sym * ld_price : rsi + ((int64_t)sym * P + row - 1) * ld_rsi;
     float2* __restrict__ dst = zones + ((int64_t)sym * (P + 1) + row) * n_blocks;
+    float2* __restrict__ fdst = fine + ((int64_t)sym * (P + 1) + row) * n_fine;
     const int lane = threadIdx.x & 31;
-    for (int64_t blk = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); blk < n_blocks; blk += (int64_t)gridDim.x * 8) {
+    // (the fine rows are padded to whole 128-bar tiles: blocks past the series hold NaN, every compare false)
+    for (int64_t blk = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); blk * (LS_ZONE / 4) < n_fine; blk += (int64_t)gridDim.x * 8) {
         const int64_t t = blk * LS_ZONE + lane;
         const float v = t < N ? __ldg(src + t) : __int_as_float(0x7fc00000);
         float lo = v, hi = v;
 #pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
+        for (int m = 1; m < 4; m <<= 1) {
             lo = fminf(lo, __shfl_xor_sync(FULL, lo, m));
             hi = fmaxf(hi, __shfl_xor_sync(FULL, hi, m));
         }
-        if (lane == 0) dst[blk] = make_float2(lo, hi);    // all-NaN block: (NaN, NaN), every compare false
+        if ((lane & 3) == 0) fdst[blk * (LS_ZONE / 4) + (lane >> 2)] = make_float2(lo, hi);
+#pragma unroll
+        for (int m = 4; m < 32; m <<= 1) {
+            lo = fminf(lo, __shfl_xor_sync(FULL, lo, m));
+            hi = fmaxf(hi, __shfl_xor_sync(FULL, hi, m));
+        }
+        if (lane == 0 && blk < n_blocks) dst[blk] = make_float2(lo, hi);    // all-NaN block: (NaN, NaN), every compare false
     }
 }
 
 struct LaneScanArgs {
     const float* price; int64_t ld_price;
     const float* rsi; int64_t ld_rsi;
-    const float2* zones; int64_t n_zone_blocks;   // zone map or NULL
+    const float2* zones; int64_t n_zone_blocks;   // zone map (coarse) or NULL
+    const float2* fine; int64_t n_fine;           // 4-bar ranges (with zones)
     int P, S; int64_t N;
     const b200bt_individual* indiv; const int32_t* order; int pop; int K; int warm;
     uint2* pool; int pool_blocks; int* next; unsigned* alloc;
@@ -292,17 +303,30 @@ __global__ void lane_tables_kernel(int pop, int K, b200bt_chunk_item* __restrict
 #ifndef B200BT_LS_MIN_BLOCKS
 #define B200BT_LS_MIN_BLOCKS 4
 #endif
-template <bool VEC16>
+__host__ __device__ constexpr int64_t zone_fine_count(int64_t N) { return ((N + LS_T - 1) / LS_T) * (LS_T / 4); }
+// float2 entries of the coarse part of a zone map, padded to an even count so that the fine part is 16-byte aligned
+__host__ __device__ constexpr int64_t zone_coarse_count(int P, int S, int64_t N) {
+    return (((int64_t)S * (P + 1) * ((N + LS_ZONE - 1) / LS_ZONE)) + 1) & ~(int64_t)1;
+}
+
+// ZONES: the zone map is staged with the tile; a 32-bar block is skipped when no machine of the WARP can fire in it
+// (a warp-uniform branch: a machine that could skip alone would wait for its neighbours anyway), and a 4-bar group is
+// tested against its precomputed range.  Without a zone map the group's range is folded from its eight values.
+template <bool VEC16, bool ZONES>
 __global__ void __launch_bounds__(LS_THREADS, B200BT_LS_MIN_BLOCKS)
 lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (see sweep.cu)
-    extern __shared__ __align__(16) float ls_tile[];   // [2][P + 1][LS_STRIDE], then zone stages [2][P + 1][LS_T / 32] float2
+    // [2][P + 1][LS_STRIDE] floats, then (ZONES) coarse ranges [2][P + 1][LS_T / 32] and fine ranges [2][P + 1][LS_T / 4] float2
+    extern __shared__ __align__(16) float ls_tile[];
     const int rows = A.P + 1;
     constexpr int ZB = LS_T / LS_ZONE;                  // zone blocks per tile
+    constexpr int FG = LS_T / 4;                        // 4-bar groups per tile
     float2* const ls_zone = reinterpret_cast<float2*>(ls_tile + (size_t)2 * rows * LS_STRIDE);
-    const float2* __restrict__ zsym = A.zones ? A.zones + (int64_t)sym_of_block(blockIdx.x, A.S) * rows * A.n_zone_blocks : nullptr;
+    float2* const ls_fine = ls_zone + (size_t)2 * rows * ZB;
     const int sym = (int)(blockIdx.x % (unsigned)A.S);
     const int c = (int)((blockIdx.x / (unsigned)A.S) % (unsigned)A.K);
     const int blk = (int)(blockIdx.x / ((unsigned)A.S * (unsigned)A.K));
+    const float2* __restrict__ zsym = ZONES ? A.zones + (int64_t)sym * rows * A.n_zone_blocks : nullptr;
+    const float2* __restrict__ fsym = ZONES ? A.fine + (int64_t)sym * rows * A.n_fine : nullptr;
     const int k = blk * LS_THREADS + (int)threadIdx.x;
     const bool active = k < A.pop;
     const int ind = active ? (A.order ? A.order[k] : k) : 0;
@@ -347,13 +371,20 @@ lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (s
                 dst0[row * LS_STRIDE + col] = (t0 + col < n) ? __ldg(src) : qnan;
             }
         }
-        if (zsym) {
+        if (ZONES) {
             float2* zdst = ls_zone + (size_t)stage * rows * ZB;
             for (int e = threadIdx.x; e < rows * ZB; e += LS_THREADS) {
                 const int row = e / ZB, zb = e - row * ZB;
-                const int64_t blk = (int64_t)tl * ZB + zb;
-                if (blk < A.n_zone_blocks) cp_async8(zdst + e, zsym + (int64_t)row * A.n_zone_blocks + blk);
+                const int64_t zblk = (int64_t)tl * ZB + zb;
+                if (zblk < A.n_zone_blocks) cp_async8(zdst + e, zsym + (int64_t)row * A.n_zone_blocks + zblk);
                 else zdst[e] = make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+            }
+            // fine ranges: FG float2 per row and tile = FG / 2 16-byte pieces (rows are padded to whole tiles)
+            float2* fdst = ls_fine + (size_t)stage * rows * FG;
+            for (int e = threadIdx.x; e < rows * (FG / 2); e += LS_THREADS) {
+                const int row = e / (FG / 2), piece = e - row * (FG / 2);
+                cp_async16(reinterpret_cast<float*>(fdst + row * FG + piece * 2),
+                           reinterpret_cast<const float*>(fsym + (int64_t)row * A.n_fine + (int64_t)tl * FG + piece * 2));
             }
         }
         cp_async_commit();
@@ -420,21 +451,37 @@ lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (s
         cp_async_wait<1>();
         __syncthreads();
         const int t0 = tl * LS_T;
+        const unsigned wmask = __ballot_sync(FULL, active);
         if (active) {
             if (t0 == T0) { A.seg_in[seg] = make_int2(pos, pos != 0 ? entry_bar : -1); rec = true; }
             const float4* __restrict__ pp = reinterpret_cast<const float4*>(ls_tile + (size_t)stage * rows * LS_STRIDE);
             const float4* __restrict__ rr = reinterpret_cast<const float4*>(ls_tile + ((size_t)stage * rows + 1 + iv.rsi_row) * LS_STRIDE);
-            const float2* __restrict__ zp = ls_zone + (size_t)stage * rows * ZB;
-            const float2* __restrict__ zr = zp + (1 + iv.rsi_row) * ZB;
+            if (ZONES) {
+                const float2* __restrict__ zp = ls_zone + (size_t)stage * rows * ZB;
+                const float2* __restrict__ zr = zp + (1 + iv.rsi_row) * ZB;
+                const float2* __restrict__ fp = ls_fine + (size_t)stage * rows * FG;
+                const float2* __restrict__ fr = fp + (1 + iv.rsi_row) * FG;
 #pragma unroll 1
-            for (int zb = 0; zb < ZB; ++zb) {
-                if (zsym) {
-                    // nothing can fire in a block whose (min, max) stay inside the machine's thresholds
+                for (int zb = 0; zb < ZB; ++zb) {
                     const float2 rz = zr[zb], pz = zp[zb];
-                    if (!((rz.x < rlo) | (rz.y > rhi) | (pz.x <= plo) | (pz.y >= phi))) continue;
-                }
+                    const bool can = (rz.x < rlo) | (rz.y > rhi) | (pz.x <= plo) | (pz.y >= phi);
+                    if (!__any_sync(wmask, can)) continue;
 #pragma unroll 2
-                for (int g = zb * (LS_ZONE / 4); g < (zb + 1) * (LS_ZONE / 4); ++g) {
+                    for (int g = zb * (LS_ZONE / 4); g < (zb + 1) * (LS_ZONE / 4); ++g) {
+                        const float2 rm = fr[g], pm = fp[g];
+                        if ((rm.x < rlo) | (rm.y > rhi) | (pm.x <= plo) | (pm.y >= phi)) {
+                            const float4 p = pp[g], r = rr[g];
+                            const int t = t0 + g * 4;
+                            step(p.x, r.x, t);
+                            step(p.y, r.y, t + 1);
+                            step(p.z, r.z, t + 2);
+                            step(p.w, r.w, t + 3);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 2
+                for (int g = 0; g < FG; ++g) {
                     const float4 p = pp[g], r = rr[g];
                     // any bar of the four beyond a threshold?  (fminf / fmaxf drop NaNs, as the per-bar compares do)
                     const float r_min = fminf(fminf(r.x, r.y), fminf(r.z, r.w)), r_max = fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w));
@@ -1109,20 +1156,22 @@ extern "C" int b200bt_sweep_chunked(const float* price, int64_t ld_price, const 
 
 extern "C" int64_t b200bt_zone_map_floats(int P, int S, int64_t N) {
     if (P <= 0 || S <= 0 || N <= 0) return 0;
-    return (int64_t)S * (P + 1) * ((N + LS_ZONE - 1) / LS_ZONE) * 2;
+    return (zone_coarse_count(P, S, N) + (int64_t)S * (P + 1) * zone_fine_count(N)) * 2;
 }
 
 extern "C" int b200bt_zone_map(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S, int64_t N,
                                float* zones, b200bt_stream_t stream) {
     B200BT_REQUIRE(price && rsi && zones, B200BT_EINVAL, "zone_map: null pointer");
     B200BT_REQUIRE(P > 0 && S > 0 && N > 0 && ld_price >= N && ld_rsi >= N, B200BT_EINVAL, "zone_map: bad sizes");
-    B200BT_REQUIRE(((uintptr_t)zones & 7) == 0, B200BT_EINVAL, "zone_map: output must be 8-byte aligned");
+    B200BT_REQUIRE(((uintptr_t)zones & 15) == 0, B200BT_EINVAL, "zone_map: output must be 16-byte aligned");
     int rc = check_device();
     if (rc) return rc;
-    const int64_t nb = (N + LS_ZONE - 1) / LS_ZONE;
-    const unsigned gx = (unsigned)min((int64_t)1024, (nb + 7) / 8);
+    const int64_t nb = (N + LS_ZONE - 1) / LS_ZONE, nf = zone_fine_count(N);
+    const unsigned gx = (unsigned)min((int64_t)1024, (nf / (LS_ZONE / 4) + 7) / 8);
+    float2* coarse = (float2*)zones;
+    float2* fine = coarse + zone_coarse_count(P, S, N);      // 16-byte aligned (even number of float2 in front)
     zone_map_kernel<<<dim3(gx, (unsigned)(S * (P + 1))), 256, 0, (cudaStream_t)stream>>>(price, ld_price, rsi, ld_rsi, P, N, nb,
-                                                                                       (float2*)zones);
+                                                                                       coarse, fine, nf);
     B200BT_LAUNCH_CHECK("zone_map launch");
     return B200BT_OK;
 }
@@ -1144,8 +1193,14 @@ extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const fl
     if (rc) return rc;
     B200BT_REQUIRE((int64_t)pop * K * S < (1ll << 31), B200BT_ELIMIT, "sweep_tiled: too many chunks");
     B200BT_REQUIRE(K == 1 || N / K >= SW_GROUP, B200BT_EINVAL, "sweep_tiled: chunks shorter than %d bars", SW_GROUP);
-    const size_t smem = (size_t)2 * (P + 1) * (LS_STRIDE * sizeof(float) + (LS_T / LS_ZONE) * sizeof(float2));
+    // shared-memory tile: values, and with a zone map the coarse and fine ranges; a bank too wide for the tile with
+    // ranges is swept without them
+    const size_t smem_plain = (size_t)2 * (P + 1) * LS_STRIDE * sizeof(float);
+    const size_t smem_zones = smem_plain + (size_t)2 * (P + 1) * (LS_T / LS_ZONE + LS_T / 4) * sizeof(float2);
+    if (zones_or_null && smem_zones > 72 * 1024) zones_or_null = nullptr;
+    const size_t smem = zones_or_null ? smem_zones : smem_plain;
     B200BT_REQUIRE(smem <= 72 * 1024, B200BT_ELIMIT, "sweep_tiled: RSI bank of %d periods exceeds the shared-memory tile", P);
+    B200BT_REQUIRE(zones_or_null == nullptr || ((uintptr_t)zones_or_null & 15) == 0, B200BT_EINVAL, "sweep_tiled: zone map must be 16-byte aligned");
     B200BT_REQUIRE(workspace_bytes >= b200bt_sweep_tiled_workspace_bytes(pool_blocks, S, pop, K), B200BT_EINVAL,
                    "sweep_tiled: workspace too small");
     B200BT_REQUIRE(((uintptr_t)workspace & 15) == 0, B200BT_EINVAL, "sweep_tiled: workspace must be 16-byte aligned");
@@ -1166,11 +1221,13 @@ extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const fl
     LaneScanArgs L;
     L.price = price; L.ld_price = ld_price; L.rsi = rsi; L.ld_rsi = ld_rsi; L.P = P; L.S = S; L.N = N;
     L.zones = (const float2*)zones_or_null; L.n_zone_blocks = (N + LS_ZONE - 1) / LS_ZONE;
+    L.fine = zones_or_null ? L.zones + zone_coarse_count(P, S, N) : nullptr; L.n_fine = zone_fine_count(N);
     L.indiv = indiv; L.order = order; L.pop = pop; L.K = K; L.warm = warm;
     L.pool = w.pool; L.pool_blocks = pool_blocks; L.next = w.next; L.alloc = w.alloc;
     L.seg_first = w.seg_first; L.seg_count = w.seg_count; L.seg_in = w.seg_in; L.seg_out = w.seg_out; L.overflow = w.overflow;
     const bool vec16 = (((uintptr_t)price | (uintptr_t)rsi) & 15) == 0 && ld_price % 4 == 0 && ld_rsi % 4 == 0;
-    auto kern = vec16 ? lane_scan_kernel<true> : lane_scan_kernel<false>;
+    auto kern = zones_or_null ? (vec16 ? lane_scan_kernel<true, true> : lane_scan_kernel<false, true>)
+                              : (vec16 ? lane_scan_kernel<true, false> : lane_scan_kernel<false, false>);
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e, "sweep_tiled: cudaFuncSetAttribute");
     const int64_t blocks = (int64_t)((pop + LS_THREADS - 1) / LS_THREADS) * K * S;

@@ -373,8 +373,7 @@ class TilePlan:
         pred = predicted_events(population, n_bars) if pred is None else np.asarray(pred, dtype=np.float64)
         # threads of a CTA wait for each other at every tile: neighbours should cost the same ("cost"), which
         # matters more than sharing RSI rows ("period": the fused kernel's order)
-        self.order = (np.argsort(-pred, kind="stable").astype(np.int32) if order_by == "cost"
-                      else evaluation_order(population))
+        self.order = tile_order(population, pred, order_by, self.THREADS)
         # every segment owns at least one block, and a repaired segment abandons its first chain
         self.pool_blocks = int(pool_scale * pred.sum() * n_symbols / 256) + 2 * self.n_seg * n_symbols + 1024
         if pool_blocks is not None:
@@ -387,6 +386,34 @@ class TilePlan:
             self.workspace = None if workspace is DEFERRED else torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
         self.invalid = torch.zeros((pop, n_symbols), dtype=torch.uint8, device=device)
         self.overflow = _pinned_flag()
+
+
+def tile_order(population: List[Dict], pred: np.ndarray, order_by: str, threads: int) -> np.ndarray:
+    """Dispatch order of the thread-per-lane scan: position k of the order goes to thread k % threads of CTA k // threads.
+      "cost"      most expensive first (neighbours cost the same; the round-1 default)
+      "period"    same RSI row adjacent, then most expensive first (evaluation_order)
+      "row"       same RSI row adjacent, rows by mean cost (most expensive first), inside a row by cost
+      "rowth"     same RSI row adjacent, inside a row by (oversold, overbought): a warp's machines fire on the same bars
+      "cost_row"  CTAs by cost (blocks of `threads` individuals in cost order), inside a CTA by (row, oversold, overbought)"""
+    n = len(population)
+    g = lambda key, default: np.array([float(p.get(key, default)) for p in population], dtype=np.float64)
+    if order_by == "cost":
+        return np.argsort(-pred, kind="stable").astype(np.int32)
+    if order_by == "period":
+        return evaluation_order(population)
+    row, lo, hi = g("rsi_period", 14).astype(np.int64), g("rsi_oversold", 30), g("rsi_overbought", 70)
+    if order_by in ("row", "rowth"):
+        mean_cost = np.zeros(int(row.max()) + 1)
+        for w in np.unique(row):
+            mean_cost[w] = pred[row == w].mean()
+        keys = (np.arange(n), -pred) if order_by == "row" else (np.arange(n), -hi, lo)
+        return np.lexsort(keys + (-mean_cost[row],)).astype(np.int32)
+    if order_by == "cost_row":
+        by_cost = np.argsort(-pred, kind="stable")
+        blk = np.empty(n, dtype=np.int64)
+        blk[by_cost] = np.arange(n) // threads
+        return np.lexsort((np.arange(n), -hi, lo, row, blk)).astype(np.int32)
+    raise ValueError(f"unknown order_by {order_by!r}")
 
 
 def evaluation_order(population: List[Dict]) -> np.ndarray:

@@ -33,6 +33,13 @@ POP_PER_GPU = 1024
 N_SYMBOLS = 10
 N_BARS = 1_000_000
 BYTES_PER_EVAL = 8  # price 4 B + RSI 4 B per (individual, symbol, bar), reference RSI rule
+# ncu figures of the dominant kernel per launch on the configs[1] workload (pop 1024 x 10 x 1M, seed-42 population), from
+# the committed `ncu --set full` capture named in "source"; "scan_share" = the kernel's share of the sweep's kernel time in
+# the committed launch list of this bench command.  Valid for exactly that workload (the kernels are deterministic).
+NCU_C2 = {
+    "tiled": {"warp_inst": 3.796e9, "threads_per_inst": 11.87, "dram_bytes": 5.222e9 + 1.006e9, "scan_share": 0.69,
+              "source": "profiles/r1_tiled_final_ncu.txt, profiles/r1_launches_v4.csv"},
+}
 
 
 def measured_hbm_peak():
@@ -89,24 +96,58 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------
-# reference arm: the reference's CPU algorithm (oracle port; the Python reference
-# itself cannot travel to the GPU box) on all host cores
+# CPU arms.  `--impl reference` and the inline `cpu_baseline` leg use ONE recipe (same pool, same sample shape, the
+# timer started after the pool is warm), so the two agree:
+#   kind "reference": the reference's own _simulate_trades + calculate_metrics + _calculate_strategy_score, imported
+#                     unmodified from oracle/_ref (placed there by oracle/make_ref.py in the build container; it
+#                     travels to the GPU box with the snapshot, where /root/reference does not exist)
+#   kind "port"     : the float64 Python restatement (oracle/simulate_ref.py) when oracle/_ref is not populated
+# plus the same algorithm as compiled C (oracle/sim_oracle.c) under the same pool: the strong CPU baseline.
 # --------------------------------------------------------------------------
 _REF_STREAMS = []   # market-data dict lists, built in the parent before the fork (shared copy-on-write)
+_REF_ARRAYS = []    # (close, rsi) fp32 rows of the same streams, for the C port
+REF_BARS = 250_000
+REF_LANES_PER_WORKER = 4
+
+
+def _ref_kind() -> str:
+    from oracle import make_ref
+    return "reference" if make_ref.available() else "port"
 
 
 def _ref_worker(job):
     stream, params, goals = job
+    if stream < 0:                 # pool warm-up: import the modules, touch the data
+        from oracle import make_ref, simulate_ref, sim_oracle   # noqa: F401
+        if make_ref.available():
+            make_ref.load()
+        sim_oracle.lib()
+        return 0.0, 0
+    from oracle import make_ref
+    if make_ref.available():
+        ses, metrics_cls, _ = make_ref.load()
+        ses.optimization_goals = goals
+        recs = ses._simulate_trades("bench", dict(params), _REF_STREAMS[stream])
+        m = metrics_cls.calculate_metrics(recs)
+        return float(ses._calculate_strategy_score(m)), len(recs)
     from oracle import simulate_ref
     recs = simulate_ref.simulate_trades(params, _REF_STREAMS[stream])
     m = simulate_ref.calculate_metrics(recs)
     return float(simulate_ref.strategy_score(m, goals)), len(recs)
 
 
+def _c_worker(job):
+    stream, plist = job
+    from oracle import sim_oracle
+    from ai_crypto_trader_b200 import synth
+    close, rsi = _REF_ARRAYS[stream]
+    out = sim_oracle.lanes(close, rsi, plist, sim_oracle.config_of(synth.EPOCH_2024_MINUTES, 1))
+    return float(out["score"].sum())
+
+
 def reference_sample(n_bars: int, lanes: int):
-    """Bounded sample of the workload: `lanes` individuals of the seed-42 population on
-    n_bars bars of symbol 0, their rsi_period folded onto two streams (7, 14) so the
-    prebuilt market-data dict lists stay small.  Returns the job list."""
+    """Bounded sample of the workload: `lanes` individuals of the seed-42 population on n_bars bars of symbol 0, their
+    rsi_period folded onto two streams (7, 14) so the prebuilt market-data dict lists stay small.  Returns the job list."""
     from ai_crypto_trader_b200 import synth
     from ai_crypto_trader_b200.sweep import DEFAULT_GOALS
     from oracle import indicators_ref, simulate_ref
@@ -115,74 +156,80 @@ def reference_sample(n_bars: int, lanes: int):
     periods = [7, 14]
     bank = indicators_ref.rsi_bank(close, periods)
     _REF_STREAMS.clear()
+    _REF_ARRAYS.clear()
     for row in bank:
         _REF_STREAMS.append(simulate_ref.market_points(close, row, "SYN000USDT", synth.EPOCH_2024_MINUTES))
+        _REF_ARRAYS.append((close, row))
     return [(i % 2, dict(p, rsi_period=periods[i % 2]), DEFAULT_GOALS) for i, p in enumerate(pop)]
+
+
+def run_cpu_pool(steps: int, warmup: int, c_port_steps: int = 0):
+    """-> (per-step seconds of the Python arm, evals per step, cores, sample text, kind, C-port dict or None)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    use = max(1, min(cores, 64))
+    lanes = use * REF_LANES_PER_WORKER
+    jobs = reference_sample(REF_BARS, lanes)
+    kind = _ref_kind()
+    times, c_port = [], None
+    with mp.get_context("fork").Pool(use) as pool:
+        pool.map(_ref_worker, [(-1, None, None)] * (2 * use), chunksize=1)         # warm: imports done in every worker
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            pool.map(_ref_worker, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+        if c_port_steps:
+            # the C port is ~200x faster per lane: full-length series, many more lanes, same pool
+            from ai_crypto_trader_b200 import synth
+            from oracle import indicators_ref
+            close = synth.synth_symbol(0, N_BARS)["close"]
+            _REF_ARRAYS.clear()
+            _REF_ARRAYS.extend((close, row) for row in indicators_ref.rsi_bank(close, [7, 14]))
+            pop = synth.random_population(use * 32, seed=42)
+            cjobs = [(w % 2, pop[w * 32:(w + 1) * 32]) for w in range(use)]
+    if c_port_steps:
+        with mp.get_context("fork").Pool(use) as pool:        # (forked after the full-length rows exist)
+            pool.map(_c_worker, cjobs, chunksize=1)
+            t0 = time.perf_counter()
+            for _ in range(c_port_steps):
+                pool.map(_c_worker, cjobs, chunksize=1)
+            dtc = (time.perf_counter() - t0) / c_port_steps
+        c_port = {"value": N_BARS * len(pop) / dtc, "unit": UNIT, "cores": use,
+                  "sample": f"{len(pop)} lanes x {N_BARS} bars per step, oracle/sim_oracle.c (-O2), {use} processes"}
+    what = ("the reference's own _simulate_trades + calculate_metrics + _calculate_strategy_score (oracle/_ref, unmodified)"
+            if kind == "reference" else "pure-Python float64 restatement of _simulate_trades + calculate_metrics + score (oracle/_ref not populated)")
+    sample = (f"{lanes} lanes x {REF_BARS} bars of configs[1] per step ({REF_LANES_PER_WORKER} lanes per worker, {use} processes; {what}; "
+              "market-data dicts prebuilt outside the timed region, pool warm before the timer starts)")
+    return times, REF_BARS * lanes, use, sample, kind, c_port
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    use = max(1, min(cores, 64))
-    n_bars = 250_000
-    lanes = use * 4
-    jobs = reference_sample(n_bars, lanes)
-    evals_per_step = n_bars * lanes
-    times = []
-    with mp.get_context("fork").Pool(use) as pool:
-        for it in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            pool.map(_ref_worker, jobs, chunksize=1)
-            dt = time.perf_counter() - t0
-            if it >= args.warmup:
-                times.append(dt)
+    times, evals_per_step, use, sample, kind, _ = run_cpu_pool(args.steps, args.warmup)
     total = sum(times)
     value = evals_per_step * len(times) / total
-    sample = f"{lanes} lanes x {n_bars} bars of configs[1] per step (pure-Python float64 restatement of _simulate_trades+calculate_metrics+score; market-data dicts prebuilt outside the timed region)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"GA fitness sweep pop={POP_PER_GPU}x{args.gpus} symbols={N_SYMBOLS} bars={N_BARS} (bounded sample)",
                    "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": use, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": use, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_inline(budget_s: float = 12.0):
-    """Rank-0, N=1 only: the oracle timed on the host cores on a bounded sample."""
-    import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    use = max(1, min(cores, 64))
-    n_bars = 200_000
-    lanes = use
-    jobs = reference_sample(n_bars, lanes)
-    t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(use) as pool:
-        pool.map(_ref_worker, jobs, chunksize=1)
-    dt = time.perf_counter() - t0
-    py = {"value": n_bars * lanes / dt, "unit": UNIT, "cores": use, "kind": "port",
-          "sample": f"{lanes} lanes x {n_bars} bars, pure-Python float64 restatement of the reference loop (its own speed class), {use} processes"}
-    # the same algorithm as compiled C (a much stronger CPU baseline than the reference's Python)
-    from oracle import sim_oracle
-    import numpy as np
-    from ai_crypto_trader_b200 import synth
-    from oracle import indicators_ref
-    close = synth.synth_symbol(0, N_BARS)["close"]
-    pop = synth.random_population(16, seed=42)
-    bank = indicators_ref.rsi_bank(close, [14])
-    cfg = sim_oracle.config_of(synth.EPOCH_2024_MINUTES, 1)
-    t0 = time.perf_counter()
-    sim_oracle.lanes(close, bank[0], pop, cfg)
-    dtc = time.perf_counter() - t0
-    py["c_port_single_core"] = {"value": N_BARS * len(pop) / dtc, "unit": UNIT, "cores": 1,
-                                "sample": f"{len(pop)} lanes x {N_BARS} bars, oracle/sim_oracle.c"}
+def cpu_baseline_inline():
+    """Rank-0, N=1 only: the CPU arms timed on the host cores on a bounded sample (same recipe as --impl reference)."""
+    times, evals_per_step, use, sample, kind, c_port = run_cpu_pool(steps=2, warmup=1, c_port_steps=2)
+    py = {"value": evals_per_step * len(times) / sum(times), "unit": UNIT, "cores": use, "kind": kind, "sample": sample}
+    py["c_port_64core"] = c_port
     # BASELINE configs[0] (the reference's own CPU-runnable case): StrategyTester.backtest_strategy on 10 000 bars of one
     # symbol, restated in Python with the LLM stubbed (oracle/tester_ref.py), single process like the reference
     from oracle import tester_ref
@@ -209,6 +256,131 @@ def configs0_frame():
                         index=pd.date_range("2024-01-01", periods=n, freq="min"))
 
 
+
+# --------------------------------------------------------------------------
+# parity of the timed population, and the rest of BASELINE.json's metric
+# --------------------------------------------------------------------------
+def parity_spot_check(sweep, my_pop, ohlcv, minute0, lanes=64):
+    """`lanes` (individual, symbol) lanes of the population that was just timed, spread over the shard and the symbols:
+    record count and trade hash (every entry / exit bar and side) bit-exact, score rel 1e-9, against oracle/sim_oracle.c
+    fed the float64-pandas RSI row (oracle/indicators_ref.py)."""
+    import numpy as np
+    from oracle import indicators_ref, sim_oracle
+    stats = sweep.lane_stats()
+    S = ohlcv.shape[1]
+    cfg = sim_oracle.config_of(minute0, 1)
+    idx = np.unique(np.linspace(0, len(my_pop) - 1, lanes).astype(int))
+    rows, bad = {}, 0
+    for j, i in enumerate(idx):
+        s = j % S
+        w = int(my_pop[i]["rsi_period"])
+        if (s, w) not in rows:
+            rows[(s, w)] = indicators_ref.rsi_bank(ohlcv[3, s], [w])[0]
+        want, _, _ = sim_oracle.lane(ohlcv[3, s], rows[(s, w)], my_pop[i], cfg)
+        got_score, want_score = float(stats["score"][i, s]), float(want["score"])
+        same_score = (got_score == want_score or (np.isnan(got_score) and np.isnan(want_score))
+                      or abs(got_score - want_score) <= 1e-9 * max(1.0, abs(want_score)))
+        if int(stats["n_records"][i, s]) != int(want["n_records"]) or int(stats["trade_hash"][i, s]) != int(want["trade_hash"]) or not same_score:
+            bad += 1
+    return {"lanes_checked": int(len(idx)), "mismatches": int(bad),
+            "what": "n_records + trade_hash bit-exact, score rel 1e-9 vs oracle/sim_oracle.c on the timed population (rank 0 shard)"}
+
+
+def run_extras(args, world, rank, dev, sweep, population, pop_local, timed_sweeps, barrier, evals_per_step_global):
+    """Keys beside the headline, every rank taking part (same collectives in the same order):
+      evolved_population_value  configs[1] throughput on the generation-3 population of a GA run (the GA drives the
+                                trade-record count, the sweep's cost driver, up)
+      ga_generation_s           configs[4]: population 10 000 x 50 symbols x 1M bars, individuals STRONG-sharded over the
+                                N ranks, one all-gather per generation, GA operators included
+      mc_c3_ms                  configs[2]: 1M GBM paths x 10 000 steps sharded over the N ranks incl. gather + statistics"""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ai_crypto_trader_b200 import synth
+    from ai_crypto_trader_b200.dist import ShardedFitness, gather_paths, shard_bounds
+    from ai_crypto_trader_b200.genetic_algorithm import DeviceGeneticAlgorithm, GeneticAlgorithm
+    from ai_crypto_trader_b200.monte_carlo import PathEngine, risk_statistics
+    from ai_crypto_trader_b200.sweep import MarketData, PopulationSweep, decode_population
+    out = {}
+
+    def wall(fn):
+        """fn() between two barriers; seconds, max over ranks."""
+        barrier()
+        t0 = time.perf_counter()
+        r = fn()
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), r
+
+    # ---- configs[1] on an evolved population ---------------------------------------------------------
+    fit = ShardedFitness(sweep.evaluate, device=dev)
+    ga = GeneticAlgorithm(synth.param_ranges(), fit, population_size=len(population), generations=3, random_seed=42)
+    ga.run(seeded_individuals=population)              # reference operators (host), fitness = the sharded sweep
+    evolved = ga.population
+    mine = evolved[rank * pop_local:(rank + 1) * pop_local]
+    indiv = torch.from_numpy(decode_population(mine, sweep.period_row).view(np.uint8)).to(dev)
+    ms_total, ms_k, _, _ = timed_sweeps(indiv, None, sweep.plan(mine))
+    records = float(sweep.lane_stats()["n_records"].sum())
+    out["evolved_population_value"] = {
+        "value": evals_per_step_global * args.steps / (ms_total * 1e-3), "unit": UNIT, "ms_per_step": ms_total / args.steps,
+        "generation": 3, "records_rank0": records,
+        "note": "same workload and timing as `value`, population = generation 3 of GeneticAlgorithm(seed 42) started from the timed random population"}
+
+    # ---- configs[4]: one GA generation at population 10 000 x 50 symbols x 1M bars --------------------
+    S5, POP5, GENS = 50, 10_000, 3
+    close = np.stack([synth.synth_symbol(s, args.bars)["close"] for s in range(S5)])
+    market5 = MarketData.from_close(torch.from_numpy(close).to(dev))
+    del close
+    sweep5 = PopulationSweep(market5, mode=args.mode)
+    fit5 = ShardedFitness(sweep5.evaluate, device=dev)
+    ga5 = DeviceGeneticAlgorithm(synth.param_ranges(), fit5, population_size=POP5, generations=GENS, random_seed=42)
+    ga5.initialize_population()
+    lo, hi, _ = shard_bounds(POP5, world, rank)
+    ga5.evaluate_population()                          # untimed: workspace allocation, zone map (built on the second sweep)
+    ga5.evaluate_population()
+    gen_s, sweep_s = [], []
+    for gen in range(GENS + 1):
+        def one_generation():
+            t0 = time.perf_counter()
+            ga5.evaluate_population()                  # this rank's shard through the sweep + the all-gather
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            ga5.evolve_generation(gen + 1)             # selection / crossover / mutation (device, Philox)
+            torch.cuda.synchronize()
+            return t1 - t0
+        t, ts = wall(one_generation)
+        gen_s.append(t)
+        sweep_s.append(ts)
+    out["ga_generation_s"] = {
+        "random": gen_s[0], "gen3": gen_s[GENS], "per_generation": gen_s, "fitness_sweep_s_rank0": sweep_s,
+        "population": POP5, "symbols": S5, "bars": args.bars, "individuals_per_rank": hi - lo,
+        "what": "wall seconds of one generation = fitness of every individual (sharded sweep, one all-gather of 8 B per individual) + GA operators (DeviceGeneticAlgorithm), barrier on both sides, max over ranks",
+        "scaling": "strong"}
+    del ga5, fit5, sweep5, market5
+    torch.cuda.empty_cache()
+
+    # ---- configs[2]: Monte-Carlo risk, 1M GBM paths x 10 000 steps, VaR + max drawdown ------------------
+    n_paths, steps = 1_000_000, 10_000
+    eng = PathEngine()
+    ret = np.random.default_rng(7).normal(5e-4, 0.02, 60)
+    mu, sigma = float(np.mean(ret) * 252), float(np.std(ret, ddof=1) * np.sqrt(252))      # monte_carlo_service.py:243-244
+    plo, phi, _ = shard_bounds(n_paths, world, rank)
+
+    def mc_job():
+        f, d, _ = eng.gbm(100.0, mu, sigma, 1 / 252, phi - plo, steps, 2024, path_offset=plo)
+        f, d = gather_paths(f, d, n_paths)
+        return risk_statistics(eng, f, d, 100.0, 0.95)
+    mc_job()
+    reps = 3
+    t, st = wall(lambda: [mc_job() for _ in range(reps)][-1])
+    out["mc_c3_ms"] = {"value": 1e3 * t / reps, "path_steps_per_s": n_paths * steps / (t / reps), "paths": n_paths, "steps": steps,
+                       "var_pct": abs(st["var"]), "mdd_mean": st["mdd_mean"], "scaling": "strong",
+                       "what": "paths sharded by rank (Philox keyed by the global path index), one all-gather of finals + drawdowns, exact radix-select percentiles and moments on every rank; wall ms per run, max over ranks"}
+    return out
+
+
 # --------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -220,6 +392,7 @@ def main():
     ap.add_argument("--symbols", type=int, default=N_SYMBOLS)
     ap.add_argument("--bars", type=int, default=N_BARS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="only the headline (configs[1]) legs")
     ap.add_argument("--mode", default="auto", choices=["auto", "fused", "chunked", "tiled"], help="sweep kernel path (auto = product default)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -270,52 +443,59 @@ def main():
     ncu_traffic = {"tiled": 5.222e9 + 1.006e9, "chunked": 45.6e9, "fused": 3.3e9}[path] \
         if (pop_local, S, N) == (POP_PER_GPU, N_SYMBOLS, N_BARS) else None
 
-    def step():
-        sweep.evaluate_device(indiv_dev, order_dev, pop_local, fit_local, plan=plan)
-        if world > 1:
-            dist.all_gather_into_tensor(fit_global, fit_local)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident leg ------------------------------------------------
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches0 = _lib.launch_count()
-    t_wall0 = time.time()
-    ev0.record()
-    for i in range(args.steps):
-        # the sweep (scan [+ verify/repair + metrics] kernels, then the fitness reduction) is bracketed by its own
-        # events inside the timed region; the all-gather follows
-        k_ev[i][0].record()
-        sweep.evaluate_device(indiv_dev, order_dev, pop_local, fit_local, plan=plan)
-        k_ev[i][1].record()
+    def timed_sweeps(indiv, order_d, pl, sample_clocks=False):
+        """W warm-up + K timed generations of this rank's shard (sweep + fitness reduce [+ all-gather]), device-resident.
+        -> (ms for the K steps, max over ranks; mean ms of the sweep kernels alone; launches; clocks or None)"""
+        def one():
+            sweep.evaluate_device(indiv, order_d, pop_local, fit_local, plan=pl)
+            if world > 1:
+                dist.all_gather_into_tensor(fit_global, fit_local)
+        for _ in range(args.warmup):
+            one()
+        barrier()
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.25)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        launches0 = _lib.launch_count()
+        t_wall0 = time.time()
+        ev0.record()
+        for i in range(args.steps):
+            # the sweep (scan, verify / repair, metrics, fitness reduction) is bracketed by its own events inside the
+            # timed region; the all-gather follows
+            k_ev[i][0].record()
+            sweep.evaluate_device(indiv, order_d, pop_local, fit_local, plan=pl)
+            k_ev[i][1].record()
+            if world > 1:
+                dist.all_gather_into_tensor(fit_global, fit_local)
+        ev1.record()
+        barrier()
+        t_wall1 = time.time()
+        n_launch = _lib.launch_count() - launches0
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_gather_into_tensor(fit_global, fit_local)
-    ev1.record()
-    barrier()
-    t_wall1 = time.time()
-    launches = _lib.launch_count() - launches0
-    ms_total = ev0.elapsed_time(ev1)
-    ms_kernel = statistics.mean(a.elapsed_time(b) for a, b in k_ev)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_k = statistics.mean(a.elapsed_time(b) for a, b in k_ev)
+        return float(t.item()), ms_k, n_launch, (sampler.stop(t_wall0, t_wall1) if sampler else None)
 
+    # ---- device-resident leg ------------------------------------------------
+    ms_total, ms_kernel, launches, clocks = timed_sweeps(indiv_dev, order_dev, plan, sample_clocks=True)
     evals_per_step_global = pop_global * S * N
     value = evals_per_step_global * args.steps / (ms_total * 1e-3)
+    fit_random = fit_local.clone()
+
+    # ---- parity spot check of the timed population (rank 0): 64 lanes against the C oracle ----
+    parity = None
+    if rank == 0:
+        parity = parity_spot_check(sweep, my_pop, ohlcv_host.numpy(), market.minute0, lanes=64)
 
     # ---- end-to-end leg: host OHLCV + host population in, host fitness out ----
     def e2e_step():
@@ -344,27 +524,59 @@ def main():
 
     # sanity: the e2e result equals the device-resident result
     assert np.allclose(f_e2e[rank * pop_local:(rank + 1) * pop_local] if world > 1 else f_e2e,
-                       fit_local.cpu().numpy(), rtol=1e-12, atol=0, equal_nan=True)
+                       fit_random.cpu().numpy(), rtol=1e-12, atol=0, equal_nan=True)
+
+    # ---- the rest of the metric: evolved population, configs[4] generation wall time, configs[2] Monte-Carlo ----
+    extras = {}
+    if not args.skip_extras:
+        extras = run_extras(args, world, rank, dev, sweep, population, pop_local, timed_sweeps, barrier, evals_per_step_global)
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         lanes_evals = pop_local * S * N
-        achieved = lanes_evals * BYTES_PER_EVAL / (ms_kernel * 1e-3) / 1e9
+        algorithmic_gbps = lanes_evals * BYTES_PER_EVAL / (ms_kernel * 1e-3) / 1e9
+        # What binds the sweep is instruction issue, not HBM (profiles/: DRAM 10-15 % of peak, issue slots ~60 % busy,
+        # the RSI rows are shared by every lane of a symbol so most of SURVEY 8(d)'s 8 B/eval never leaves L1/L2).
+        # The roofline is therefore stated against the issue rate: warp-instructions of the dominant kernel per launch
+        # (ncu, committed under profiles/, valid for exactly this workload) / its share of the live kernel time, against
+        # 148 SMs x 4 schedulers x the SM clock sampled during the timed region.
+        ncu = NCU_C2.get(path) if (pop_local, S, N) == (POP_PER_GPU, N_SYMBOLS, N_BARS) else None
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        issue_peak = 148 * 4 * sm_mhz * 1e6 / 1e9                     # G warp-instructions / s
+        roofline = {"bound": "issue", "kernel": path_kernels, "sweep_mode": path, "kernel_ms": ms_kernel,
+                    "peak": issue_peak, "unit": "Ginst/s", "peak_source": f"148 SMs x 4 warp schedulers x {sm_mhz:.0f} MHz (sampled under load)",
+                    "algorithmic_gbps": algorithmic_gbps, "bytes_per_eval": BYTES_PER_EVAL,
+                    "hbm_peak_gbs": peak, "hbm_peak_source": peak_src}
+        if ncu:
+            scan_ms = ms_kernel * ncu["scan_share"]
+            achieved = ncu["warp_inst"] / (scan_ms * 1e-3) / 1e9
+            roofline.update({
+                "achieved": achieved, "frac": achieved / issue_peak,
+                "warp_inst_per_launch": ncu["warp_inst"], "warp_inst_per_eval": ncu["warp_inst"] / lanes_evals,
+                "threads_per_inst": ncu["threads_per_inst"], "dominant_kernel_share_of_step": ncu["scan_share"],
+                "traffic": ncu["dram_bytes"], "traffic_unit": "DRAM bytes per launch of the dominant kernel (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                "dram_frac": ncu["dram_bytes"] / (scan_ms * 1e-3) / 1e9 / peak, "compulsory_bytes": (S * N * 4 + sweep.bank.numel() * 4),
+                "source": ncu["source"],
+                "note": "achieved = warp-instructions of lane_scan_kernel per launch (ncu, this workload) / (its share of the live CUDA-event time of the sweep kernels); algorithmic_gbps = SURVEY 8(d)'s 8 B x evals / kernel time, a throughput figure, not a bound"})
+        else:
+            roofline.update({"achieved": None, "frac": None, "traffic": None,
+                             "note": "no committed ncu capture for this workload size: only the algorithmic throughput is reported"})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 streams / f64 trade arithmetic", "data": "synthetic",
             "config": {"workload": f"GA fitness sweep (BASELINE configs[1] per GPU): population {pop_local}/GPU x {S} symbols x {N} 1-min bars, reference RSI rule",
                        "global_population": pop_global, "symbols": S, "bars": N, "parallelism": f"individuals sharded x{world}, market replicated, 1 all-gather/generation" if world > 1 else "single GPU",
+                       "population": "GeneticAlgorithm.initialize_population draw, seed 42 (see evolved_population_value for generation 3)",
                        "l2_policy": "inputs larger than L2 (price+RSI bank = %.2f GB per GPU)" % ((S * N * 4 + sweep.bank.numel() * 4) / 1e9)},
-            "roofline": {"bound": "hbm", "kernel": path_kernels, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic, "traffic_unit": "bytes per launch of the dominant kernel (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "peak_source": peak_src, "bytes_per_eval": BYTES_PER_EVAL,
-                         "kernel_ms": ms_kernel, "sweep_mode": path, "note": "achieved = 8 B x evals per sweep / CUDA-event duration of the sweep kernels (scan, verify/repair, metrics, fitness reduce); lanes sharing a (symbol, period) stream are served from L1/L2, so DRAM traffic is far below the algorithmic bytes (see profiles/)"},
+            "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "path": "MarketData(pinned host OHLCV; close prices uploaded, the fields the sweep does not read stay on the host) -> PopulationSweep (RSI bank) -> evaluate(list of dicts) -> host fitness"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+            "parity": parity,
             "clocks": clocks,
         }
+        line.update(extras)
         if cpu_baseline is not None:
             if "configs0_backtest" in cpu_baseline:
                 # the same configs[0] backtest through the GPU path (indicators, backtest_ref kernel, stats dict)
