@@ -243,20 +243,22 @@ constexpr int LS_THREADS = B200BT_LS_THREADS;
 constexpr int LS_ZONE = 32;             // bars per zone-map block
 
 // Zone map: (min, max) of every 32-bar block ("coarse") and of every 4-bar group ("fine") of the price row and of each
-// RSI row, NaNs ignored.  A machine whose thresholds lie outside a block's range cannot fire in it: the scan skips a
-// 32-bar block after four compares when no machine of the warp can fire, and inside a block it tests each 4-bar group
-// against the precomputed range (two 8-byte loads, four compares) instead of folding the eight values itself.
-// Layout: coarse [S][P + 1][ceil(N / 32)] float2, then fine [S][P + 1][ceil(N / 128) * 32] float2; row 0 = price.
+// RSI row, NaNs ignored.  A machine whose thresholds lie outside a range cannot fire inside it: the scan skips a 32-bar
+// block after four compares when no machine of the warp can fire in it, and inside a block it tests each 4-bar group
+// against the group's precomputed range (two 8-byte loads, four compares) instead of folding the eight values itself.
+// Layout: coarse [S][P + 1][zone_row_stride(N)] float2, then fine [S][P + 1][zone_fine_stride(N)] float2; row 0 = price;
+// both strides keep rows 16-byte aligned and pad with (NaN, NaN) (every compare false).
 __global__ void __launch_bounds__(256)
 zone_map_kernel(const float* __restrict__ price, int64_t ld_price, const float* __restrict__ rsi, int64_t ld_rsi, int P,
-                int64_t N, int64_t n_blocks, float2* __restrict__ zones, float2* __restrict__ fine, int64_t n_fine) {
+                int64_t N, int64_t row_stride, int64_t fine_stride, float2* __restrict__ zones, float2* __restrict__ fine) {
     const int row = blockIdx.y % (P + 1), sym = blockIdx.y / (P + 1);
     const float* __restrict__ src = row == 0 ? price + (int64_t)sym * ld_price : rsi + ((int64_t)sym * P + row - 1) * ld_rsi;
-    float2* __restrict__ dst = zones + ((int64_t)sym * (P + 1) + row) * n_blocks;
-    float2* __restrict__ fdst = fine + ((int64_t)sym * (P + 1) + row) * n_fine;
+    float2* __restrict__ dst = zones + ((int64_t)sym * (P + 1) + row) * row_stride;
+    float2* __restrict__ fdst = fine + ((int64_t)sym * (P + 1) + row) * fine_stride;
     const int lane = threadIdx.x & 31;
-    // (the fine rows are padded to whole 128-bar tiles: blocks past the series hold NaN, every compare false)
-    for (int64_t blk = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); blk * (LS_ZONE / 4) < n_fine; blk += (int64_t)gridDim.x * 8) {
+    // (fine_stride covers whole 128-bar tiles and is >= 8 * row_stride - 8: one pass writes both)
+    for (int64_t blk = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); blk * (LS_ZONE / 4) < fine_stride || blk < row_stride;
+         blk += (int64_t)gridDim.x * 8) {
         const int64_t t = blk * LS_ZONE + lane;
         const float v = t < N ? __ldg(src + t) : __int_as_float(0x7fc00000);
         float lo = v, hi = v;
@@ -265,23 +267,23 @@ zone_map_kernel(const float* __restrict__ price, int64_t ld_price, const float* 
             lo = fminf(lo, __shfl_xor_sync(FULL, lo, m));
             hi = fmaxf(hi, __shfl_xor_sync(FULL, hi, m));
         }
-        if ((lane & 3) == 0) fdst[blk * (LS_ZONE / 4) + (lane >> 2)] = make_float2(lo, hi);
+        if ((lane & 3) == 0 && blk * (LS_ZONE / 4) + (lane >> 2) < fine_stride) fdst[blk * (LS_ZONE / 4) + (lane >> 2)] = make_float2(lo, hi);
 #pragma unroll
         for (int m = 4; m < 32; m <<= 1) {
             lo = fminf(lo, __shfl_xor_sync(FULL, lo, m));
             hi = fmaxf(hi, __shfl_xor_sync(FULL, hi, m));
         }
-        if (lane == 0 && blk < n_blocks) dst[blk] = make_float2(lo, hi);    // all-NaN block: (NaN, NaN), every compare false
+        if (lane == 0 && blk < row_stride) dst[blk] = make_float2(lo, hi);
     }
 }
 
 struct LaneScanArgs {
     const float* price; int64_t ld_price;
     const float* rsi; int64_t ld_rsi;
-    const float2* zones; int64_t n_zone_blocks;   // zone map (coarse) or NULL
-    const float2* fine; int64_t n_fine;           // 4-bar ranges (with zones)
+    const float2* zones; int64_t n_zone_blocks;   // zone map (coarse part; n_zone_blocks = its row stride) or NULL
+    const float2* fine; int64_t n_fine;           // 4-bar ranges and their row stride
     int P, S; int64_t N;
-    const b200bt_individual* indiv; const int32_t* order; int pop; int K; int warm;
+    const b200bt_individual* indiv; const int32_t* slots; int n_slots; int pop; int K; int warm;
     uint2* pool; int pool_blocks; int* next; unsigned* alloc;
     int* seg_first; unsigned* seg_count; int2* seg_in; int2* seg_out; int* overflow;
 };
@@ -303,33 +305,51 @@ __global__ void lane_tables_kernel(int pop, int K, b200bt_chunk_item* __restrict
 #ifndef B200BT_LS_MIN_BLOCKS
 #define B200BT_LS_MIN_BLOCKS 4
 #endif
-__host__ __device__ constexpr int64_t zone_fine_count(int64_t N) { return ((N + LS_T - 1) / LS_T) * (LS_T / 4); }
-// float2 entries of the coarse part of a zone map, padded to an even count so that the fine part is 16-byte aligned
-__host__ __device__ constexpr int64_t zone_coarse_count(int P, int S, int64_t N) {
-    return (((int64_t)S * (P + 1) * ((N + LS_ZONE - 1) / LS_ZONE)) + 1) & ~(int64_t)1;
-}
+#ifndef B200BT_LS_STAGES
+#define B200BT_LS_STAGES 2
+#endif
+#ifndef B200BT_LS_UNROLL
+#define B200BT_LS_UNROLL 2
+#endif
+constexpr int LS_STAGES = B200BT_LS_STAGES;   // tiles in flight per warp (ring depth)
+constexpr int LS_UNROLL = B200BT_LS_UNROLL;   // 4-bar groups per iteration of the scan loop
+constexpr int LS_WARPS = LS_THREADS / 32;
+constexpr int LS_RSI_ROWS = 2;                // distinct RSI rows the 32 machines of a warp may read (host packing)
+constexpr int LS_ROWS = 1 + LS_RSI_ROWS;      // staged rows per warp: price + its RSI rows
 
-// ZONES: the zone map is staged with the tile; a 32-bar block is skipped when no machine of the WARP can fire in it
-// (a warp-uniform branch: a machine that could skip alone would wait for its neighbours anyway), and a 4-bar group is
-// tested against its precomputed range.  Without a zone map the group's range is folded from its eight values.
-template <bool VEC16, bool ZONES>
+// row stride (float2 entries) of the zone map: rows start 16-byte aligned so that a tile's ranges move as one bulk copy
+__host__ __device__ constexpr int64_t zone_row_stride(int64_t N) { return (((N + LS_ZONE - 1) / LS_ZONE) + 1) & ~(int64_t)1; }
+// row stride (float2 entries) of the fine (4-bar) ranges: whole 128-bar tiles
+__host__ __device__ constexpr int64_t zone_fine_stride(int64_t N) { return ((N + LS_T - 1) / LS_T) * (LS_T / 4); }
+
+// Tile movement.  The 32 machines of a warp read the price row and (the host packs them so) at most LS_RSI_ROWS RSI rows.
+// Every WARP owns a private ring of LS_STAGES shared-memory stages, each holding one 128-bar tile of those rows plus the
+// tile's zone ranges; a stage is filled by bulk async copies (cp.async.bulk, one per row, issued by LS_ROWS lanes,
+// completion counted on the stage's mbarrier) LS_STAGES - 1 tiles ahead of the scan and refilled by the warp itself the
+// moment it has scanned it.  No warp ever waits for another one -- ncu on the round-1 form (one tile of all P + 1 rows per
+// CTA, two CTA barriers per tile) showed a third of the warp time parked at those barriers behind the CTA's busiest warp
+// and 18 % of the instructions computing cp.async addresses -- and the bytes moved per machine stay what they were,
+// because a CTA-wide tile staged P + 1 rows for 256 machines and a warp stages 3 for 32.
+template <bool ZONES>
 __global__ void __launch_bounds__(LS_THREADS, B200BT_LS_MIN_BLOCKS)
-lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (see sweep.cu)
-    // [2][P + 1][LS_STRIDE] floats, then (ZONES) coarse ranges [2][P + 1][LS_T / 32] and fine ranges [2][P + 1][LS_T / 4] float2
+lane_scan_kernel(const LaneScanArgs A, const bool vec16) {   // by value, not __grid_constant__ (see sweep.cu)
+    // [LS_WARPS][LS_STAGES][LS_ROWS][LS_STRIDE] floats, then (ZONES) per warp and stage [LS_ROWS][LS_T / 32 + LS_T / 4] float2
     extern __shared__ __align__(16) float ls_tile[];
-    const int rows = A.P + 1;
+    __shared__ __align__(8) unsigned long long ls_full[LS_WARPS][LS_STAGES];   // "tile landed" (1 arrival + the copies' bytes)
     constexpr int ZB = LS_T / LS_ZONE;                  // zone blocks per tile
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* const wtile = ls_tile + (size_t)warp * LS_STAGES * LS_ROWS * LS_STRIDE;
     constexpr int FG = LS_T / 4;                        // 4-bar groups per tile
-    float2* const ls_zone = reinterpret_cast<float2*>(ls_tile + (size_t)2 * rows * LS_STRIDE);
-    float2* const ls_fine = ls_zone + (size_t)2 * rows * ZB;
+    constexpr int ZR = ZB + FG;                         // float2 per staged row: coarse ranges, then fine ranges
+    float2* const wzone = reinterpret_cast<float2*>(ls_tile + (size_t)LS_WARPS * LS_STAGES * LS_ROWS * LS_STRIDE) + (size_t)warp * LS_STAGES * LS_ROWS * ZR;
+    unsigned long long* const full = ls_full[warp];
     const int sym = (int)(blockIdx.x % (unsigned)A.S);
     const int c = (int)((blockIdx.x / (unsigned)A.S) % (unsigned)A.K);
     const int blk = (int)(blockIdx.x / ((unsigned)A.S * (unsigned)A.K));
-    const float2* __restrict__ zsym = ZONES ? A.zones + (int64_t)sym * rows * A.n_zone_blocks : nullptr;
-    const float2* __restrict__ fsym = ZONES ? A.fine + (int64_t)sym * rows * A.n_fine : nullptr;
     const int k = blk * LS_THREADS + (int)threadIdx.x;
-    const bool active = k < A.pop;
-    const int ind = active ? (A.order ? A.order[k] : k) : 0;
+    const int slot = k < A.n_slots ? (A.slots ? A.slots[k] : (k < A.pop ? k : -1)) : -1;
+    const bool active = slot >= 0;
+    const int ind = active ? slot : 0;
     const b200bt_individual iv = A.indiv[ind];
     // the screening multipliers are needed on events only: shared memory, [multiplier][thread] (conflict-free),
     // side-major so that the side selects an address instead of a value: long hi_c lo_c hi_d lo_d, short ...
@@ -342,8 +362,13 @@ lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (s
         m[0 * LS_THREADS] = sc.hiL_c; m[1 * LS_THREADS] = sc.loL_c; m[2 * LS_THREADS] = sc.hiL_d; m[3 * LS_THREADS] = sc.loL_d;
         m[4 * LS_THREADS] = sc.hiS_c; m[5 * LS_THREADS] = sc.loS_c; m[6 * LS_THREADS] = sc.hiS_d; m[7 * LS_THREADS] = sc.loS_d;
     }
-    const float* __restrict__ pr = A.price + (int64_t)sym * A.ld_price;
-    const float* __restrict__ rb = A.rsi + (int64_t)sym * A.P * A.ld_rsi;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < LS_STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    __syncwarp();
 
     const int n = (int)A.N;
     const int T0 = (int)chunk_begin(A.N, c, A.K);       // first recorded bar (multiple of SW_GROUP, hence of LS_T)
@@ -351,44 +376,78 @@ lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (s
     int s0 = (c == 0) ? 0 : T0 - A.warm;
     if (s0 < 0) s0 = 0;
     s0 &= ~(LS_T - 1);
-    const int tl_begin = s0 / LS_T, tl_end = (T1 + LS_T - 1) / LS_T;
+    const int tl_begin = s0 / LS_T, n_tiles = (T1 + LS_T - 1) / LS_T - tl_begin;
     const int seg = sym * (A.pop * A.K) + ind * A.K + c;
 
-    auto load_tile = [&](int tl, int stage) {
-        float* dst0 = ls_tile + (size_t)stage * rows * LS_STRIDE;
+    // the warp's distinct RSI rows: staged row 1 + j holds the j-th of them (in lane order of first use)
+    const unsigned amask = __ballot_sync(FULL, active);
+    if (amask == 0u) return;                            // an empty warp (padding of the last CTA)
+    const unsigned peers = __match_any_sync(FULL, active ? iv.rsi_row : -1 - lane);
+    const int leader = __ffs(peers) - 1;
+    const unsigned heads = __ballot_sync(FULL, active && lane == leader);
+    const int n_rsi = __popc(heads);
+    const int my_row = 1 + __popc(heads & ((1u << leader) - 1u));       // staged row this machine reads
+    if (n_rsi > LS_RSI_ROWS) {
+        // not packed for this schedule: the lanes are flagged and re-run by the caller's exact fallback (fused kernel)
+        if (active) {
+            A.seg_in[seg] = make_int2(0, -1);
+            A.seg_out[seg] = make_int2(0, -1);
+            A.seg_count[seg] = 0xffffffffu;
+        }
+        return;
+    }
+    // lane L <= n_rsi issues the copies of staged row L (0 = price)
+    const unsigned src_lane = __fns(heads, 0, lane);                    // lane of the (lane)-th head (1-based), or ~0u
+    const int row_of_lane = __shfl_sync(FULL, iv.rsi_row, src_lane < 32u ? (int)src_lane : 0);
+    const bool issuer = lane <= n_rsi;
+    const int zrow = (lane == 0 || !issuer) ? 0 : 1 + row_of_lane;      // row of the zone map (0 = price)
+    // source rows of the warp's staged rows: a small table in shared memory (read by the issuing lanes only: three
+    // 64-bit pointers per thread would not fit the register budget of the scan loop)
+    __shared__ const void* ls_src[LS_WARPS][LS_ROWS][3];
+    if (issuer) {
+        ls_src[warp][lane][0] = (lane == 0) ? A.price + (int64_t)sym * A.ld_price : A.rsi + ((int64_t)sym * A.P + row_of_lane) * A.ld_rsi;
+        ls_src[warp][lane][1] = ZONES ? A.zones + ((int64_t)sym * (A.P + 1) + zrow) * A.n_zone_blocks : nullptr;   // (n_zone_blocks = row stride)
+        ls_src[warp][lane][2] = ZONES ? A.fine + ((int64_t)sym * (A.P + 1) + zrow) * A.n_fine : nullptr;
+    }
+    __syncwarp();
+    const unsigned stage_bytes = (unsigned)(1 + n_rsi) * (LS_T * 4 + (ZONES ? ZR * 8 : 0));
+
+    // fill stage `stage` of this warp's ring with tile `tl`
+    auto issue = [&](int tl, int stage) {
+        float* dst0 = wtile + (size_t)stage * LS_ROWS * LS_STRIDE;
+        float2* zdst = wzone + (size_t)stage * LS_ROWS * ZR;
         const int t0 = tl * LS_T;
-        if (VEC16 && t0 + LS_T <= n) {
-            for (int e = threadIdx.x; e < rows * (LS_T / 4); e += LS_THREADS) {
-                const int row = e / (LS_T / 4), piece = e - row * (LS_T / 4);
-                const float* src = (row == 0 ? pr : rb + (int64_t)(row - 1) * A.ld_rsi) + t0 + piece * 4;
-                cp_async16(dst0 + row * LS_STRIDE + piece * 4, src);
+        if (vec16 && t0 + LS_T <= n) {
+            if (lane == 0) mbar_arrive_expect_tx(&full[stage], stage_bytes);
+            __syncwarp();
+            if (issuer) {
+                fence_proxy_async();      // the warp's reads of the stage (generic proxy) are ordered before the async writes
+                bulk_g2s(dst0 + lane * LS_STRIDE, static_cast<const float*>(ls_src[warp][lane][0]) + t0, LS_T * 4, &full[stage]);
+                if (ZONES) {
+                    bulk_g2s(zdst + lane * ZR, static_cast<const float2*>(ls_src[warp][lane][1]) + (int64_t)tl * ZB, ZB * 8, &full[stage]);
+                    bulk_g2s(zdst + lane * ZR + ZB, static_cast<const float2*>(ls_src[warp][lane][2]) + (int64_t)tl * FG, FG * 8, &full[stage]);
+                }
             }
         } else {
-            const float qnan = __int_as_float(0x7fc00000);   // unaligned input or the ragged last tile
-            for (int e = threadIdx.x; e < rows * LS_T; e += LS_THREADS) {
-                const int row = e / LS_T, col = e - row * LS_T;
-                const float* src = (row == 0 ? pr : rb + (int64_t)(row - 1) * A.ld_rsi) + t0 + col;
-                dst0[row * LS_STRIDE + col] = (t0 + col < n) ? __ldg(src) : qnan;
+            const float qnan = __int_as_float(0x7fc00000);   // unaligned input or the ragged last tile: plain copies
+            for (int r = 0; r <= n_rsi; ++r) {
+                const float* src = static_cast<const float*>(ls_src[warp][r][0]);
+                for (int col = lane; col < LS_T; col += 32) dst0[r * LS_STRIDE + col] = (t0 + col < n) ? __ldg(src + t0 + col) : qnan;
+                if (ZONES) {
+                    const float2* zs = static_cast<const float2*>(ls_src[warp][r][1]);
+                    const float2* fs = static_cast<const float2*>(ls_src[warp][r][2]);
+                    if (lane < ZB) {
+                        const int64_t zblk = (int64_t)tl * ZB + lane;
+                        zdst[r * ZR + lane] = (zblk * LS_ZONE < n) ? zs[zblk] : make_float2(qnan, qnan);
+                    }
+                    zdst[r * ZR + ZB + lane] = fs[(int64_t)tl * FG + lane];        // (FG == 32; rows are padded to whole tiles)
+                }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);     // (release: the stores above are visible after the wait)
         }
-        if (ZONES) {
-            float2* zdst = ls_zone + (size_t)stage * rows * ZB;
-            for (int e = threadIdx.x; e < rows * ZB; e += LS_THREADS) {
-                const int row = e / ZB, zb = e - row * ZB;
-                const int64_t zblk = (int64_t)tl * ZB + zb;
-                if (zblk < A.n_zone_blocks) cp_async8(zdst + e, zsym + (int64_t)row * A.n_zone_blocks + zblk);
-                else zdst[e] = make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
-            }
-            // fine ranges: FG float2 per row and tile = FG / 2 16-byte pieces (rows are padded to whole tiles)
-            float2* fdst = ls_fine + (size_t)stage * rows * FG;
-            for (int e = threadIdx.x; e < rows * (FG / 2); e += LS_THREADS) {
-                const int row = e / (FG / 2), piece = e - row * (FG / 2);
-                cp_async16(reinterpret_cast<float*>(fdst + row * FG + piece * 2),
-                           reinterpret_cast<const float*>(fsym + (int64_t)row * A.n_fine + (int64_t)tl * FG + piece * 2));
-            }
-        }
-        cp_async_commit();
     };
+    for (int it = 0; it < LS_STAGES && it < n_tiles; ++it) issue(tl_begin + it, it);
 
     // machine state (per thread)
     int pos = 0, entry_bar = 0;
@@ -444,49 +503,44 @@ lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (s
         }
     };
 
-    load_tile(tl_begin, 0);
-    for (int tl = tl_begin; tl < tl_end; ++tl) {
-        const int stage = (tl - tl_begin) & 1;
-        if (tl + 1 < tl_end) load_tile(tl + 1, stage ^ 1); else cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
-        const int t0 = tl * LS_T;
-        const unsigned wmask = __ballot_sync(FULL, active);
+    int stage = 0;
+    unsigned parity = 0;
+    for (int it = 0; it < n_tiles; ++it) {
+        mbar_wait(&full[stage], parity);
+        const int t0 = (tl_begin + it) * LS_T;
         if (active) {
             if (t0 == T0) { A.seg_in[seg] = make_int2(pos, pos != 0 ? entry_bar : -1); rec = true; }
-            const float4* __restrict__ pp = reinterpret_cast<const float4*>(ls_tile + (size_t)stage * rows * LS_STRIDE);
-            const float4* __restrict__ rr = reinterpret_cast<const float4*>(ls_tile + ((size_t)stage * rows + 1 + iv.rsi_row) * LS_STRIDE);
-            if (ZONES) {
-                const float2* __restrict__ zp = ls_zone + (size_t)stage * rows * ZB;
-                const float2* __restrict__ zr = zp + (1 + iv.rsi_row) * ZB;
-                const float2* __restrict__ fp = ls_fine + (size_t)stage * rows * FG;
-                const float2* __restrict__ fr = fp + (1 + iv.rsi_row) * FG;
+            const float4* __restrict__ pp = reinterpret_cast<const float4*>(wtile + (size_t)stage * LS_ROWS * LS_STRIDE);
+            const float4* __restrict__ rr = reinterpret_cast<const float4*>(wtile + ((size_t)stage * LS_ROWS + my_row) * LS_STRIDE);
+            const float2* __restrict__ zp = wzone + (size_t)stage * LS_ROWS * ZR;
+            const float2* __restrict__ zr = zp + my_row * ZR;
 #pragma unroll 1
-                for (int zb = 0; zb < ZB; ++zb) {
+            for (int zb = 0; zb < ZB; ++zb) {
+                if (ZONES) {
+                    // nothing can fire in a block whose (min, max) stay inside the machine's thresholds; the skip is
+                    // taken when NO machine of the warp can fire (a warp-uniform branch: a machine that could skip alone
+                    // would wait for its neighbours anyway, and the divergent form costs the re-convergence on top)
                     const float2 rz = zr[zb], pz = zp[zb];
-                    const bool can = (rz.x < rlo) | (rz.y > rhi) | (pz.x <= plo) | (pz.y >= phi);
-                    if (!__any_sync(wmask, can)) continue;
-#pragma unroll 2
-                    for (int g = zb * (LS_ZONE / 4); g < (zb + 1) * (LS_ZONE / 4); ++g) {
-                        const float2 rm = fr[g], pm = fp[g];
-                        if ((rm.x < rlo) | (rm.y > rhi) | (pm.x <= plo) | (pm.y >= phi)) {
-                            const float4 p = pp[g], r = rr[g];
-                            const int t = t0 + g * 4;
-                            step(p.x, r.x, t);
-                            step(p.y, r.y, t + 1);
-                            step(p.z, r.z, t + 2);
-                            step(p.w, r.w, t + 3);
-                        }
-                    }
+                    if (!__any_sync(amask, (rz.x < rlo) | (rz.y > rhi) | (pz.x <= plo) | (pz.y >= phi))) continue;
                 }
-            } else {
-#pragma unroll 2
-                for (int g = 0; g < FG; ++g) {
+#pragma unroll LS_UNROLL
+                for (int g = zb * (LS_ZONE / 4); g < (zb + 1) * (LS_ZONE / 4); ++g) {
+                    bool hit;
+                    if (ZONES) {
+                        // the group's precomputed range decides whether any of its four bars can fire (tested against the
+                        // machine's CURRENT thresholds: they move whenever it fires)
+                        const float2 rm = zr[ZB + g], pm = zp[ZB + g];
+                        hit = (rm.x < rlo) | (rm.y > rhi) | (pm.x <= plo) | (pm.y >= phi);
+                        if (!hit) continue;
+                    }
                     const float4 p = pp[g], r = rr[g];
-                    // any bar of the four beyond a threshold?  (fminf / fmaxf drop NaNs, as the per-bar compares do)
-                    const float r_min = fminf(fminf(r.x, r.y), fminf(r.z, r.w)), r_max = fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w));
-                    const float p_min = fminf(fminf(p.x, p.y), fminf(p.z, p.w)), p_max = fmaxf(fmaxf(p.x, p.y), fmaxf(p.z, p.w));
-                    if ((r_min < rlo) | (r_max > rhi) | (p_min <= plo) | (p_max >= phi)) {
+                    if (!ZONES) {
+                        // any bar of the four beyond a threshold?  (fminf / fmaxf drop NaNs, as the per-bar compares do)
+                        const float r_min = fminf(fminf(r.x, r.y), fminf(r.z, r.w)), r_max = fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w));
+                        const float p_min = fminf(fminf(p.x, p.y), fminf(p.z, p.w)), p_max = fmaxf(fmaxf(p.x, p.y), fmaxf(p.z, p.w));
+                        hit = (r_min < rlo) | (r_max > rhi) | (p_min <= plo) | (p_max >= phi);
+                    }
+                    if (hit) {
                         const int t = t0 + g * 4;
                         step(p.x, r.x, t);
                         step(p.y, r.y, t + 1);
@@ -496,9 +550,10 @@ lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (s
                 }
             }
         }
-        __syncthreads();   // the stage is refilled by the next iteration's load
+        __syncwarp();      // every machine of the warp is done with the stage: refill it with the tile LS_STAGES ahead
+        if (it + LS_STAGES < n_tiles) issue(tl_begin + it + LS_STAGES, stage);
+        if (++stage == LS_STAGES) { stage = 0; parity ^= 1u; }
     }
-    cp_async_wait<0>();
     if (!active) return;
     A.seg_out[seg] = make_int2(pos, pos != 0 ? entry_bar : -1);
     if (c == A.K - 1 && pos != 0)   // force-close at the last bar (:849-876)
@@ -514,7 +569,7 @@ lane_scan_kernel(const LaneScanArgs A) {   // by value, not __grid_constant__ (s
                 wptr = A.pool + (int64_t)b * CK_BLOCK;
             }
         }
-        if (!dead) *wptr = make_uint2(word, __float_as_uint(__ldg(pr + (n - 1))));
+        if (!dead) *wptr = make_uint2(word, __float_as_uint(__ldg(A.price + (int64_t)sym * A.ld_price + (n - 1))));
         ++count;
     }
     A.seg_count[seg] = dead ? 0xffffffffu : count;
@@ -1156,7 +1211,7 @@ extern "C" int b200bt_sweep_chunked(const float* price, int64_t ld_price, const 
 
 extern "C" int64_t b200bt_zone_map_floats(int P, int S, int64_t N) {
     if (P <= 0 || S <= 0 || N <= 0) return 0;
-    return (zone_coarse_count(P, S, N) + (int64_t)S * (P + 1) * zone_fine_count(N)) * 2;
+    return (int64_t)S * (P + 1) * (zone_row_stride(N) + zone_fine_stride(N)) * 2;
 }
 
 extern "C" int b200bt_zone_map(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S, int64_t N,
@@ -1166,12 +1221,13 @@ extern "C" int b200bt_zone_map(const float* price, int64_t ld_price, const float
     B200BT_REQUIRE(((uintptr_t)zones & 15) == 0, B200BT_EINVAL, "zone_map: output must be 16-byte aligned");
     int rc = check_device();
     if (rc) return rc;
-    const int64_t nb = (N + LS_ZONE - 1) / LS_ZONE, nf = zone_fine_count(N);
-    const unsigned gx = (unsigned)min((int64_t)1024, (nf / (LS_ZONE / 4) + 7) / 8);
+    const int64_t stride = zone_row_stride(N), fstride = zone_fine_stride(N);
+    const int64_t blocks = max(stride, fstride / (LS_ZONE / 4));
+    const unsigned gx = (unsigned)min((int64_t)1024, (blocks + 7) / 8);
     float2* coarse = (float2*)zones;
-    float2* fine = coarse + zone_coarse_count(P, S, N);      // 16-byte aligned (even number of float2 in front)
-    zone_map_kernel<<<dim3(gx, (unsigned)(S * (P + 1))), 256, 0, (cudaStream_t)stream>>>(price, ld_price, rsi, ld_rsi, P, N, nb,
-                                                                                       coarse, fine, nf);
+    float2* fine = coarse + (int64_t)S * (P + 1) * stride;          // (16-byte aligned: stride is even)
+    zone_map_kernel<<<dim3(gx, (unsigned)(S * (P + 1))), 256, 0, (cudaStream_t)stream>>>(price, ld_price, rsi, ld_rsi, P, N, stride, fstride,
+                                                                                       coarse, fine);
     B200BT_LAUNCH_CHECK("zone_map launch");
     return B200BT_OK;
 }
@@ -1182,24 +1238,21 @@ extern "C" int64_t b200bt_sweep_tiled_workspace_bytes(int pool_blocks, int S, in
 }
 
 extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S,
-                                  int64_t N, const float* zones_or_null, const b200bt_individual* indiv, const int32_t* order,
-                                  int pop, int K, int warm, int max_repair_rounds, int pool_blocks, void* workspace, int64_t workspace_bytes,
-                                  const b200bt_sweep_config* cfg_host, b200bt_lane_stats* stats, uint32_t* events,
-                                  int64_t event_cap, unsigned char* lane_invalid, int* overflow_host_or_null,
+                                  int64_t N, const float* zones_or_null, const b200bt_individual* indiv, const int32_t* slots,
+                                  int n_slots, int pop, int K, int warm, int max_repair_rounds, int pool_blocks, void* workspace,
+                                  int64_t workspace_bytes, const b200bt_sweep_config* cfg_host, b200bt_lane_stats* stats,
+                                  uint32_t* events, int64_t event_cap, unsigned char* lane_invalid, int* overflow_host_or_null,
                                   b200bt_stream_t stream) {
     B200BT_REQUIRE(indiv && workspace && stats && lane_invalid, B200BT_EINVAL, "sweep_tiled: null pointer");
     B200BT_REQUIRE(pop > 0 && K > 0 && K <= 120 && pool_blocks > 0 && warm >= 0, B200BT_EINVAL, "sweep_tiled: bad sizes (1 <= K <= 120)");
+    B200BT_REQUIRE(slots ? (n_slots > 0 && n_slots % 32 == 0) : true, B200BT_EINVAL, "sweep_tiled: n_slots must be a positive multiple of 32");
+    if (!slots) n_slots = (pop + 31) & ~31;
     int rc = check_sweep_args("sweep_tiled", price, ld_price, rsi, ld_rsi, P, S, N, cfg_host, events, event_cap);
     if (rc) return rc;
     B200BT_REQUIRE((int64_t)pop * K * S < (1ll << 31), B200BT_ELIMIT, "sweep_tiled: too many chunks");
     B200BT_REQUIRE(K == 1 || N / K >= SW_GROUP, B200BT_EINVAL, "sweep_tiled: chunks shorter than %d bars", SW_GROUP);
-    // shared-memory tile: values, and with a zone map the coarse and fine ranges; a bank too wide for the tile with
-    // ranges is swept without them
-    const size_t smem_plain = (size_t)2 * (P + 1) * LS_STRIDE * sizeof(float);
-    const size_t smem_zones = smem_plain + (size_t)2 * (P + 1) * (LS_T / LS_ZONE + LS_T / 4) * sizeof(float2);
-    if (zones_or_null && smem_zones > 72 * 1024) zones_or_null = nullptr;
-    const size_t smem = zones_or_null ? smem_zones : smem_plain;
-    B200BT_REQUIRE(smem <= 72 * 1024, B200BT_ELIMIT, "sweep_tiled: RSI bank of %d periods exceeds the shared-memory tile", P);
+    // shared-memory rings: one per warp, LS_STAGES tiles of LS_ROWS rows (+ their zone ranges): independent of P
+    const size_t smem = (size_t)LS_WARPS * LS_STAGES * LS_ROWS * (LS_STRIDE * sizeof(float) + (zones_or_null ? (LS_T / LS_ZONE + LS_T / 4) * sizeof(float2) : 0));
     B200BT_REQUIRE(zones_or_null == nullptr || ((uintptr_t)zones_or_null & 15) == 0, B200BT_EINVAL, "sweep_tiled: zone map must be 16-byte aligned");
     B200BT_REQUIRE(workspace_bytes >= b200bt_sweep_tiled_workspace_bytes(pool_blocks, S, pop, K), B200BT_EINVAL,
                    "sweep_tiled: workspace too small");
@@ -1220,19 +1273,19 @@ extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const fl
 
     LaneScanArgs L;
     L.price = price; L.ld_price = ld_price; L.rsi = rsi; L.ld_rsi = ld_rsi; L.P = P; L.S = S; L.N = N;
-    L.zones = (const float2*)zones_or_null; L.n_zone_blocks = (N + LS_ZONE - 1) / LS_ZONE;
-    L.fine = zones_or_null ? L.zones + zone_coarse_count(P, S, N) : nullptr; L.n_fine = zone_fine_count(N);
-    L.indiv = indiv; L.order = order; L.pop = pop; L.K = K; L.warm = warm;
+    L.zones = (const float2*)zones_or_null; L.n_zone_blocks = zone_row_stride(N);    // (row stride of the zone map)
+    L.fine = zones_or_null ? L.zones + (int64_t)S * (P + 1) * zone_row_stride(N) : nullptr; L.n_fine = zone_fine_stride(N);
+    L.indiv = indiv; L.slots = slots; L.n_slots = n_slots; L.pop = pop; L.K = K; L.warm = warm;
     L.pool = w.pool; L.pool_blocks = pool_blocks; L.next = w.next; L.alloc = w.alloc;
     L.seg_first = w.seg_first; L.seg_count = w.seg_count; L.seg_in = w.seg_in; L.seg_out = w.seg_out; L.overflow = w.overflow;
     const bool vec16 = (((uintptr_t)price | (uintptr_t)rsi) & 15) == 0 && ld_price % 4 == 0 && ld_rsi % 4 == 0;
-    auto kern = zones_or_null ? (vec16 ? lane_scan_kernel<true, true> : lane_scan_kernel<false, true>)
-                              : (vec16 ? lane_scan_kernel<true, false> : lane_scan_kernel<false, false>);
+    auto kern = zones_or_null ? lane_scan_kernel<true> : lane_scan_kernel<false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return cuda_status(e, "sweep_tiled: cudaFuncSetAttribute");
-    const int64_t blocks = (int64_t)((pop + LS_THREADS - 1) / LS_THREADS) * K * S;
+    const int64_t blocks = (int64_t)((n_slots + LS_THREADS - 1) / LS_THREADS) * K * S;
     B200BT_REQUIRE(blocks < (1ll << 31), B200BT_ELIMIT, "sweep_tiled: too many work items");
-    kern<<<(unsigned)blocks, LS_THREADS, smem, st>>>(L);
+    kern<<<(unsigned)blocks, LS_THREADS, smem, st>>>(L, vec16);
     B200BT_LAUNCH_CHECK("lane_scan launch");
 
     ChunkScanArgs A;   // for the shared repair / metrics kernels

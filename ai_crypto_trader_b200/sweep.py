@@ -226,7 +226,7 @@ def lane_cost(p: Dict) -> float:
 
 
 EVENTS_PER_COST_BAR = 0.27
-TILED_MAX_PERIODS = 64      # shared-memory tile of the thread-per-lane sweep: 2 (P + 1) 560 B <= 72 KB
+TILED_MAX_PERIODS = 118     # shared-memory tile ring of the thread-per-lane sweep: 3 stages x (P + 1) rows x 560 B <= 200 KB
 
 
 def predicted_events(population: List[Dict], n_bars: int) -> np.ndarray:
@@ -349,36 +349,36 @@ class TilePlan:
     CTAS_PER_SM = int(os.environ.get("B200BT_LS_CTAS", 4))
 
     @classmethod
-    def chunks_for(cls, pop: int, n_bars: int, n_symbols: int, device, warm: int = 8192, max_chunks: int = 64) -> int:
+    def chunks_for(cls, pop: int, n_bars: int, n_symbols: int, device, warm: int = 8192, max_chunks: int = 64,
+                   n_slots: Optional[int] = None) -> int:
         """About 1.75 resident sets of CTAs (measured optimum on the C2 workload, flat from 1.6 to 1.9: heavy CTAs
         run longer, so whole "waves" do not exist), chunks at least 4 warm-ups long."""
         kmax = max(1, min(max_chunks, n_bars // max(4 * warm, 2048)))
         slots = _sm_count(device) * cls.CTAS_PER_SM
-        groups = -(-pop // cls.THREADS) * n_symbols
+        groups = -(-(n_slots if n_slots is not None else pop) // cls.THREADS) * n_symbols
         return min(kmax, max(1, round(1.75 * slots / groups)))
 
     def __init__(self, population: List[Dict], n_bars: int, n_symbols: int, device, warm: int = 8192,
                  max_chunks: int = 64, chunks: Optional[int] = None, pool_scale: float = 1.5,
                  pool_blocks: Optional[int] = None, max_repair_rounds: Optional[int] = None, lo: int = 0,
-                 workspace: Optional[torch.Tensor] = None, order_by: str = "cost", pred: Optional[np.ndarray] = None):
+                 workspace: Optional[torch.Tensor] = None, order_by: str = "row_cost", pred: Optional[np.ndarray] = None):
         pop = len(population)
         self.lo, self.pop = int(lo), pop
         self.warm = int(warm)
+        pred = predicted_events(population, n_bars) if pred is None else np.asarray(pred, dtype=np.float64)
+        # thread slots: 32 consecutive slots = one warp, which stages its own tiles and may read two distinct RSI rows
+        self.slots = pack_warps(population, pred, order_by)
         if chunks is None:
-            chunks = self.chunks_for(pop, n_bars, n_symbols, device, warm, max_chunks)
+            chunks = self.chunks_for(pop, n_bars, n_symbols, device, warm, max_chunks, n_slots=len(self.slots))
         self.K = int(chunks)
         # a lane that holds one position across many chunks needs one repair round per boundary
         self.max_repair_rounds = int(max_repair_rounds) if max_repair_rounds is not None else min(self.K, 24)
         self.n_seg = pop * self.K
-        pred = predicted_events(population, n_bars) if pred is None else np.asarray(pred, dtype=np.float64)
-        # threads of a CTA wait for each other at every tile: neighbours should cost the same ("cost"), which
-        # matters more than sharing RSI rows ("period": the fused kernel's order)
-        self.order = tile_order(population, pred, order_by, self.THREADS)
         # every segment owns at least one block, and a repaired segment abandons its first chain
         self.pool_blocks = int(pool_scale * pred.sum() * n_symbols / 256) + 2 * self.n_seg * n_symbols + 1024
         if pool_blocks is not None:
             self.pool_blocks = int(pool_blocks)
-        self.order_dev = torch.from_numpy(self.order).to(device)
+        self.slots_dev = torch.from_numpy(self.slots).to(device)
         self.ws_bytes = int(_lib.load().b200bt_sweep_tiled_workspace_bytes(self.pool_blocks, n_symbols, pop, self.K))
         if workspace is not None and workspace.numel() >= self.ws_bytes:
             self.workspace = workspace
@@ -388,32 +388,50 @@ class TilePlan:
         self.overflow = _pinned_flag()
 
 
-def tile_order(population: List[Dict], pred: np.ndarray, order_by: str, threads: int) -> np.ndarray:
-    """Dispatch order of the thread-per-lane scan: position k of the order goes to thread k % threads of CTA k // threads.
-      "cost"      most expensive first (neighbours cost the same; the round-1 default)
-      "period"    same RSI row adjacent, then most expensive first (evaluation_order)
-      "row"       same RSI row adjacent, rows by mean cost (most expensive first), inside a row by cost
-      "rowth"     same RSI row adjacent, inside a row by (oversold, overbought): a warp's machines fire on the same bars
-      "cost_row"  CTAs by cost (blocks of `threads` individuals in cost order), inside a CTA by (row, oversold, overbought)"""
+WARP_RSI_ROWS = 2       # distinct RSI rows the machines of one warp may read (csrc/sweep_chunked.cu LS_RSI_ROWS)
+
+
+def pack_warps(population: List[Dict], pred: np.ndarray, order_by: str = "row_cost") -> np.ndarray:
+    """Thread slots of the thread-per-lane scan: int32[n_warps * 32], the individual each slot runs, -1 = empty.
+
+    A warp stages the price row and the RSI rows of its own 32 machines, at most WARP_RSI_ROWS of them, and its cost is
+    the UNION of its machines' events.  So individuals are sorted by (RSI row, predicted cost) -- neighbours read the same
+    row and fire at similar rates on the same bars -- and cut into warps that never span more than WARP_RSI_ROWS rows (a
+    row's tail shares a warp with the head of the next row; slots stay empty only where a third row would enter).  Warps
+    are then dispatched most expensive first, so that the warps resident together (and the 8 of a CTA) cost the same.
+    order_by = "identity" keeps the population order (testing: warps that break the row rule are re-run by the exact
+    fallback), "row_thresholds" sorts a row by (oversold, overbought) instead of cost."""
     n = len(population)
+    if order_by == "identity":
+        out = np.full(-(-n // 32) * 32, -1, dtype=np.int32)
+        out[:n] = np.arange(n, dtype=np.int32)
+        return out
     g = lambda key, default: np.array([float(p.get(key, default)) for p in population], dtype=np.float64)
-    if order_by == "cost":
-        return np.argsort(-pred, kind="stable").astype(np.int32)
-    if order_by == "period":
-        return evaluation_order(population)
-    row, lo, hi = g("rsi_period", 14).astype(np.int64), g("rsi_oversold", 30), g("rsi_overbought", 70)
-    if order_by in ("row", "rowth"):
-        mean_cost = np.zeros(int(row.max()) + 1)
-        for w in np.unique(row):
-            mean_cost[w] = pred[row == w].mean()
-        keys = (np.arange(n), -pred) if order_by == "row" else (np.arange(n), -hi, lo)
-        return np.lexsort(keys + (-mean_cost[row],)).astype(np.int32)
-    if order_by == "cost_row":
-        by_cost = np.argsort(-pred, kind="stable")
-        blk = np.empty(n, dtype=np.int64)
-        blk[by_cost] = np.arange(n) // threads
-        return np.lexsort((np.arange(n), -hi, lo, row, blk)).astype(np.int32)
-    raise ValueError(f"unknown order_by {order_by!r}")
+    row = g("rsi_period", 14).astype(np.int64)
+    pred = np.asarray(pred, dtype=np.float64)
+    rows, inv = np.unique(row, return_inverse=True)
+    mean_cost = np.bincount(inv, weights=pred) / np.maximum(np.bincount(inv), 1)
+    if order_by == "row_thresholds":
+        idx = np.lexsort((np.arange(n), -g("rsi_overbought", 70), g("rsi_oversold", 30), -mean_cost[inv]))
+    else:
+        idx = np.lexsort((np.arange(n), -pred, -mean_cost[inv]))          # rows by mean cost, inside a row by cost
+    counts = np.bincount(inv, minlength=len(rows))[np.argsort(-mean_cost, kind="stable")]    # members per row, in dispatch order
+    warps, fill, used, pos = [], 0, 0, 0
+    cur = np.full(32, -1, dtype=np.int32)
+    for cnt in counts:
+        left = int(cnt)
+        while left:
+            if fill == 32 or (fill and used == WARP_RSI_ROWS):
+                warps.append(cur)
+                cur, fill, used = np.full(32, -1, dtype=np.int32), 0, 0
+            take = min(32 - fill, left)
+            cur[fill:fill + take] = idx[pos:pos + take]
+            fill, used, pos, left = fill + take, used + 1, pos + take, left - take
+    if fill:
+        warps.append(cur)
+    warps = np.stack(warps)
+    cost = np.where(warps >= 0, pred[np.maximum(warps, 0)], 0.0).sum(axis=1)
+    return np.ascontiguousarray(warps[np.argsort(-cost, kind="stable")]).reshape(-1)
 
 
 def evaluation_order(population: List[Dict]) -> np.ndarray:
@@ -576,7 +594,7 @@ class PopulationSweep:
             _lib.call("b200bt_sweep_tiled", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
                       len(self.periods), m.S, m.N, _lib.ptr(self._zones_if_amortised()),
                       indiv_dev.data_ptr() + lo * C.sizeof(_lib.Individual),
-                      plan.order_dev.data_ptr(), n, plan.K, plan.warm, plan.max_repair_rounds, plan.pool_blocks,
+                      plan.slots_dev.data_ptr(), int(plan.slots_dev.numel()), n, plan.K, plan.warm, plan.max_repair_rounds, plan.pool_blocks,
                       plan.workspace.data_ptr(), plan.workspace.numel(), C.byref(self.cfg), stats.data_ptr(),
                       _lib.ptr(events), self.event_cap, plan.invalid.data_ptr(), plan.overflow.data_ptr(), st)
             bad = torch.nonzero(plan.invalid.any(dim=1)).flatten()          # device -> host sync (tiny)

@@ -271,20 +271,24 @@ int b200bt_sweep_chunked(const float* price, int64_t ld_price, const float* rsi,
                          unsigned char* lane_invalid, int* overflow_host_or_null, b200bt_stream_t stream);
 
 /* Same contract as b200bt_sweep_chunked, thread-per-lane form: EVERY individual is cut into the same K time
- * chunks (chunk c of K covers [floor(N c / K) & ~511, ...)), a CTA owns (symbol, chunk, 256 individuals in `order`)
- * and each thread steps its own state machine through shared-memory tiles of the price row and the RSI bank.
+ * chunks (chunk c of K covers [floor(N c / K) & ~511, ...)) and each THREAD steps the state machine of one (individual,
+ * symbol, chunk) through shared-memory tiles.  Every warp stages its own tiles -- the price row and the RSI rows its 32
+ * machines read -- through a private ring of bulk async copies (cp.async.bulk + mbarrier), so warps never wait for each other.
  * Verification, in-place repair, metrics and the lane_invalid / overflow outputs are those of b200bt_sweep_chunked.
- * order: device int32[pop] dispatch order (NULL = identity; same-period, similar-cost neighbours are cheapest).
+ * slots: device int32[n_slots] (n_slots a multiple of 32): individual run by each thread slot, -1 = empty; 32 consecutive
+ *        slots form a warp, which may read at most TWO distinct RSI rows (rsi_row) -- the host packs individuals by row and
+ *        similar cost; a warp that breaks the rule is not scanned: its lanes are flagged in lane_invalid and the caller
+ *        re-evaluates them with b200bt_sweep (exact).  NULL = identity (thread k runs individual k).
  * zones: optional zone map of the same price / RSI arrays (b200bt_zone_map), NULL = none: (min, max) per 32-bar
- * block of every row, which lets a machine skip blocks in which none of its thresholds can be crossed.
- * Requires 2 (P + 1) 560 B of shared memory <= 72 KB, i.e. P <= 64 RSI periods. */
-int64_t b200bt_zone_map_floats(int P, int S, int64_t N);     /* floats in the zone map: [S][P+1][ceil(N/32)][2] */
+ *        block of every row, which lets a warp skip blocks in which none of its machines' thresholds can be crossed.
+ * Shared memory does not depend on P (any number of RSI rows). */
+int64_t b200bt_zone_map_floats(int P, int S, int64_t N);     /* floats in the zone map: coarse (32-bar) ranges [S][P+1][ceil(N/32) rounded up to even][2], then fine (4-bar) ranges [S][P+1][ceil(N/128)*32][2]; 16-byte aligned */
 int b200bt_zone_map(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S, int64_t N,
                     float* zones, b200bt_stream_t stream);
 int64_t b200bt_sweep_tiled_workspace_bytes(int pool_blocks, int S, int pop, int K);
 int b200bt_sweep_tiled(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S,
-                       int64_t N, const float* zones, const b200bt_individual* indiv, const int32_t* order, int pop, int K, int warm,
-                       int max_repair_rounds, int pool_blocks, void* workspace, int64_t workspace_bytes,
+                       int64_t N, const float* zones, const b200bt_individual* indiv, const int32_t* slots, int n_slots, int pop,
+                       int K, int warm, int max_repair_rounds, int pool_blocks, void* workspace, int64_t workspace_bytes,
                        const b200bt_sweep_config* cfg, b200bt_lane_stats* stats, uint32_t* events,
                        int64_t event_cap, unsigned char* lane_invalid, int* overflow_host_or_null,
                        b200bt_stream_t stream);

@@ -300,6 +300,8 @@ def test_chunked_sweep_in_population_slices_with_duplicates(torch_cuda):
     (150_000, dict(warm=0, chunks=32, max_repair_rounds=64)),          # no warm-up: repaired chunk by chunk
     (200_000, dict(warm=2048, chunks=8, pool_blocks=8)),               # pool far too small -> flagged lanes re-run
     (5_000, dict(warm=512, chunks=1)),                                 # a single chunk
+    (140_000, dict(warm=2048, chunks=6, order_by="identity")),         # population order: warps reading > 2 RSI rows are flagged and re-run
+    (140_000, dict(warm=2048, chunks=6, order_by="row_thresholds")),   # the other packing
 ])
 def test_tiled_sweep_is_exact_and_self_repairing(torch_cuda, n_bars, opts):
     """Thread-per-lane sweep == serial reference semantics, whether or not the speculation holds."""
@@ -329,6 +331,8 @@ def test_tiled_sweep_is_exact_and_self_repairing(torch_cuda, n_bars, opts):
         assert first_invalid > 0                       # the fallback path really ran
     if opts.get("max_repair_rounds", 8) == 64:
         assert first_invalid == 0                      # every wrong boundary was repaired in place
+    if opts.get("order_by") == "identity":
+        assert first_invalid > 0                       # unpacked warps went through the exact fallback
     if "pool_blocks" in opts:
         assert first_overflow and first_invalid > 0    # (the second sweep planned a larger pool)
         assert not tiled.last_pool_overflow

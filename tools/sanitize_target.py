@@ -36,6 +36,7 @@ if "sweep" in legs:
     for mode, opts in (("tiled", dict(warm=0, chunks=12, max_repair_rounds=64)),      # repaired chunk by chunk, side stream
                        ("tiled", dict(warm=1024, chunks=6)),                          # speculation mostly right
                        ("tiled", dict(warm=512, chunks=6, pool_blocks=8)),            # pool overflow -> fused fallback
+                       ("tiled", dict(warm=1024, chunks=6, order_by="identity")),     # unpacked warps (> 2 RSI rows) -> flagged, fused fallback
                        ("chunked", dict(target_events=300, warm=0, max_chunks=16, max_repair_rounds=64)),
                        ("fused", {})):
         sw = PopulationSweep(market, event_cap=256, mode=mode, chunk_options=opts)

@@ -27,7 +27,7 @@ order = torch.from_numpy(evaluation_order(pop)).cuda()
 print("fused %.2f ms" % timed(None, order)); ref = fit.clone()
 ks = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else (0, 7, 11, 15)
 warms = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else (4096, 8192)
-orders = sys.argv[3].split(",") if len(sys.argv) > 3 else ("cost",)
+orders = sys.argv[3].split(",") if len(sys.argv) > 3 else ("row_cost",)
 for k, warm, ob in itertools.product(ks, warms, orders):
     plan = sw.plan_tiles(pop, warm=warm, order_by=ob, **({"chunks": k} if k else {}))
     ms = timed(plan)
