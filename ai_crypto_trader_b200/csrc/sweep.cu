@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(SW_WARPS * 32, SW_MIN_BLOCKS)
 sweep_kernel(const float* __restrict__ price, int64_t ld_price,
              const float* __restrict__ rsi, int64_t ld_rsi, int P, int S, int64_t N,
              const b200bt_individual* __restrict__ indiv, const int32_t* __restrict__ order, int pop,
+             const int* __restrict__ pop_dev,   // optional: number of entries of `order` to evaluate, on the device (<= pop)
              const b200bt_sweep_config cfg,  // NOT __grid_constant__: nvcc 12.9 miscompiled a loop-carried value with it
              b200bt_lane_stats* __restrict__ stats, uint32_t* __restrict__ events, int64_t ev_cap) {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -44,7 +45,7 @@ sweep_kernel(const float* __restrict__ price, int64_t ld_price,
     // in longest-processing-time-first order and the tail consists of cheap lanes.
     const int sym = (int)(blockIdx.x % (unsigned)S);
     const int k = (int)(blockIdx.x / (unsigned)S) * SW_WARPS + (threadIdx.x >> 5);
-    if (k >= pop) return;
+    if (k >= (pop_dev ? min(pop, *pop_dev) : pop)) return;
     const int ind = order ? order[k] : k;
     const b200bt_individual iv = indiv[ind];
     WarpShared* ws = reinterpret_cast<WarpShared*>(s_raw) + (threadIdx.x >> 5);
@@ -179,6 +180,29 @@ __global__ void fitness_reduce_kernel(const b200bt_lane_stats* __restrict__ stat
 
 using namespace b200bt;
 
+namespace b200bt {
+// The fused sweep over the first *pop_dev (<= pop) entries of `order`: the grid covers `pop` entries and warps beyond the
+// device-side count leave at once.  The exact fallback of the time-chunked sweeps: the list of individuals to re-run and its
+// length never leave the device.
+int launch_sweep(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S, int64_t N,
+                 const b200bt_individual* indiv, const int32_t* order, int pop, const int* pop_dev,
+                 const b200bt_sweep_config* cfg_host, b200bt_lane_stats* stats, uint32_t* events, int64_t event_cap,
+                 cudaStream_t stream) {
+    const int64_t blocks = (int64_t)((pop + SW_WARPS - 1) / SW_WARPS) * S;
+    B200BT_REQUIRE(blocks < (1ll << 31), B200BT_ELIMIT, "sweep: too many lanes");
+    const size_t smem = sizeof(WarpShared) * SW_WARPS;
+    // 16-byte cp.async needs every (symbol, period) row to start on a 16-byte boundary
+    const bool vec16 = (((uintptr_t)price | (uintptr_t)rsi) & 15) == 0 && ld_price % 4 == 0 && ld_rsi % 4 == 0;
+    auto kern = vec16 ? sweep_kernel<true> : sweep_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "sweep: cudaFuncSetAttribute");
+    kern<<<(unsigned)blocks, SW_WARPS * 32, smem, stream>>>(
+        price, ld_price, rsi, ld_rsi, P, S, N, indiv, order, pop, pop_dev, *cfg_host, stats, events, event_cap);
+    B200BT_LAUNCH_CHECK("sweep launch");
+    return B200BT_OK;
+}
+}  // namespace b200bt
+
 extern "C" int b200bt_sweep(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P,
                             int S, int64_t N, const b200bt_individual* indiv, const int32_t* order, int pop,
                             const b200bt_sweep_config* cfg_host, b200bt_lane_stats* stats,
@@ -195,18 +219,8 @@ extern "C" int b200bt_sweep(const float* price, int64_t ld_price, const float* r
     B200BT_REQUIRE(events == nullptr || event_cap > 0, B200BT_EINVAL, "sweep: event buffer without capacity");
     int rc = check_device();
     if (rc) return rc;
-    const int64_t blocks = (int64_t)((pop + SW_WARPS - 1) / SW_WARPS) * S;
-    B200BT_REQUIRE(blocks < (1ll << 31), B200BT_ELIMIT, "sweep: too many lanes");
-    const size_t smem = sizeof(WarpShared) * SW_WARPS;
-    // 16-byte cp.async needs every (symbol, period) row to start on a 16-byte boundary
-    const bool vec16 = (((uintptr_t)price | (uintptr_t)rsi) & 15) == 0 && ld_price % 4 == 0 && ld_rsi % 4 == 0;
-    auto kern = vec16 ? sweep_kernel<true> : sweep_kernel<false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_status(e, "sweep: cudaFuncSetAttribute");
-    kern<<<(unsigned)blocks, SW_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        price, ld_price, rsi, ld_rsi, P, S, N, indiv, order, pop, *cfg_host, stats, events, event_cap);
-    B200BT_LAUNCH_CHECK("sweep launch");
-    return B200BT_OK;
+    return launch_sweep(price, ld_price, rsi, ld_rsi, P, S, N, indiv, order, pop, nullptr, cfg_host, stats, events, event_cap,
+                        (cudaStream_t)stream);
 }
 
 extern "C" int b200bt_fitness_reduce(const b200bt_lane_stats* stats, int pop, int S, double* fitness,

@@ -39,6 +39,7 @@ struct ChunkScanArgs {
     uint2* pool; int pool_blocks; int* next; unsigned* alloc;
     int* seg_first; unsigned* seg_count; int2* seg_in; int2* seg_out; int* overflow;
     const int4* repair;   // REPAIR launches: (individual, chunk, segment, symbol) per work item
+    const unsigned* n_repair_dev;   // REPAIR launches: length of the work list (device)
     const int32_t* n_chunks;
     unsigned char* redo;  // REPAIR launches of the overlapped tail: individuals whose metrics must be recomputed
 };
@@ -52,27 +53,9 @@ __device__ __forceinline__ int64_t chunk_begin(int64_t N, int c, int K) {
 // REPAIR = true : re-scan of chunks whose assumed state was wrong, started AT T_c from the now known
 //                 true state (end state of the preceding chunk); one work item per listed chunk.
 template <bool VEC16, bool REPAIR>
-__global__ void __launch_bounds__(SW_WARPS * 32, 3)
-chunk_scan_kernel(const ChunkScanArgs A) {   // by value, not __grid_constant__ (see sweep.cu)
-    extern __shared__ __align__(16) unsigned char s_raw[];
+__device__ __forceinline__ void chunk_scan_item(const ChunkScanArgs& A, const b200bt_chunk_item item, const int sym, WarpShared* ws) {
     const int lane = threadIdx.x & 31;
-    int sym, it;
-    b200bt_chunk_item item;
-    if (REPAIR) {
-        it = (int)blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
-        if (it >= A.n_items) return;
-        const int4 r = A.repair[it];
-        item.individual = r.x; item.chunk = r.y; item.segment = r.z; item.n_chunks = A.n_chunks[r.x];
-        sym = r.w;
-        if (A.redo && lane == 0) A.redo[r.x] = 1;
-    } else {
-        sym = (int)(blockIdx.x % (unsigned)A.S);
-        it = (int)(blockIdx.x / (unsigned)A.S) * SW_WARPS + (threadIdx.x >> 5);
-        if (it >= A.n_items) return;
-        item = A.items[it];
-    }
     const b200bt_individual iv = A.indiv[item.individual];
-    WarpShared* ws = reinterpret_cast<WarpShared*>(s_raw) + (threadIdx.x >> 5);
     if (lane == 0) {
         ScanConst sc0;
         init_scan_const(sc0, iv);
@@ -220,6 +203,31 @@ chunk_scan_kernel(const ChunkScanArgs A) {   // by value, not __grid_constant__ 
     __syncwarp();
     while (m.qhead != qtail) flush((int)min(32u, m.qhead - qtail));
     if (lane == 0) A.seg_count[seg] = dead ? 0xffffffffu : m.qhead;
+    __syncwarp();
+}
+
+template <bool VEC16, bool REPAIR>
+__global__ void __launch_bounds__(SW_WARPS * 32, 3)
+chunk_scan_kernel(const ChunkScanArgs A) {   // by value, not __grid_constant__ (see sweep.cu)
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    WarpShared* ws = reinterpret_cast<WarpShared*>(s_raw) + (threadIdx.x >> 5);
+    if (REPAIR) {
+        // the work list and its length live on the device (written by chunk_verify_kernel of the same round): the grid has
+        // a fixed size and strides over the list, so the host never reads the count back
+        const int n = (int)*A.n_repair_dev;
+        for (int it = (int)blockIdx.x * SW_WARPS + (threadIdx.x >> 5); it < n; it += (int)gridDim.x * SW_WARPS) {
+            const int4 r = A.repair[it];
+            b200bt_chunk_item item;
+            item.individual = r.x; item.chunk = r.y; item.segment = r.z; item.n_chunks = A.n_chunks[r.x];
+            if (A.redo && (threadIdx.x & 31) == 0) A.redo[r.x] = 1;
+            chunk_scan_item<VEC16, true>(A, item, r.w, ws);
+        }
+    } else {
+        const int sym = (int)(blockIdx.x % (unsigned)A.S);
+        const int it = (int)(blockIdx.x / (unsigned)A.S) * SW_WARPS + (threadIdx.x >> 5);
+        if (it >= A.n_items) return;
+        chunk_scan_item<VEC16, false>(A, A.items[it], sym, ws);
+    }
 }
 
 // ---- thread-per-lane scan ---------------------------------------------------------------------------
@@ -290,16 +298,19 @@ struct LaneScanArgs {
 
 __device__ __forceinline__ int sym_of_block(unsigned bx, int S) { return (int)(bx % (unsigned)S); }
 
-// device-side tables the shared kernels expect: uniform K chunks per individual
-__global__ void lane_tables_kernel(int pop, int K, b200bt_chunk_item* __restrict__ items, int32_t* __restrict__ seg_base,
-                                   int32_t* __restrict__ n_chunks) {
+// device-side tables the shared kernels expect: uniform K chunks per individual.  Work items are listed in dispatch
+// order (`order`: individuals by predicted cost, a lane's chunks adjacent), so that the 32 chunks a warp of the
+// thread-per-chunk metrics kernels folds hold similar numbers of records; segments stay indexed by individual.
+__global__ void lane_tables_kernel(int pop, int K, const int32_t* __restrict__ order, b200bt_chunk_item* __restrict__ items,
+                                   int32_t* __restrict__ seg_base, int32_t* __restrict__ n_chunks) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pop * K) return;
-    const int ind = i / K, c = i - ind * K;
+    const int k = i / K, c = i - k * K;
+    const int ind = order ? order[k] : k;
     b200bt_chunk_item it;
-    it.individual = ind; it.chunk = c; it.n_chunks = K; it.segment = i;
+    it.individual = ind; it.chunk = c; it.n_chunks = K; it.segment = ind * K + c;
     items[i] = it;
-    if (c == 0) { seg_base[ind] = i; n_chunks[ind] = K; }
+    if (c == 0) { seg_base[ind] = ind * K; n_chunks[ind] = K; }
 }
 
 #ifndef B200BT_LS_MIN_BLOCKS
@@ -577,10 +588,14 @@ lane_scan_kernel(const LaneScanArgs A, const bool vec16) {   // by value, not __
 
 // One thread per (individual, symbol): list every chunk whose assumed state differs from the end state
 // of its predecessor while that predecessor is itself consistent (so its end state is the truth).
+// `n_repair` points at this round's counter (zero on entry); `n_prev` at the previous round's (NULL for the first
+// round): when the previous round found nothing to repair every boundary is consistent and the round is a no-op --
+// all rounds are launched unconditionally, the host never reads a count back.
 __global__ void chunk_verify_kernel(int pop, int S, const int32_t* __restrict__ seg_base,
                                     const int32_t* __restrict__ n_chunks, int n_seg, const unsigned* __restrict__ seg_count,
                                     const int2* __restrict__ seg_in, const int2* __restrict__ seg_out,
-                                    int4* __restrict__ repair, unsigned* __restrict__ n_repair) {
+                                    int4* __restrict__ repair, unsigned* __restrict__ n_repair, const unsigned* __restrict__ n_prev) {
+    if (n_prev && *n_prev == 0u) return;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)pop * S) return;
     const int ind = (int)(t / S), sym = (int)(t % S);
@@ -906,6 +921,20 @@ __global__ void fix_items_kernel(const b200bt_chunk_item* __restrict__ items, in
     if (redo[it.individual]) out[atomicAdd(n_out, 1)] = it;
 }
 
+// Individuals with a lane the chunked evaluation could not settle (a boundary still inconsistent after the repair rounds, a
+// full event pool, a warp not packed for the thread-per-lane scan): listed on the device for the exact fallback.
+__global__ void redo_list_kernel(int pop, int S, const unsigned char* __restrict__ invalid, int32_t* __restrict__ list,
+                                 int* __restrict__ n_list, int* __restrict__ n_invalid_lanes) {
+    const int ind = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ind >= pop) return;
+    int bad = 0;
+    for (int s = 0; s < S; ++s) bad += invalid[(int64_t)ind * S + s] ? 1 : 0;
+    if (bad) {
+        list[atomicAdd(n_list, 1)] = ind;
+        atomicAdd(n_invalid_lanes, bad);
+    }
+}
+
 __global__ void lane_combine_kernel(const b200bt_individual* __restrict__ indiv, int pop, int S,
                                     const int32_t* __restrict__ seg_base, const int32_t* __restrict__ n_chunks, int n_seg,
                                     const unsigned* __restrict__ seg_count, const int2* __restrict__ seg_in,
@@ -989,6 +1018,7 @@ using namespace b200bt;
 
 namespace {
 
+constexpr int REPAIR_COUNTERS = 130;   // >= the largest max_repair_rounds (K <= 120) + 2, and 2 + REPAIR_COUNTERS a multiple of 4 (alignment)
 struct ChunkWorkspace {
     uint2* pool; int2* seg_in; int2* seg_out; int* seg_first; unsigned* seg_count; unsigned* alloc; int* overflow;
     unsigned* n_repair; int4* repair; int* next; ChunkPartial* partial; double* seg_sum; double* seg_max;
@@ -997,7 +1027,7 @@ struct ChunkWorkspace {
 };
 
 // pool[pool_blocks][256] uint2 | seg_in[segs] int2 | seg_out[segs] int2 | seg_first[segs] | seg_count[segs] |
-// alloc, overflow, n_repair, pad | repair[segs] int4 | next[pool_blocks] | (16-byte aligned) partial[segs] (128 B) |
+// alloc, overflow, n_repair[REPAIR_COUNTERS] (one per round) | repair[segs] int4 | next[pool_blocks] | (16-byte aligned) partial[segs] (128 B) |
 // seg_sum[segs] | seg_max[segs] | fix_items[n_seg] (16 B) | n_fix (16 B) | redo[pop]
 // (wide types first: the base must be 16-byte aligned)
 ChunkWorkspace carve(void* workspace, int pool_blocks, int64_t segs, int n_seg, int pop) {
@@ -1010,7 +1040,7 @@ ChunkWorkspace carve(void* workspace, int pool_blocks, int64_t segs, int n_seg, 
     w.alloc = w.seg_count + segs;
     w.overflow = (int*)(w.alloc + 1);
     w.n_repair = (unsigned*)(w.overflow + 1);
-    w.repair = (int4*)(w.n_repair + 2);
+    w.repair = (int4*)(((uintptr_t)(w.n_repair + REPAIR_COUNTERS) + 15) & ~(uintptr_t)15);
     w.next = (int*)(w.repair + segs);
     w.partial = (ChunkPartial*)(((uintptr_t)(w.next + pool_blocks) + 15) & ~(uintptr_t)15);
     w.seg_sum = (double*)(w.partial + segs);
@@ -1023,7 +1053,7 @@ ChunkWorkspace carve(void* workspace, int pool_blocks, int64_t segs, int n_seg, 
 }
 
 int64_t chunk_workspace_bytes(int pool_blocks, int64_t segs, int n_seg, int pop) {
-    return (int64_t)pool_blocks * CK_BLOCK * 8 + segs * 16 + (segs * 2 + 4) * 4 + segs * 16 + (int64_t)pool_blocks * 4 + 16 +
+    return (int64_t)pool_blocks * CK_BLOCK * 8 + segs * 16 + (segs * 2 + 2 + REPAIR_COUNTERS) * 4 + 16 + segs * 16 + (int64_t)pool_blocks * 4 + 16 +
            segs * (int64_t)(sizeof(ChunkPartial) + 16) + (int64_t)n_seg * 16 + 16 + ((pop + 15) & ~15);
 }
 
@@ -1078,26 +1108,22 @@ int finish_chunks(const ChunkScanArgs& A, const ChunkWorkspace& w, const b200bt_
     const int64_t mblocks = (int64_t)((n_items + 3) / 4) * S;
     B200BT_REQUIRE(mblocks < (1ll << 31), B200BT_ELIMIT, "sweep_chunked: too many work items");
 
-    // one verify -> (readback) -> repair round on stream `rs`; *left = chunks listed (0: everything is consistent)
-    auto repair_round = [&](cudaStream_t rs, unsigned char* redo, unsigned* left) -> int {
-        cudaError_t er = cudaMemsetAsync(w.n_repair, 0, sizeof(unsigned), rs);
-        if (er != cudaSuccess) return cuda_status(er, "sweep_chunked: memset");
+    // One verify -> repair round on stream `rs`.  Nothing is read back: the verify kernel leaves the round's work list and
+    // its length on the device, the repair kernel (fixed grid) strides over it, and a round after a clean one is a no-op.
+    const unsigned repair_grid = 3u * 148u;
+    auto repair_round = [&](cudaStream_t rs, int round, unsigned char* redo) -> int {
         chunk_verify_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, rs>>>(pop, S, seg_base, A.n_chunks, n_seg, w.seg_count,
-                                                                             w.seg_in, w.seg_out, w.repair, w.n_repair);
+                                                                             w.seg_in, w.seg_out, w.repair, w.n_repair + round,
+                                                                             round ? w.n_repair + round - 1 : nullptr);
         B200BT_LAUNCH_CHECK("chunk_verify launch");
-        unsigned h_rep = 0;
-        er = cudaMemcpyAsync(&h_rep, w.n_repair, sizeof(unsigned), cudaMemcpyDeviceToHost, rs);
-        if (er == cudaSuccess) er = cudaStreamSynchronize(rs);
-        if (er != cudaSuccess) return cuda_status(er, "sweep_chunked: verify readback");
-        *left = h_rep;
-        if (h_rep == 0) return B200BT_OK;
         ChunkScanArgs R = A;
-        R.n_items = (int)h_rep;
+        R.n_repair_dev = w.n_repair + round;
         R.redo = redo;
-        kern_fix<<<(h_rep + SW_WARPS - 1) / SW_WARPS, SW_WARPS * 32, smem, rs>>>(R);
+        kern_fix<<<repair_grid, SW_WARPS * 32, smem, rs>>>(R);
         B200BT_LAUNCH_CHECK("chunk_repair launch");
         return B200BT_OK;
     };
+    // (the fix-up pass reuses the full-size grid with a device-side item count: CTAs beyond it leave at once)
     auto metrics = [&](const b200bt_chunk_item* its, const int* n_dev) -> int {
         chunk_sums_kernel<<<(unsigned)mblocks, 128, 0, st>>>(A.price, A.ld_price, A.indiv, its, n_items, S, n_seg, w.pool, w.next,
                                                               w.seg_first, w.seg_count, w.seg_in, w.seg_sum, w.seg_max, n_dev, A.pool_blocks);
@@ -1109,25 +1135,28 @@ int finish_chunks(const ChunkScanArgs& A, const ChunkWorkspace& w, const b200bt_
         return B200BT_OK;
     };
 
-    // rounds on the critical path
-    int round = 0, rc = B200BT_OK;
-    unsigned left = 1;
-    for (; round < max_repair_rounds && round < main_repair_rounds() && left; ++round)
-        if ((rc = repair_round(st, nullptr, &left))) return rc;
-    const bool tail = left != 0 && round < max_repair_rounds;   // a repair was just launched and more rounds are allowed
+    // Rounds on the critical path, then the rest on a second stream BESIDE the metrics kernels of all lanes: what remains
+    // after two rounds is a handful of lanes whose trajectories never merge and which are re-scanned chunk after chunk by
+    // one warp each; the individuals those rounds touch are flagged and only their metrics are recomputed afterwards.
+    int rc = B200BT_OK, round = 0;
+    B200BT_REQUIRE(max_repair_rounds + 1 < REPAIR_COUNTERS, B200BT_ELIMIT, "sweep_chunked: at most %d repair rounds", REPAIR_COUNTERS - 2);
+    for (; round < max_repair_rounds && round < main_repair_rounds(); ++round)
+        if ((rc = repair_round(st, round, nullptr))) return rc;
+    const bool tail = round < max_repair_rounds;
     SideStream* side = nullptr;
+    e = cudaMemsetAsync(w.n_fix, 0, 16 + ((pop + 15) & ~15), st);   // n_fix, redo-list length, flagged lanes + redo flags
+    if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: memset");
     if (tail) {
         if ((rc = side_stream(&side))) return rc;
-        e = cudaMemsetAsync(w.n_fix, 0, 16 + ((pop + 15) & ~15), st);   // n_fix + redo flags
-        if (e == cudaSuccess) e = cudaEventRecord(side->fork, st);
+        e = cudaEventRecord(side->fork, st);
         if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: fork");
     }
     if ((rc = metrics(items, nullptr))) return rc;
     if (tail) {
         e = cudaStreamWaitEvent(side->stream, side->fork, 0);
         if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: side wait");
-        for (; round < max_repair_rounds && left; ++round)
-            if ((rc = repair_round(side->stream, w.redo, &left))) return rc;
+        for (; round < max_repair_rounds; ++round)
+            if ((rc = repair_round(side->stream, round, w.redo))) return rc;
         e = cudaEventRecord(side->join, side->stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(st, side->join, 0);
         if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: join");
@@ -1139,8 +1168,18 @@ int finish_chunks(const ChunkScanArgs& A, const ChunkWorkspace& w, const b200bt_
                                                                         w.seg_in, w.seg_out, w.partial, *cfg_host, stats,
                                                                         lane_invalid);
     B200BT_LAUNCH_CHECK("lane_combine launch");
+    // exact fallback, driven from the device: the flagged individuals are listed and re-evaluated by the fused (serial)
+    // kernel; with nothing flagged its warps leave at once.  [n_fix + 1] = list length, [n_fix + 2] = flagged lanes.
+    int32_t* redo_list = reinterpret_cast<int32_t*>(w.fix_items);      // (the fix-up item list is no longer needed)
+    redo_list_kernel<<<(pop + 127) / 128, 128, 0, st>>>(pop, S, lane_invalid, redo_list, w.n_fix + 1, w.n_fix + 2);
+    B200BT_LAUNCH_CHECK("redo_list launch");
+    if ((rc = launch_sweep(A.price, A.ld_price, A.rsi, A.ld_rsi, A.P, S, A.N, A.indiv, redo_list, pop, w.n_fix + 1, cfg_host, stats,
+                           events, event_cap, st)))
+        return rc;
     if (overflow_host_or_null) {
+        // [0] = the event pool overflowed, [1] = lanes that went through the fallback (read by the host after its next sync)
         e = cudaMemcpyAsync(overflow_host_or_null, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(overflow_host_or_null + 1, w.n_fix + 2, sizeof(int), cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: overflow readback");
     }
     return B200BT_OK;
@@ -1187,7 +1226,7 @@ extern "C" int b200bt_sweep_chunked(const float* price, int64_t ld_price, const 
     const int64_t segs = (int64_t)S * n_seg;
     B200BT_REQUIRE(pop <= n_seg, B200BT_EINVAL, "sweep_chunked: fewer segments than individuals");
     const ChunkWorkspace w = carve(workspace, pool_blocks, segs, n_seg, pop);
-    cudaError_t e = cudaMemsetAsync(w.seg_in, 0, (size_t)(segs * 6 + 4) * 4, st);
+    cudaError_t e = cudaMemsetAsync(w.seg_in, 0, (size_t)(segs * 6 + 2 + REPAIR_COUNTERS) * 4, st);
     if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: memset");
 
     ChunkScanArgs A;
@@ -1239,7 +1278,7 @@ extern "C" int64_t b200bt_sweep_tiled_workspace_bytes(int pool_blocks, int S, in
 
 extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S,
                                   int64_t N, const float* zones_or_null, const b200bt_individual* indiv, const int32_t* slots,
-                                  int n_slots, int pop, int K, int warm, int max_repair_rounds, int pool_blocks, void* workspace,
+                                  int n_slots, const int32_t* order, int pop, int K, int warm, int max_repair_rounds, int pool_blocks, void* workspace,
                                   int64_t workspace_bytes, const b200bt_sweep_config* cfg_host, b200bt_lane_stats* stats,
                                   uint32_t* events, int64_t event_cap, unsigned char* lane_invalid, int* overflow_host_or_null,
                                   b200bt_stream_t stream) {
@@ -1266,9 +1305,9 @@ extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const fl
     b200bt_chunk_item* items = (b200bt_chunk_item*)(((uintptr_t)w.end + 15) & ~(uintptr_t)15);
     int32_t* seg_base = (int32_t*)(items + n_seg);
     int32_t* n_chunks = seg_base + pop;
-    cudaError_t e = cudaMemsetAsync(w.seg_in, 0, (size_t)(segs * 6 + 4) * 4, st);
+    cudaError_t e = cudaMemsetAsync(w.seg_in, 0, (size_t)(segs * 6 + 2 + REPAIR_COUNTERS) * 4, st);
     if (e != cudaSuccess) return cuda_status(e, "sweep_tiled: memset");
-    lane_tables_kernel<<<(n_seg + 255) / 256, 256, 0, st>>>(pop, K, items, seg_base, n_chunks);
+    lane_tables_kernel<<<(n_seg + 255) / 256, 256, 0, st>>>(pop, K, order, items, seg_base, n_chunks);
     B200BT_LAUNCH_CHECK("lane_tables launch");
 
     LaneScanArgs L;

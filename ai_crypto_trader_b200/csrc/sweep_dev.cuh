@@ -7,6 +7,12 @@
 
 namespace b200bt {
 
+// the fused sweep over a device-side list of individuals (sweep.cu): the exact fallback of the time-chunked sweeps
+int launch_sweep(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S, int64_t N,
+                 const b200bt_individual* indiv, const int32_t* order, int pop, const int* pop_dev,
+                 const b200bt_sweep_config* cfg_host, b200bt_lane_stats* stats, uint32_t* events, int64_t event_cap,
+                 cudaStream_t stream);
+
 constexpr int SW_WARPS = 8;         // warps (lanes of the sweep) per CTA
 #ifndef B200BT_SW_MIN_BLOCKS
 #define B200BT_SW_MIN_BLOCKS 2

@@ -185,8 +185,11 @@ def rsi_bank(close: torch.Tensor, periods: Sequence[int], fill: bool = True,
     return out
 
 
-def decode_population(population: List[Dict], period_row: Dict[int, int]) -> np.ndarray:
-    """List of GA parameter dicts -> packed b200bt_individual array (numpy structured)."""
+def decode_population(population: List[Dict], period_row: Dict[int, int], n_timeframes: int = 1) -> np.ndarray:
+    """List of GA parameter dicts -> packed b200bt_individual array (numpy structured).
+
+    With `n_timeframes` > 1 the bank holds one block of len(period_row) rows per timeframe and the gene
+    `rsi_timeframe` (an index into PopulationSweep.timeframes, default 0 = the base clock) selects the block."""
     dt = np.dtype([("rsi_row", "<i4"), ("rsi_lo", "<f4"), ("rsi_hi", "<f4"), ("reserved", "<i4"),
                    ("take_profit", "<f8"), ("stop_loss", "<f8"), ("position_size", "<f8")])
     assert dt.itemsize == C.sizeof(_lib.Individual)
@@ -201,6 +204,11 @@ def decode_population(population: List[Dict], period_row: Dict[int, int]) -> np.
     if len(period) and (period.min() < 0 or row.min() < 0):
         bad = int(period[(row < 0) | (period < 0)][0])
         raise KeyError(f"rsi_period {bad} is not in the RSI bank {sorted(period_row)}")
+    if n_timeframes > 1:
+        tf = g("rsi_timeframe", 0).astype(np.int64)
+        if len(tf) and (tf.min() < 0 or tf.max() >= n_timeframes):
+            raise KeyError(f"rsi_timeframe {int(tf[(tf < 0) | (tf >= n_timeframes)][0])} is not an index into the {n_timeframes} timeframes of the bank")
+        row = row + tf * len(period_row)
     out["rsi_row"] = row
     # thresholds rounded towards the side that keeps `rsi < oversold` / `rsi > overbought` exact in fp32
     lo, hi = g("rsi_oversold", 30), g("rsi_overbought", 70)
@@ -226,7 +234,6 @@ def lane_cost(p: Dict) -> float:
 
 
 EVENTS_PER_COST_BAR = 0.27
-TILED_MAX_PERIODS = 118     # shared-memory tile ring of the thread-per-lane sweep: 3 stages x (P + 1) rows x 560 B <= 200 KB
 
 
 def predicted_events(population: List[Dict], n_bars: int) -> np.ndarray:
@@ -263,12 +270,18 @@ def _duplicate_classes(packed: np.ndarray):
     return (first, inverse) if len(first) < len(packed) else None
 
 
-def costs_from_packed(packed: np.ndarray, periods: Sequence[int]) -> np.ndarray:
-    """lane_cost of already decoded individuals (b200bt_individual records): no second pass over the dicts."""
+def costs_from_packed(packed: np.ndarray, periods: Sequence[int], timeframes: Sequence[int] = (1,)) -> np.ndarray:
+    """lane_cost of already decoded individuals (b200bt_individual records): no second pass over the dicts.  An RSI row
+    of a k-times slower clock changes every k bars: its threshold crossings (events) are rarer by about sqrt(k)."""
     from scipy.special import ndtr
-    w = np.asarray(periods, dtype=np.float64)[packed["rsi_row"]]
+    P = len(periods)
+    w = np.asarray(periods, dtype=np.float64)[packed["rsi_row"] % P]
     sd = 44.0 / np.sqrt(np.maximum(w, 1.0))
-    return ndtr((packed["rsi_lo"].astype(np.float64) - 50.0) / sd) + 1.0 - ndtr((packed["rsi_hi"].astype(np.float64) - 50.0) / sd)
+    c = ndtr((packed["rsi_lo"].astype(np.float64) - 50.0) / sd) + 1.0 - ndtr((packed["rsi_hi"].astype(np.float64) - 50.0) / sd)
+    if len(timeframes) > 1:
+        k = np.asarray(timeframes, dtype=np.float64)[packed["rsi_row"] // P] / float(timeframes[0])
+        c = c / np.sqrt(k)
+    return c
 
 
 _SM_COUNT: Dict[int, int] = {}
@@ -282,17 +295,27 @@ def _sm_count(device) -> int:
     return _SM_COUNT[idx]
 
 
-_PINNED_FLAG = None
+_PINNED_FLAGS = None
 DEFERRED = torch.empty(0, dtype=torch.uint8)      # sentinel: the caller assigns plan.workspace (plan_batches)
+_FLAG_SLOTS = 256
 
 
-def _pinned_flag() -> torch.Tensor:
-    """One pinned int32 the kernels' pool-overflow flag is copied into (page-locking memory is slow: shared by
-    every plan; each sweep call reads it right after its own stream synchronisation)."""
-    global _PINNED_FLAG
-    if _PINNED_FLAG is None:
-        _PINNED_FLAG = torch.zeros(1, dtype=torch.int32).pin_memory()
-    return _PINNED_FLAG
+def _pinned_flags() -> torch.Tensor:
+    """Pinned int32 [256][2]: per plan (slice) of a sweep, [0] = the event pool overflowed, [1] = lanes that went through
+    the exact fallback.  The kernels' flags are copied here asynchronously; the host looks at them only after a stream
+    synchronisation it does anyway (page-locking memory is slow: one table shared by every plan)."""
+    global _PINNED_FLAGS
+    if _PINNED_FLAGS is None:
+        _PINNED_FLAGS = torch.zeros((_FLAG_SLOTS, 2), dtype=torch.int32).pin_memory()
+    return _PINNED_FLAGS
+
+
+_NEXT_FLAG = [0]
+
+
+def _flag_slot() -> torch.Tensor:
+    i = _NEXT_FLAG[0] = (_NEXT_FLAG[0] + 1) % _FLAG_SLOTS
+    return _pinned_flags()[i]
 
 
 class ChunkPlan:
@@ -337,7 +360,7 @@ class ChunkPlan:
         else:
             self.workspace = None if workspace is DEFERRED else torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
         self.invalid = torch.zeros((pop, n_symbols), dtype=torch.uint8, device=device)
-        self.overflow = _pinned_flag()
+        self.overflow = _flag_slot()
         self.pop = pop
 
 
@@ -361,13 +384,14 @@ class TilePlan:
     def __init__(self, population: List[Dict], n_bars: int, n_symbols: int, device, warm: int = 8192,
                  max_chunks: int = 64, chunks: Optional[int] = None, pool_scale: float = 1.5,
                  pool_blocks: Optional[int] = None, max_repair_rounds: Optional[int] = None, lo: int = 0,
-                 workspace: Optional[torch.Tensor] = None, order_by: str = "row_cost", pred: Optional[np.ndarray] = None):
+                 workspace: Optional[torch.Tensor] = None, order_by: str = "row_cost", pred: Optional[np.ndarray] = None,
+                 rows: Optional[np.ndarray] = None):
         pop = len(population)
         self.lo, self.pop = int(lo), pop
         self.warm = int(warm)
         pred = predicted_events(population, n_bars) if pred is None else np.asarray(pred, dtype=np.float64)
         # thread slots: 32 consecutive slots = one warp, which stages its own tiles and may read two distinct RSI rows
-        self.slots = pack_warps(population, pred, order_by)
+        self.slots = pack_warps(population, pred, order_by, rows)
         if chunks is None:
             chunks = self.chunks_for(pop, n_bars, n_symbols, device, warm, max_chunks, n_slots=len(self.slots))
         self.K = int(chunks)
@@ -378,20 +402,21 @@ class TilePlan:
         self.pool_blocks = int(pool_scale * pred.sum() * n_symbols / 256) + 2 * self.n_seg * n_symbols + 1024
         if pool_blocks is not None:
             self.pool_blocks = int(pool_blocks)
-        self.slots_dev = torch.from_numpy(self.slots).to(device)
+        self.order = np.ascontiguousarray(self.slots[self.slots >= 0])      # individuals in dispatch order
+        self.slots_dev = torch.from_numpy(np.concatenate([self.slots, self.order])).to(device)     # [slots | order]
         self.ws_bytes = int(_lib.load().b200bt_sweep_tiled_workspace_bytes(self.pool_blocks, n_symbols, pop, self.K))
         if workspace is not None and workspace.numel() >= self.ws_bytes:
             self.workspace = workspace
         else:
             self.workspace = None if workspace is DEFERRED else torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
         self.invalid = torch.zeros((pop, n_symbols), dtype=torch.uint8, device=device)
-        self.overflow = _pinned_flag()
+        self.overflow = _flag_slot()
 
 
 WARP_RSI_ROWS = 2       # distinct RSI rows the machines of one warp may read (csrc/sweep_chunked.cu LS_RSI_ROWS)
 
 
-def pack_warps(population: List[Dict], pred: np.ndarray, order_by: str = "row_cost") -> np.ndarray:
+def pack_warps(population: List[Dict], pred: np.ndarray, order_by: str = "row_cost", rows: Optional[np.ndarray] = None) -> np.ndarray:
     """Thread slots of the thread-per-lane scan: int32[n_warps * 32], the individual each slot runs, -1 = empty.
 
     A warp stages the price row and the RSI rows of its own 32 machines, at most WARP_RSI_ROWS of them, and its cost is
@@ -400,14 +425,15 @@ def pack_warps(population: List[Dict], pred: np.ndarray, order_by: str = "row_co
     row's tail shares a warp with the head of the next row; slots stay empty only where a third row would enter).  Warps
     are then dispatched most expensive first, so that the warps resident together (and the 8 of a CTA) cost the same.
     order_by = "identity" keeps the population order (testing: warps that break the row rule are re-run by the exact
-    fallback), "row_thresholds" sorts a row by (oversold, overbought) instead of cost."""
+    fallback), "row_thresholds" sorts a row by (oversold, overbought) instead of cost.  `rows`: the bank row of every
+    individual when it is not a function of `rsi_period` alone (several timeframes)."""
     n = len(population)
     if order_by == "identity":
         out = np.full(-(-n // 32) * 32, -1, dtype=np.int32)
         out[:n] = np.arange(n, dtype=np.int32)
         return out
     g = lambda key, default: np.array([float(p.get(key, default)) for p in population], dtype=np.float64)
-    row = g("rsi_period", 14).astype(np.int64)
+    row = g("rsi_period", 14).astype(np.int64) if rows is None else np.asarray(rows, dtype=np.int64)    # (bank row when given)
     pred = np.asarray(pred, dtype=np.float64)
     rows, inv = np.unique(row, return_inverse=True)
     mean_cost = np.bincount(inv, weights=pred) / np.maximum(np.bincount(inv), 1)
@@ -457,7 +483,7 @@ class PopulationSweep:
     def __init__(self, market: MarketData, rsi_periods: Iterable[int] = range(5, 31),
                  optimization_goals: Optional[Dict] = None, initial_capital: float = 10000.0,
                  event_cap: int = 0, mode: str = "auto", chunk_options: Optional[Dict] = None,
-                 score_on_advanced: bool = False):
+                 score_on_advanced: bool = False, timeframes: Sequence[int] = ()):
         """score_on_advanced: take the strategy score on calculate_advanced_metrics' dict (the composition of
         evaluate_strategy, strategy_evaluation.py:545-557: `expectancy`, `sortino_ratio`, ... exist as keys) instead of the
         plain calculate_metrics dict (cross_validate_strategy :683-691, the default).
@@ -472,7 +498,14 @@ class PopulationSweep:
         self.cfg = _lib.SweepConfig(initial_capital=float(initial_capital), minute0=market.minute0,
                                     bar_minutes=market.bar_minutes, primary=primary, secondary_mask=mask, variant=0)
         self.event_cap = int(event_cap)
-        self.bank = self._bank_behind_the_upload(market)
+        # timeframes (minutes per bar, the first one = the market's own clock): BASELINE configs[3] evaluates the RSI rule on
+        # 1m / 5m / 15m indicators (recipe: services/market_monitor_service.py:219-301); the bank then holds one block of rows
+        # per timeframe, each higher-timeframe RSI brought back to the base clock by "last completed bar", and the gene
+        # `rsi_timeframe` (index into `timeframes`) selects the block
+        self.timeframes = tuple(int(k) for k in timeframes) or (market.bar_minutes,)
+        if self.timeframes[0] != market.bar_minutes or any(k % market.bar_minutes for k in self.timeframes):
+            raise ValueError("timeframes must start with the market's own bar spacing and be multiples of it")
+        self.bank = self._bank_behind_the_upload(market) if len(self.timeframes) == 1 else self._multi_timeframe_bank(market)
         self.mode, self.chunk_min_bars, self.chunk_options = mode, 131072, dict(chunk_options or {})
         self._stats = None
         self._events = None
@@ -497,6 +530,23 @@ class PopulationSweep:
         market._join_close()                           # the current stream now waits for copies AND bank rows
         return bank
 
+    def _multi_timeframe_bank(self, market: MarketData) -> torch.Tensor:
+        """[S][T * P][N] bank: block 0 = RSI of the base clock, block i = RSI of the clock-aligned timeframes[i]-minute bars
+        (b200bt_resample), NaN policy applied on that clock like the reference's analyzer does per kline series, then aligned
+        to the base clock with the value of the last COMPLETED higher-timeframe bar (b200bt_align: no look-ahead; NaN before
+        the first completed bar, where no threshold compare is true)."""
+        from . import indicators as ind
+        P, T = len(self.periods), len(self.timeframes)
+        bank = torch.empty((market.S, T * P, market.N), dtype=torch.float32, device=market.device)
+        bank[:, :P] = rsi_bank(market.close, self.periods)
+        for i, k in enumerate(self.timeframes[1:], start=1):
+            hi = ind.resample(market, k)
+            rows = rsi_bank(hi.close, self.periods)                                        # [S][P][M]
+            aligned = ind.align_to_base(rows.view(market.S * P, hi.N), market, k)          # [S * P][N]
+            bank[:, i * P:(i + 1) * P] = aligned.view(market.S, P, market.N)
+            del hi, rows, aligned
+        return bank
+
     @classmethod
     def from_bank(cls, market: MarketData, bank: torch.Tensor, periods, optimization_goals=None,
                   initial_capital: float = 10000.0, event_cap: int = 0, mode: str = "fused",
@@ -512,6 +562,7 @@ class PopulationSweep:
         self.cfg = _lib.SweepConfig(initial_capital=float(initial_capital), minute0=market.minute0,
                                     bar_minutes=market.bar_minutes, primary=primary, secondary_mask=mask, variant=0)
         self.event_cap = int(event_cap)
+        self.timeframes = (market.bar_minutes,)
         assert bank.is_cuda and bank.dtype == torch.float32 and tuple(bank.shape) == (market.S, len(self.periods), market.N)
         self.bank = bank.contiguous()
         self.mode, self.chunk_min_bars, self.chunk_options = mode, 131072, {}
@@ -529,7 +580,7 @@ class PopulationSweep:
         if plan is not None:
             plans = plan if isinstance(plan, (list, tuple)) else [plan]
             self._ensure_buffers(pop)
-            self.last_invalid_lanes, self.last_pool_overflow = 0, False
+            self._last_plans = plans
             for pl in plans:
                 (self._evaluate_tiled if isinstance(pl, TilePlan) else self._evaluate_chunked)(indiv_dev, pl)
             with torch.cuda.device(self.market.device):
@@ -537,6 +588,7 @@ class PopulationSweep:
                           _lib.current_stream())
             return
         m = self.market
+        self._last_plans = []
         if self._stats is None or self._pop != pop:
             self._stats = torch.empty((pop, m.S, _lib.LANE_STATS_WORDS), dtype=torch.float64, device=m.device)
             self._events = (torch.zeros((pop, m.S, self.event_cap), dtype=torch.int32, device=m.device)
@@ -545,7 +597,7 @@ class PopulationSweep:
         with torch.cuda.device(m.device):
             st = _lib.current_stream()
             _lib.call("b200bt_sweep", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(),
-                      _lib.ld(self.bank), len(self.periods), m.S, m.N, indiv_dev.data_ptr(),
+                      _lib.ld(self.bank), self.bank.shape[1], m.S, m.N, indiv_dev.data_ptr(),
                       _lib.ptr(order_dev), pop, C.byref(self.cfg), self._stats.data_ptr(),
                       _lib.ptr(self._events), self.event_cap, st)
             _lib.call("b200bt_fitness_reduce", self._stats.data_ptr(), pop, m.S, fitness_dev.data_ptr(), st)
@@ -568,20 +620,12 @@ class PopulationSweep:
         with torch.cuda.device(m.device):
             st = _lib.current_stream()
             _lib.call("b200bt_sweep_chunked", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
-                      len(self.periods), m.S, m.N, indiv_dev.data_ptr() + lo * C.sizeof(_lib.Individual),
+                      self.bank.shape[1], m.S, m.N, indiv_dev.data_ptr() + lo * C.sizeof(_lib.Individual),
                       plan.order_dev.data_ptr(), n,
                       plan.items.data_ptr(), plan.n_seg, plan.seg_base_dev.data_ptr(), plan.n_chunks_dev.data_ptr(),
                       plan.n_seg, plan.warm, plan.max_repair_rounds, plan.pool_blocks, plan.workspace.data_ptr(), plan.workspace.numel(),
                       C.byref(self.cfg), stats.data_ptr(), _lib.ptr(events), self.event_cap,
                       plan.invalid.data_ptr(), plan.overflow.data_ptr(), st)
-            bad = torch.nonzero(plan.invalid.any(dim=1)).flatten()          # device -> host sync (tiny)
-            self.last_invalid_lanes += int(plan.invalid.sum().item())
-            self.last_pool_overflow |= bool(plan.overflow.item())
-            if bad.numel():
-                redo = (bad + lo).to(torch.int32).contiguous()
-                _lib.call("b200bt_sweep", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
-                          len(self.periods), m.S, m.N, indiv_dev.data_ptr(), redo.data_ptr(), int(redo.numel()),
-                          C.byref(self.cfg), self._stats.data_ptr(), _lib.ptr(self._events), self.event_cap, st)
 
     def _evaluate_tiled(self, indiv_dev, plan: "TilePlan") -> None:
         """One slice of the population through the thread-per-lane kernels (same verification / fallback)."""
@@ -592,19 +636,29 @@ class PopulationSweep:
         with torch.cuda.device(m.device):
             st = _lib.current_stream()
             _lib.call("b200bt_sweep_tiled", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
-                      len(self.periods), m.S, m.N, _lib.ptr(self._zones_if_amortised()),
+                      self.bank.shape[1], m.S, m.N, _lib.ptr(self._zones_if_amortised()),
                       indiv_dev.data_ptr() + lo * C.sizeof(_lib.Individual),
-                      plan.slots_dev.data_ptr(), int(plan.slots_dev.numel()), n, plan.K, plan.warm, plan.max_repair_rounds, plan.pool_blocks,
+                      plan.slots_dev.data_ptr(), len(plan.slots), plan.slots_dev.data_ptr() + 4 * len(plan.slots), n, plan.K, plan.warm,
+                      plan.max_repair_rounds, plan.pool_blocks,
                       plan.workspace.data_ptr(), plan.workspace.numel(), C.byref(self.cfg), stats.data_ptr(),
                       _lib.ptr(events), self.event_cap, plan.invalid.data_ptr(), plan.overflow.data_ptr(), st)
-            bad = torch.nonzero(plan.invalid.any(dim=1)).flatten()          # device -> host sync (tiny)
-            self.last_invalid_lanes += int(plan.invalid.sum().item())
-            self.last_pool_overflow |= bool(plan.overflow.item())
-            if bad.numel():
-                redo = (bad + lo).to(torch.int32).contiguous()
-                _lib.call("b200bt_sweep", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
-                          len(self.periods), m.S, m.N, indiv_dev.data_ptr(), redo.data_ptr(), int(redo.numel()),
-                          C.byref(self.cfg), self._stats.data_ptr(), _lib.ptr(self._events), self.event_cap, st)
+
+    # Lanes the time-chunked kernels flagged (a boundary still inconsistent after the repair rounds, a full event pool, a warp
+    # not packed for the thread-per-lane scan) are re-evaluated by the fused kernel ON THE DEVICE, inside b200bt_sweep_chunked /
+    # b200bt_sweep_tiled: an evaluation reads nothing back.  These two look at the flags of the last evaluation afterwards.
+    def _sync_flags(self):
+        torch.cuda.current_stream(self.market.device).synchronize()
+        return [pl.overflow for pl in (getattr(self, "_last_plans", None) or [])]
+
+    @property
+    def last_invalid_lanes(self) -> int:
+        """(individual, symbol) lanes of the last evaluation that went through the exact fallback."""
+        return int(sum(int(f[1]) for f in self._sync_flags()))
+
+    @property
+    def last_pool_overflow(self) -> bool:
+        """The event pool of the last evaluation was too small (its lanes were re-run exactly; the next plan is larger)."""
+        return any(bool(f[0]) for f in self._sync_flags())
 
     def set_gap(self, gap_bar: int, gap_minutes: int) -> None:
         """Declare the series as two pieces glued at `gap_bar`, the second one `gap_minutes` later on the calendar
@@ -615,11 +669,11 @@ class PopulationSweep:
         """(min, max) per 32-bar block of the price rows and of the RSI bank (b200bt_zone_map), built on first use."""
         if getattr(self, "_zones", None) is None:
             m = self.market
-            n = int(_lib.load().b200bt_zone_map_floats(len(self.periods), m.S, m.N))
+            n = int(_lib.load().b200bt_zone_map_floats(self.bank.shape[1], m.S, m.N))
             z = torch.empty(n, dtype=torch.float32, device=m.device)
             with torch.cuda.device(m.device):
                 _lib.call("b200bt_zone_map", m.close.data_ptr(), _lib.ld(m.close), self.bank.data_ptr(), _lib.ld(self.bank),
-                          len(self.periods), m.S, m.N, z.data_ptr(), _lib.current_stream())
+                          self.bank.shape[1], m.S, m.N, z.data_ptr(), _lib.current_stream())
             self._zones = z
         return self._zones
 
@@ -633,13 +687,13 @@ class PopulationSweep:
             return None
         return self.zone_map()
 
-    def plan(self, population: List[Dict], pred: Optional[np.ndarray] = None) -> Optional[List]:
+    def plan(self, population: List[Dict], pred: Optional[np.ndarray] = None, rows: Optional[np.ndarray] = None) -> Optional[List]:
         """The kernel path `evaluate` takes for this population under self.mode: None = fused kernel, else the
         list of TilePlan / ChunkPlan slices to pass to evaluate_device(plan=...).  `pred`: predicted_events of the
         population when the caller already has it (evaluate derives it from the decoded records)."""
         long_enough = self.market.N >= self.chunk_min_bars
         tiled = self.mode == "tiled"
-        if self.mode == "auto" and long_enough and len(self.periods) <= TILED_MAX_PERIODS:
+        if self.mode == "auto" and long_enough:
             # thread-per-lane needs many machines: enough chunks per lane, or enough lanes (tools/mode_crossover.py:
             # at 200k bars the warp-per-chunk path is faster below ~2000 individuals x 10 symbols)
             k = TilePlan.chunks_for(len(population), self.market.N, self.market.S, self.market.device,
@@ -650,10 +704,12 @@ class PopulationSweep:
         options = dict(self.chunk_options)
         if not tiled and self.mode == "auto":
             options.setdefault("target_events", 8192)
-        if getattr(self, "last_pool_overflow", False):      # the previous sweep ran out of event pool: plan larger
+        if getattr(self, "_last_plans", None) and self.last_pool_overflow:      # the previous sweep ran out of event pool: plan larger
             options["pool_scale"] = 4.0 * options.get("pool_scale", 1.5)
             options.pop("pool_blocks", None)
-        return self.plan_batches(population, tiled=tiled, pred=pred, **options)
+        if tiled and rows is None and len(self.timeframes) > 1:
+            rows = decode_population(population, self.period_row, len(self.timeframes))["rsi_row"]
+        return self.plan_batches(population, tiled=tiled, pred=pred, rows=rows, **options)
 
     def plan_tiles(self, population: List[Dict], **kw) -> "TilePlan":
         return TilePlan(population, self.market.N, self.market.S, self.market.device, **kw)
@@ -662,7 +718,7 @@ class PopulationSweep:
         return ChunkPlan(population, self.market.N, self.market.S, self.market.device, **kw)
 
     def plan_batches(self, population: List[Dict], max_pool_bytes: int = 8 << 30, tiled: bool = False,
-                     pred: Optional[np.ndarray] = None, **kw) -> List:
+                     pred: Optional[np.ndarray] = None, rows: Optional[np.ndarray] = None, **kw) -> List:
         """Plans for contiguous slices of the population whose event pools each stay below `max_pool_bytes`
         and share one workspace: large populations (BASELINE configs[4]: 10 000 x 50 symbols) record more
         events than fit in HBM at once, so they go through the chunked kernels slice by slice."""
@@ -671,11 +727,12 @@ class PopulationSweep:
         kw = {k: v for k, v in kw.items() if k in accepted}
         if pred is None:
             pred = predicted_events(population, self.market.N)
+        rows_of = (lambda lo, hi: {"rows": None if rows is None else rows[lo:hi]}) if tiled else (lambda lo, hi: {})
         if kw.get("pool_blocks") is not None:
-            return [cls(population, self.market.N, self.market.S, self.market.device, pred=pred, **kw)]
+            return [cls(population, self.market.N, self.market.S, self.market.device, pred=pred, **rows_of(0, None), **kw)]
         pool_bytes = pred * (self.market.S * 8 * kw.get("pool_scale", 1.5))
         if float(pool_bytes.sum()) <= max_pool_bytes:
-            return [cls(population, self.market.N, self.market.S, self.market.device, pred=pred, **kw)]
+            return [cls(population, self.market.N, self.market.S, self.market.device, pred=pred, **rows_of(0, None), **kw)]
         cuts, acc = [0], 0.0
         for i, b in enumerate(pool_bytes):
             if acc + b > max_pool_bytes and i > cuts[-1]:
@@ -684,7 +741,7 @@ class PopulationSweep:
             acc += b
         cuts.append(len(population))
         plans = [cls(population[lo:hi], self.market.N, self.market.S, self.market.device, lo=lo, workspace=DEFERRED,
-                     pred=pred[lo:hi], **kw) for lo, hi in zip(cuts[:-1], cuts[1:])]
+                     pred=pred[lo:hi], **rows_of(lo, hi), **kw) for lo, hi in zip(cuts[:-1], cuts[1:])]
         shared = torch.empty(max(pl.ws_bytes for pl in plans), dtype=torch.uint8, device=self.market.device)
         for pl in plans:
             pl.workspace = shared        # the slices run one after the other on the same stream
@@ -697,7 +754,7 @@ class PopulationSweep:
         if not population:
             return np.zeros(0, dtype=np.float64)
         dev = self.market.device
-        packed = decode_population(population, self.period_row)
+        packed = decode_population(population, self.period_row, len(self.timeframes))
         # individuals that decode to the same kernel parameters (the reference rule reads 6 of the 18 genes,
         # and elitism / crossover copy individuals) are evaluated once
         expand = None
@@ -712,8 +769,8 @@ class PopulationSweep:
             population = [population[i] for i in keep]
         self.last_unique = len(population)
         pop = len(population)
-        pred = EVENTS_PER_COST_BAR * costs_from_packed(packed, self.periods) * self.market.N
-        plan = self.plan(population, pred=pred)
+        pred = EVENTS_PER_COST_BAR * costs_from_packed(packed, self.periods, self.timeframes) * self.market.N
+        plan = self.plan(population, pred=pred, rows=packed["rsi_row"])
         if plan is None:       # the fused kernel dispatches in this order: same RSI period adjacent, most expensive first
             order = np.lexsort((np.arange(pop), -pred, packed["rsi_row"])).astype(np.int32)
         else:

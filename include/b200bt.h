@@ -253,7 +253,11 @@ int b200bt_sweep(const float* price, int64_t ld_price,
  *  items      [n_items] device      seg_base, n_chunks  [pop] device int32      n_seg = sum of n_chunks
  *  pool_blocks  event pool size in blocks of 256 events; a chunk that cannot get a block flags its lane
  *  workspace  b200bt_sweep_chunked_workspace_bytes(pool_blocks, S, n_seg) device bytes
- *  overflow_host_or_null  optional pinned host int receiving 1 if the pool ran out (grow it next time) */
+ *  overflow_host_or_null  optional PINNED host int[2], written asynchronously on `stream` (read after synchronising it):
+ *                         [0] = 1 if the event pool ran out (grow it next time), [1] = number of (individual, symbol)
+ *                         lanes that were flagged and re-evaluated by the exact fallback.
+ * Flagged lanes are re-evaluated by the fused kernel (b200bt_sweep's) inside this call, from a device-side list: the call
+ * reads nothing back and never synchronises; lane_invalid reports which lanes took that path. */
 typedef struct b200bt_chunk_item {
     int32_t individual;
     int32_t chunk;
@@ -279,6 +283,8 @@ int b200bt_sweep_chunked(const float* price, int64_t ld_price, const float* rsi,
  *        slots form a warp, which may read at most TWO distinct RSI rows (rsi_row) -- the host packs individuals by row and
  *        similar cost; a warp that breaks the rule is not scanned: its lanes are flagged in lane_invalid and the caller
  *        re-evaluates them with b200bt_sweep (exact).  NULL = identity (thread k runs individual k).
+ * order: device int32[pop], the individuals in dispatch order (by predicted cost), NULL = identity: the order in which the
+ *        per-chunk metrics kernels list their work (one thread per chunk: neighbours should hold similar record counts).
  * zones: optional zone map of the same price / RSI arrays (b200bt_zone_map), NULL = none: (min, max) per 32-bar
  *        block of every row, which lets a warp skip blocks in which none of its machines' thresholds can be crossed.
  * Shared memory does not depend on P (any number of RSI rows). */
@@ -287,8 +293,8 @@ int b200bt_zone_map(const float* price, int64_t ld_price, const float* rsi, int6
                     float* zones, b200bt_stream_t stream);
 int64_t b200bt_sweep_tiled_workspace_bytes(int pool_blocks, int S, int pop, int K);
 int b200bt_sweep_tiled(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S,
-                       int64_t N, const float* zones, const b200bt_individual* indiv, const int32_t* slots, int n_slots, int pop,
-                       int K, int warm, int max_repair_rounds, int pool_blocks, void* workspace, int64_t workspace_bytes,
+                       int64_t N, const float* zones, const b200bt_individual* indiv, const int32_t* slots, int n_slots,
+                       const int32_t* order, int pop, int K, int warm, int max_repair_rounds, int pool_blocks, void* workspace, int64_t workspace_bytes,
                        const b200bt_sweep_config* cfg, b200bt_lane_stats* stats, uint32_t* events,
                        int64_t event_cap, unsigned char* lane_invalid, int* overflow_host_or_null,
                        b200bt_stream_t stream);

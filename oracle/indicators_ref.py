@@ -151,3 +151,22 @@ def analyzer_scalars(open_, high, low, close, volume) -> dict:
     return {"rsi": last(c["rsi"]), "stoch_k": last(c["stoch_k"]), "stoch_d": last(c["stoch_d"]), "macd": last(c["macd"]),
             "macd_signal": last(c["macd_signal"]), "williams_r": last(c["williams_r"]), "bb_position": last(c["bb_position"]),
             "volatility": last(c["atr"]) / last_close, "trend": trend, "trend_strength": abs(strength)}
+
+
+def rsi_rows_on_timeframe(close32: np.ndarray, minute0: int, k: int, periods, bar_minutes: int = 1) -> np.ndarray:
+    """[P][N] float32: RSI of the clock-aligned k-minute closes (last close of each bucket, like an exchange kline /
+    pandas resample), NaN-filled on that clock the TechnicalAnalyzer way, then brought back to the base clock with the value
+    of the last COMPLETED k-minute bar (no look-ahead; NaN before the first completed bar).  The multi-timeframe recipe of
+    services/market_monitor_service.py:219-301 applied to one derived series -- the contract of PopulationSweep's
+    multi-timeframe bank (b200bt_resample -> b200bt_rsi_bank -> b200bt_align)."""
+    n = len(close32)
+    m = minute0 + np.arange(n, dtype=np.int64) * bar_minutes
+    bucket = m // k - minute0 // k
+    last = np.zeros(int(bucket[-1]) + 1, dtype=np.int64)
+    last[bucket] = np.arange(n)                                   # ascending assignment: the last bar of each bucket wins
+    rows = rsi_bank(np.asarray(close32, dtype=np.float32)[last], periods)      # [P][M] float32
+    closes_here = ((m + bar_minutes) // k) != (m // k)
+    j = np.where(closes_here, bucket, bucket - 1)
+    out = rows[:, np.maximum(j, 0)].astype(np.float32)
+    out[:, j < 0] = np.nan
+    return out

@@ -362,3 +362,56 @@ def test_evaluate_edge_populations(torch_cuda):
                                      sim_oracle.config_of(market.minute0, 1))
         assert f.shape == (1,) and f[0] == pytest.approx(float(want["score"]), rel=1e-9, abs=1e-12)
         assert int(sweep.lane_stats()["n_records"][0, 0]) == int(want["n_records"])
+
+
+def test_multi_timeframe_bank_and_sweep(torch_cuda):
+    """BASELINE configs[3]: RSI banks on 1m / 5m / 15m (device resample -> RSI -> align to the 1-minute clock), the gene
+    `rsi_timeframe` selecting the block: bank rows against the pandas/NumPy restatement, lanes against the C oracle fed
+    those rows -- through the fused kernel and through the thread-per-lane kernels (78 RSI rows)."""
+    from ai_crypto_trader_b200 import synth
+    from ai_crypto_trader_b200.sweep import MarketData, PopulationSweep
+    from oracle import indicators_ref, sim_oracle
+    import random
+    S, N, POP = 2, 150_001, 200
+    minute0 = synth.EPOCH_2024_MINUTES + 7                       # not aligned to the 5 / 15 minute grid
+    ohlcv = synth.synth_ohlcv(S, N, first_symbol=4)
+    market = MarketData(ohlcv, minute0=minute0)
+    tfs = (1, 5, 15)
+    population = synth.random_population(POP, seed=21)
+    rnd = random.Random(5)
+    for p in population:
+        p["rsi_timeframe"] = rnd.randint(0, 2)
+    population[0].update(rsi_oversold=35, rsi_overbought=65, rsi_period=5, take_profit=1, stop_loss=1, rsi_timeframe=2)
+    cfg = sim_oracle.config_of(minute0, 1)
+    want = None
+    for mode, opts in (("fused", {}), ("tiled", dict(chunks=6, warm=4096))):
+        sweep = PopulationSweep(market, timeframes=tfs, mode=mode, chunk_options=opts, event_cap=0)
+        P = len(sweep.periods)
+        assert tuple(sweep.bank.shape) == (S, 3 * P, N)
+        if want is None:
+            bank = sweep.bank.cpu().numpy()
+            rows = {}
+            for s in range(S):
+                rows[s, 0] = indicators_ref.rsi_bank(ohlcv[3, s], sweep.periods)
+                for i, k in enumerate(tfs[1:], start=1):
+                    rows[s, i] = indicators_ref.rsi_rows_on_timeframe(ohlcv[3, s], minute0, k, sweep.periods)
+                for i in range(3):
+                    got, ref = bank[s, i * P:(i + 1) * P], rows[s, i]
+                    assert np.array_equal(np.isnan(got), np.isnan(ref)), (s, i)
+                    neq = (got != ref) & ~np.isnan(ref)
+                    assert int(neq.sum()) <= max(2, int(2e-6 * ref.size)), (s, i, int(neq.sum()))   # double-rounding ties only
+            want = np.zeros((POP, S), dtype=sim_oracle.STATS_DTYPE)
+            for s in range(S):
+                for i, p in enumerate(population):
+                    r = rows[s, p["rsi_timeframe"]][sweep.period_row[p["rsi_period"]]]
+                    want[i, s] = sim_oracle.lane(ohlcv[3, s], r, p, cfg)[0]
+        for _ in range(2):
+            fit = sweep.evaluate(population)
+        st = sweep.lane_stats()
+        assert np.array_equal(st["n_records"], want["n_records"]), mode
+        assert np.array_equal(st["trade_hash"], want["trade_hash"]), mode
+        np.testing.assert_allclose(st["score"], want["score"], rtol=1e-9, atol=1e-11, equal_nan=True)
+        np.testing.assert_allclose(fit, want["score"].mean(axis=1), rtol=1e-9, atol=1e-11, equal_nan=True)
+        if mode == "tiled":
+            assert sweep.last_invalid_lanes == 0             # packed by bank row: no warp reads more than two rows
+    assert len({int(r) for r in want["n_records"][:, 0]}) > 20
