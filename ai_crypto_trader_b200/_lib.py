@@ -98,6 +98,7 @@ _SIGNATURES = {
     "b200bt_last_error": (C.c_char_p, []),
     "b200bt_launch_count": (C.c_int64, []),
     "b200bt_rsi_bank": (C.c_int, [_vp, _i, _i64, _i64, C.POINTER(C.c_int), _i, _i, _vp, _vp]),
+    "b200bt_rsi_bank_zones": (C.c_int, [_vp, _i, _i64, _i64, C.POINTER(C.c_int), _i, _vp, _vp, _i, _i, _vp]),
     "b200bt_ema_bank": (C.c_int, [_vp, _i, _i64, _i64, C.POINTER(C.c_int), _i, _vp, _vp]),
     "b200bt_sma_bank": (C.c_int, [_vp, _i, _i64, _i64, C.POINTER(C.c_int), _i, _vp, _vp]),
     "b200bt_macd": (C.c_int, [_vp, _i, _i64, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]),

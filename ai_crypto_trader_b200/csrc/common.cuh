@@ -35,6 +35,14 @@ inline int cuda_status(cudaError_t e, const char* what) {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// Zone map of a sweep's price / RSI rows (b200bt_zone_map, csrc/sweep_chunked.cu): (min, max) per 32-bar block ("coarse")
+// and per 4-bar group ("fine") of every row.  Layout: coarse [S][P + 1][zone_row_stride(N)] float2, then fine
+// [S][P + 1][zone_fine_stride(N)] float2, row 0 = price; rows are 16-byte aligned and padded with (NaN, NaN).
+constexpr int ZONE_BLOCK = 32;          // bars per coarse range
+constexpr int ZONE_TILE = 128;          // bars per tile of the thread-per-lane scan (fine rows hold whole tiles)
+__host__ __device__ constexpr int64_t zone_row_stride(int64_t N) { return (((N + ZONE_BLOCK - 1) / ZONE_BLOCK) + 1) & ~(int64_t)1; }
+__host__ __device__ constexpr int64_t zone_fine_stride(int64_t N) { return ((N + ZONE_TILE - 1) / ZONE_TILE) * (ZONE_TILE / 4); }
+
 __device__ __forceinline__ double shfl_up_d(double v, int d) {
     return __shfl_up_sync(FULL, v, d);
 }

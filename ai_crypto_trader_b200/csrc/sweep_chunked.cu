@@ -328,10 +328,7 @@ constexpr int LS_WARPS = LS_THREADS / 32;
 constexpr int LS_RSI_ROWS = 2;                // distinct RSI rows the 32 machines of a warp may read (host packing)
 constexpr int LS_ROWS = 1 + LS_RSI_ROWS;      // staged rows per warp: price + its RSI rows
 
-// row stride (float2 entries) of the zone map: rows start 16-byte aligned so that a tile's ranges move as one bulk copy
-__host__ __device__ constexpr int64_t zone_row_stride(int64_t N) { return (((N + LS_ZONE - 1) / LS_ZONE) + 1) & ~(int64_t)1; }
-// row stride (float2 entries) of the fine (4-bar) ranges: whole 128-bar tiles
-__host__ __device__ constexpr int64_t zone_fine_stride(int64_t N) { return ((N + LS_T - 1) / LS_T) * (LS_T / 4); }
+static_assert(LS_ZONE == ZONE_BLOCK && LS_T == ZONE_TILE, "zone map layout (common.cuh) follows the scan's tile");
 
 // Tile movement.  The 32 machines of a warp read the price row and (the host packs them so) at most LS_RSI_ROWS RSI rows.
 // Every WARP owns a private ring of LS_STAGES shared-memory stages, each holding one 128-bar tile of those rows plus the
@@ -1177,9 +1174,11 @@ int finish_chunks(const ChunkScanArgs& A, const ChunkWorkspace& w, const b200bt_
                            events, event_cap, st)))
         return rc;
     if (overflow_host_or_null) {
-        // [0] = the event pool overflowed, [1] = lanes that went through the fallback (read by the host after its next sync)
+        // [0] = the event pool overflowed, [1] = lanes that went through the fallback, [2] = pool blocks handed out (read by
+        // the host after its next sync)
         e = cudaMemcpyAsync(overflow_host_or_null, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(overflow_host_or_null + 1, w.n_fix + 2, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(overflow_host_or_null + 2, w.alloc, sizeof(int), cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: overflow readback");
     }
     return B200BT_OK;

@@ -168,10 +168,13 @@ def _copy_stream(device: torch.device, which: int = 0) -> "torch.cuda.Stream":
 
 
 def rsi_bank(close: torch.Tensor, periods: Sequence[int], fill: bool = True,
-             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+             out: Optional[torch.Tensor] = None, zones: Optional[torch.Tensor] = None, zones_symbols: int = 0,
+             first_symbol: int = 0) -> torch.Tensor:
     """RSI for every window in `periods`: close [S][N] fp32 -> [S][P][N] fp32.
 
     ta.momentum.RSIIndicator semantics as used at binance_ml_strategy.py:112.
+    `zones`: a sweep zone map (zone_map_floats(P, zones_symbols, N) floats) whose rows of the symbols
+    [first_symbol, first_symbol + S) are written in the same pass (b200bt_rsi_bank_zones; needs fill=True).
     """
     assert close.is_cuda and close.dtype == torch.float32 and close.dim() == 2
     S, N = close.shape
@@ -180,8 +183,13 @@ def rsi_bank(close: torch.Tensor, periods: Sequence[int], fill: bool = True,
         out = torch.empty((S, P, N), dtype=torch.float32, device=close.device)
     arr = (C.c_int * P)(*[int(p) for p in periods])
     with torch.cuda.device(close.device):
-        _lib.call("b200bt_rsi_bank", close.data_ptr(), S, N, _lib.ld(close), arr, P, 1 if fill else 0,
-                  out.data_ptr(), _lib.current_stream())
+        if zones is not None:
+            assert fill, "zone rows describe the NaN-filled bank"
+            _lib.call("b200bt_rsi_bank_zones", close.data_ptr(), S, N, _lib.ld(close), arr, P, out.data_ptr(), zones.data_ptr(),
+                      int(zones_symbols), int(first_symbol), _lib.current_stream())
+        else:
+            _lib.call("b200bt_rsi_bank", close.data_ptr(), S, N, _lib.ld(close), arr, P, 1 if fill else 0,
+                      out.data_ptr(), _lib.current_stream())
     return out
 
 
@@ -301,12 +309,12 @@ _FLAG_SLOTS = 256
 
 
 def _pinned_flags() -> torch.Tensor:
-    """Pinned int32 [256][2]: per plan (slice) of a sweep, [0] = the event pool overflowed, [1] = lanes that went through
-    the exact fallback.  The kernels' flags are copied here asynchronously; the host looks at them only after a stream
+    """Pinned int32 [256][4]: per plan (slice) of a sweep, [0] = the event pool overflowed, [1] = lanes that went through
+    the exact fallback, [2] = pool blocks handed out.  The kernels' flags are copied here asynchronously; the host looks at them only after a stream
     synchronisation it does anyway (page-locking memory is slow: one table shared by every plan)."""
     global _PINNED_FLAGS
     if _PINNED_FLAGS is None:
-        _PINNED_FLAGS = torch.zeros((_FLAG_SLOTS, 2), dtype=torch.int32).pin_memory()
+        _PINNED_FLAGS = torch.zeros((_FLAG_SLOTS, 4), dtype=torch.int32).pin_memory()
     return _PINNED_FLAGS
 
 
@@ -347,7 +355,8 @@ class ChunkPlan:
                 row += 1
         self.warm = int(warm)
         self.max_repair_rounds = int(max_repair_rounds)
-        self.pool_blocks = int(pool_scale * pred.sum() * n_symbols / 256) + 2 * self.n_seg * n_symbols + 1024
+        self.pred_blocks = float(pred.sum()) * n_symbols / 256
+        self.pool_blocks = int(pool_scale * self.pred_blocks) + 2 * self.n_seg * n_symbols + 1024
         if pool_blocks is not None:
             self.pool_blocks = int(pool_blocks)
         self.items = torch.from_numpy(items).to(device)
@@ -399,7 +408,8 @@ class TilePlan:
         self.max_repair_rounds = int(max_repair_rounds) if max_repair_rounds is not None else min(self.K, 24)
         self.n_seg = pop * self.K
         # every segment owns at least one block, and a repaired segment abandons its first chain
-        self.pool_blocks = int(pool_scale * pred.sum() * n_symbols / 256) + 2 * self.n_seg * n_symbols + 1024
+        self.pred_blocks = float(pred.sum()) * n_symbols / 256
+        self.pool_blocks = int(pool_scale * self.pred_blocks) + 2 * self.n_seg * n_symbols + 1024
         if pool_blocks is not None:
             self.pool_blocks = int(pool_blocks)
         self.order = np.ascontiguousarray(self.slots[self.slots >= 0])      # individuals in dispatch order
@@ -518,16 +528,21 @@ class PopulationSweep:
         pinned host tensor), each quarter's rows are computed on that quarter's copy stream, so the bank is ready one
         quarter of its kernel time after the last byte instead of one whole kernel."""
         parts = market._close_parts
-        if not parts:
-            return rsi_bank(market.close, self.periods)
         P = len(self.periods)
+        # the zone map of the bank (ranges of every 32-bar block and 4-bar group) comes out of the same pass
+        zones = torch.empty(int(_lib.load().b200bt_zone_map_floats(P, market.S, market.N)), dtype=torch.float32, device=market.device)
+        if not parts:
+            bank = rsi_bank(market.close, self.periods, zones=zones, zones_symbols=market.S)
+            self._zones = zones
+            return bank
         bank = torch.empty((market.S, P, market.N), dtype=torch.float32, device=market.device)
         cur = torch.cuda.current_stream(market.device)
         for lo, hi, st in parts:
-            st.wait_stream(cur)                        # (the bank's allocation)
+            st.wait_stream(cur)                        # (the allocations of the bank and of the zone map)
             with torch.cuda.stream(st):
-                rsi_bank(market._ohlcv[3, lo:hi], self.periods, out=bank[lo:hi])
+                rsi_bank(market._ohlcv[3, lo:hi], self.periods, out=bank[lo:hi], zones=zones, zones_symbols=market.S, first_symbol=lo)
         market._join_close()                           # the current stream now waits for copies AND bank rows
+        self._zones = zones
         return bank
 
     def _multi_timeframe_bank(self, market: MarketData) -> torch.Tensor:
@@ -704,9 +719,20 @@ class PopulationSweep:
         options = dict(self.chunk_options)
         if not tiled and self.mode == "auto":
             options.setdefault("target_events", 8192)
-        if getattr(self, "_last_plans", None) and self.last_pool_overflow:      # the previous sweep ran out of event pool: plan larger
-            options["pool_scale"] = 4.0 * options.get("pool_scale", 1.5)
-            options.pop("pool_blocks", None)
+        # Event-pool sizing learns from the previous sweep of this bank: the cost model behind `pred` is calibrated on random
+        # populations, while the populations a GA evolves write several times more records.  The pool is scaled by the
+        # measured blocks-per-predicted-block ratio (never below the model), and by 4x more whenever it still overflowed.
+        if getattr(self, "_last_plans", None):
+            flags = self._sync_flags()
+            used = sum(int(f[2]) - 2 * pl.n_seg * self.market.S for f, pl in zip(flags, self._last_plans))
+            predicted = sum(pl.pred_blocks for pl in self._last_plans)
+            if any(bool(f[0]) for f in flags):
+                self._pool_factor = 4.0 * max(getattr(self, "_pool_factor", 1.0), 1.0)
+                options.pop("pool_blocks", None)
+            elif predicted > 0:
+                self._pool_factor = max(1.0, 1.2 * used / predicted)
+        if getattr(self, "_pool_factor", 1.0) > 1.0:
+            options["pool_scale"] = getattr(self, "_pool_factor") * options.get("pool_scale", 1.5)
         if tiled and rows is None and len(self.timeframes) > 1:
             rows = decode_population(population, self.period_row, len(self.timeframes))["rsi_row"]
         return self.plan_batches(population, tiled=tiled, pred=pred, rows=rows, **options)

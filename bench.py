@@ -292,6 +292,7 @@ def run_extras(args, world, rank, dev, sweep, population, pop_local, timed_sweep
                                 trade-record count, the sweep's cost driver, up)
       ga_generation_s           configs[4]: population 10 000 x 50 symbols x 1M bars, individuals STRONG-sharded over the
                                 N ranks, one all-gather per generation, GA operators included
+      evolution_c4_s            configs[3]: 100 generations, population 4096, 20 symbols x 1M bars, RSI on 1m / 5m / 15m
       mc_c3_ms                  configs[2]: 1M GBM paths x 10 000 steps sharded over the N ranks incl. gather + statistics"""
     import numpy as np
     import torch
@@ -359,6 +360,19 @@ def run_extras(args, world, rank, dev, sweep, population, pop_local, timed_sweep
         "what": "wall seconds of one generation = fitness of every individual (sharded sweep, one all-gather of 8 B per individual) + GA operators (DeviceGeneticAlgorithm), barrier on both sides, max over ranks",
         "scaling": "strong"}
     del ga5, fit5, sweep5, market5
+    torch.cuda.empty_cache()
+
+    # ---- configs[3]: the evolution loop, 100 generations, population 4096, 20 symbols, RSI on 1m / 5m / 15m -------------
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("evolution_c4", str(ROOT / "tools" / "evolution_c4.py"))
+    c4mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(c4mod)
+    c4 = c4mod.run(generations=100, population=4096, symbols=20, bars=args.bars, device=dev)
+    out["evolution_c4_s"] = {k: c4[k] for k in ("loop_s", "per_generation_s", "setup_s", "bank_rows", "operators", "best_fitness",
+                                                "distinct_individuals_rank0", "evaluations_computed_rank0", "evaluations_nominal", "workload")}
+    out["evolution_c4_s"]["scaling"] = "strong"
+    out["evolution_c4_s"]["what"] = ("wall seconds of the whole loop (initial population + 100 generations: GA operators on the device, fitness = "
+                                     "sharded sweep over the 78-row multi-timeframe bank, one all-gather per generation); max over ranks")
     torch.cuda.empty_cache()
 
     # ---- configs[2]: Monte-Carlo risk, 1M GBM paths x 10 000 steps, VaR + max drawdown ------------------

@@ -60,6 +60,13 @@ int b200bt_rsi_bank(const float* close, int S, int64_t N, int64_t ld,
                     const int* periods_host, int P, int fill,
                     float* out, b200bt_stream_t stream);
 
+/* b200bt_rsi_bank (NaN policy applied) that also writes the bank's rows of a sweep zone map (see b200bt_zone_map: row 0 =
+ * the close prices, rows 1..P = the RSI rows) while the values are in registers, so that the first sweep of a fresh bank can
+ * already skip quiet blocks.  `zones` is the WHOLE zone map of S_total symbols (b200bt_zone_map_floats(P, S_total, N) floats);
+ * this call fills the rows of symbols [sym0, sym0 + S), whose closes / bank rows `close` / `out` point at. */
+int b200bt_rsi_bank_zones(const float* close, int S, int64_t N, int64_t ld, const int* periods_host, int P,
+                          float* out, float* zones, int S_total, int sym0, b200bt_stream_t stream);
+
 /* EMA bank: ta.trend.EMAIndicator(close, window=w) = ewm(span=w, min_periods=w, adjust=False)
  * (binance_ml_strategy.py:79-83).  out [S][P][N]; undefined leading values are NaN. */
 int b200bt_ema_bank(const float* x, int S, int64_t N, int64_t ld, const int* spans_host, int P,
@@ -253,9 +260,10 @@ int b200bt_sweep(const float* price, int64_t ld_price,
  *  items      [n_items] device      seg_base, n_chunks  [pop] device int32      n_seg = sum of n_chunks
  *  pool_blocks  event pool size in blocks of 256 events; a chunk that cannot get a block flags its lane
  *  workspace  b200bt_sweep_chunked_workspace_bytes(pool_blocks, S, n_seg) device bytes
- *  overflow_host_or_null  optional PINNED host int[2], written asynchronously on `stream` (read after synchronising it):
+ *  overflow_host_or_null  optional PINNED host int[3], written asynchronously on `stream` (read after synchronising it):
  *                         [0] = 1 if the event pool ran out (grow it next time), [1] = number of (individual, symbol)
- *                         lanes that were flagged and re-evaluated by the exact fallback.
+ *                         lanes that were flagged and re-evaluated by the exact fallback, [2] = pool blocks handed out
+ *                         (what the next sweep of a similar population needs).
  * Flagged lanes are re-evaluated by the fused kernel (b200bt_sweep's) inside this call, from a device-side list: the call
  * reads nothing back and never synchronises; lane_invalid reports which lanes took that path. */
 typedef struct b200bt_chunk_item {

@@ -415,3 +415,29 @@ def test_multi_timeframe_bank_and_sweep(torch_cuda):
         if mode == "tiled":
             assert sweep.last_invalid_lanes == 0             # packed by bank row: no warp reads more than two rows
     assert len({int(r) for r in want["n_records"][:, 0]}) > 20
+
+
+@pytest.mark.parametrize("n_bars", [5, 127, 4096, 8192, 70_001, 262_144 + 33])
+def test_zone_rows_written_with_the_bank_equal_the_zone_map_kernel(torch_cuda, n_bars):
+    """b200bt_rsi_bank_zones writes the (min, max) ranges of the bank while it computes it (rows of a sub-range of the
+    symbols, as the upload pipeline does per quarter): bit-equal to b200bt_zone_map run on the finished bank, padding
+    included."""
+    torch = torch_cuda
+    import ctypes as C
+    from ai_crypto_trader_b200 import _lib, synth
+    from ai_crypto_trader_b200.sweep import rsi_bank
+    S, periods = 3, [2, 5, 14, 30]
+    P = len(periods)
+    close = torch.from_numpy(synth.synth_ohlcv(S, n_bars, first_symbol=3)[3]).cuda()
+    nz = int(_lib.load().b200bt_zone_map_floats(P, S, n_bars))
+    fused = torch.full((nz,), 7.0, dtype=torch.float32, device="cuda")
+    bank = torch.empty((S, P, n_bars), dtype=torch.float32, device="cuda")
+    rsi_bank(close[:1], periods, out=bank[:1], zones=fused, zones_symbols=S, first_symbol=0)
+    rsi_bank(close[1:], periods, out=bank[1:], zones=fused, zones_symbols=S, first_symbol=1)
+    assert torch.equal(bank, rsi_bank(close, periods))
+    want = torch.empty(nz, dtype=torch.float32, device="cuda")
+    _lib.call("b200bt_zone_map", close.data_ptr(), _lib.ld(close), bank.data_ptr(), _lib.ld(bank), P, S, n_bars, want.data_ptr(),
+              _lib.current_stream())
+    a, b = fused.cpu().numpy(), want.cpu().numpy()
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.array_equal(a[~np.isnan(b)], b[~np.isnan(b)])
