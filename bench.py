@@ -37,8 +37,9 @@ BYTES_PER_EVAL = 8  # price 4 B + RSI 4 B per (individual, symbol, 
 # the committed `ncu --set full` capture named in "source"; "scan_share" = the kernel's share of the sweep's kernel time in
 # the committed launch list of this bench command.  Valid for exactly that workload (the kernels are deterministic).
 NCU_C2 = {
-    "tiled": {"warp_inst": 3.796e9, "threads_per_inst": 11.87, "dram_bytes": 5.222e9 + 1.006e9, "scan_share": 0.69,
-              "source": "profiles/r1_tiled_final_ncu.txt, profiles/r1_launches_v4.csv"},
+    "tiled": {"warp_inst": 3.7396e9, "threads_per_inst": 14.01, "dram_bytes": 3.998e9 + 1.031e9, "scan_share": 0.605,
+              "issue_active_pct": 67.1, "alu_pipe_pct": 51.9,
+              "source": "profiles/r2_lane_scan_ncu.txt (ncu --set full), profiles/r2_launches.csv (launch list of `bench.py --steps 2 --warmup 3 --skip-extras`)"},
 }
 
 
@@ -568,6 +569,7 @@ def main():
                 "achieved": achieved, "frac": achieved / issue_peak,
                 "warp_inst_per_launch": ncu["warp_inst"], "warp_inst_per_eval": ncu["warp_inst"] / lanes_evals,
                 "threads_per_inst": ncu["threads_per_inst"], "dominant_kernel_share_of_step": ncu["scan_share"],
+                "issue_active_pct_ncu": ncu["issue_active_pct"], "alu_pipe_pct_ncu": ncu["alu_pipe_pct"],
                 "traffic": ncu["dram_bytes"], "traffic_unit": "DRAM bytes per launch of the dominant kernel (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                 "dram_frac": ncu["dram_bytes"] / (scan_ms * 1e-3) / 1e9 / peak, "compulsory_bytes": (S * N * 4 + sweep.bank.numel() * 4),
                 "source": ncu["source"],
