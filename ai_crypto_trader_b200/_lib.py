@@ -62,6 +62,10 @@ LANE_STATS_FIELDS = (
 )
 LANE_STATS_WORDS = len(LANE_STATS_FIELDS)
 
+ANALYZER_COLUMNS = ("sma_20", "sma_50", "sma_200", "ema_12", "ema_26", "macd", "macd_signal", "macd_diff", "ichimoku_a",
+                    "ichimoku_b", "rsi", "bb_high", "bb_mid", "bb_low", "bb_width", "atr", "vwap", "stoch_k", "stoch_d",
+                    "williams_r", "bb_position")      # enum b200bt_analyzer_column
+
 EVENT_EXIT = 0x40000000
 EVENT_SELL = 0x80000000
 EVENT_BAR_MASK = 0x3FFFFFFF
@@ -108,6 +112,8 @@ _SIGNATURES = {
     "b200bt_ichimoku": (C.c_int, [_vp, _vp, _i, _i64, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "b200bt_atr_bank": (C.c_int, [_vp, _vp, _vp, _i, _i64, _i64, C.POINTER(C.c_int), _i, _vp, _vp]),
     "b200bt_vwap": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _vp]),
+    "b200bt_analyzer_workspace_floats": (C.c_int64, [_i, _i64]),
+    "b200bt_analyzer": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i64, _i64, _vp, _vp, _vp]),
     "b200bt_resample_bars": (C.c_int64, [_i64, _i64, _i, _i]),
     "b200bt_resample": (C.c_int, [_vp, _i, _i64, _i64, _i, _i, _vp, _i64, _vp]),
     "b200bt_align": (C.c_int, [_vp, _i, _i64, _i64, _i64, _i, _i, _vp, _vp]),

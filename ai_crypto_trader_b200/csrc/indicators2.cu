@@ -140,12 +140,12 @@ ema_bank_kernel(const float* __restrict__ x, int64_t N, int64_t ld, const __grid
 // both are), signal = ewm(span=sign, min_periods=sign, adjust=False) of the line seeded with its
 // first defined value, diff = line - signal.  One warp per CTA does the three scans in sequence.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
-macd_kernel(const float* __restrict__ x, int64_t N, int64_t ld, int fast, int slow, int sign, int halo_ema, int halo_sig,
-            float* __restrict__ o_line, float* __restrict__ o_sig, float* __restrict__ o_diff) {
-    extern __shared__ double s_line[];  // line over [s0, tile_end)
-    const int sym = blockIdx.y, lane = threadIdx.x;
-    const int64_t tile_start = (int64_t)blockIdx.x * IND_TILE;
+// (one warp; o_ef / o_es: optional outputs of the two EMAs themselves, ta.trend.EMAIndicator semantics, :79-83)
+__device__ __forceinline__ void macd_tile(const float* __restrict__ x, int64_t N, int64_t ld, int fast, int slow, int sign,
+                                          int halo_ema, int halo_sig, float* __restrict__ o_line, float* __restrict__ o_sig,
+                                          float* __restrict__ o_diff, float* __restrict__ o_ef, float* __restrict__ o_es,
+                                          double* __restrict__ s_line, int sym, int64_t tile_start) {
+    const int lane = threadIdx.x & 31;
     const int64_t tile_end = min(tile_start + (int64_t)IND_TILE, N);
     const int64_t s1 = max((int64_t)0, tile_start - halo_sig) & ~(int64_t)3;   // first bar whose line is needed
     const int64_t s0 = max((int64_t)0, s1 - halo_ema) & ~(int64_t)3;           // first bar the EMAs start from
@@ -173,8 +173,13 @@ macd_kernel(const float* __restrict__ x, int64_t N, int64_t ld, int fast, int sl
         sf.run(bf, cf, yf, lane);
         ss.run(bs, cs, ys, lane);
 #pragma unroll
-        for (int j = 0; j < K; ++j)
+        for (int j = 0; j < K; ++j) {
             if (t + j >= s1 && t + j < tile_end) s_line[t + j - s1] = yf[j] - ys[j];
+            if (o_ef && t + j >= tile_start && t + j < tile_end) {
+                o_ef[(int64_t)sym * N + t + j] = (t + j >= fast - 1) ? (float)yf[j] : nanf32();
+                o_es[(int64_t)sym * N + t + j] = (t + j >= slow - 1) ? (float)ys[j] : nanf32();
+            }
+        }
     }
     __syncwarp();
     // signal: starts at max(s1, first_line); seeded with the line itself at first_line
@@ -214,6 +219,14 @@ macd_kernel(const float* __restrict__ x, int64_t N, int64_t ld, int fast, int sl
         o_sig[o] = nanf32();
         o_diff[o] = nanf32();
     }
+}
+
+__global__ void __launch_bounds__(32)
+macd_kernel(const float* __restrict__ x, int64_t N, int64_t ld, int fast, int slow, int sign, int halo_ema, int halo_sig,
+            float* __restrict__ o_line, float* __restrict__ o_sig, float* __restrict__ o_diff) {
+    extern __shared__ double s_line[];  // line over [s1, tile_end)
+    macd_tile(x, N, ld, fast, slow, sign, halo_ema, halo_sig, o_line, o_sig, o_diff, nullptr, nullptr, s_line, blockIdx.y,
+              (int64_t)blockIdx.x * IND_TILE);
 }
 
 // ---------------------------------------------------------------------------------
@@ -350,12 +363,11 @@ __device__ __forceinline__ float window_min(const float* __restrict__ s, int i, 
 // mode 0: stochastic (%K into o_a, %D = rolling mean(smooth) of %K into o_b)   :121-127
 // mode 1: Williams %R into o_a                                                 :135-140
 // mode 2: Ichimoku a, b (w1 conversion, w2 base, w3 span b)                    :102-104
-__global__ void __launch_bounds__(IND_THREADS)
-extrema_kernel(const float* __restrict__ high, const float* __restrict__ low, const float* __restrict__ close,
-               int64_t N, int64_t ld, int mode, int w1, int w2, int w3, float* __restrict__ o_a, float* __restrict__ o_b) {
-    extern __shared__ float s_hl[];  // [halo + tile] highs, then lows, then %K scratch
-    const int sym = blockIdx.y;
-    const int64_t tile_start = (int64_t)blockIdx.x * IND_TILE;
+// (whole CTA; s_hl: 3 (IND_TILE + 2 IND_MAX_WINDOW) floats of shared memory -- highs, lows, %K scratch; ends with every
+// thread past its last shared-memory access only after the caller's next barrier)
+__device__ __forceinline__ void extrema_tile(const float* __restrict__ high, const float* __restrict__ low, const float* __restrict__ close,
+                                             int64_t N, int64_t ld, int mode, int w1, int w2, int w3, float* __restrict__ o_a,
+                                             float* __restrict__ o_b, float* __restrict__ s_hl, int sym, int64_t tile_start) {
     const int64_t tile_end = min(tile_start + (int64_t)IND_TILE, N);
     const int wmax = max(w1, max(w2, w3));
     const int extra = (mode == 0) ? (w2 - 1) : 0;  // %D needs %K of the previous smooth-1 bars
@@ -423,18 +435,22 @@ extrema_kernel(const float* __restrict__ high, const float* __restrict__ low, co
     }
 }
 
+__global__ void __launch_bounds__(IND_THREADS)
+extrema_kernel(const float* __restrict__ high, const float* __restrict__ low, const float* __restrict__ close,
+               int64_t N, int64_t ld, int mode, int w1, int w2, int w3, float* __restrict__ o_a, float* __restrict__ o_b) {
+    extern __shared__ float s_hl[];  // [halo + tile] highs, then lows, then %K scratch
+    extrema_tile(high, low, close, N, ld, mode, w1, w2, w3, o_a, o_b, s_hl, blockIdx.y, (int64_t)blockIdx.x * IND_TILE);
+}
+
 // ---------------------------------------------------------------------------------
 // ATR bank (ta.volatility.AverageTrueRange; :164): TR_t = max(h-l, |h-c_{t-1}|, |l-c_{t-1}|),
 // TR_0 = h_0-l_0; atr[t<w-1] = 0, atr[w-1] = mean(TR[0:w]), atr[i] = (atr[i-1](w-1)+TR[i])/w.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(IND_THREADS)
-atr_bank_kernel(const float* __restrict__ high, const float* __restrict__ low, const float* __restrict__ close,
-                int64_t N, int64_t ld, const __grid_constant__ BankParams prm, int P, int halo_max,
-                float* __restrict__ out) {
-    extern __shared__ float s_tr[];  // true range over [s0, tile_end) as fp32-exact differences kept in double? -> store double
-    double* tr = reinterpret_cast<double*>(s_tr);
-    const int sym = blockIdx.y;
-    const int64_t tile_start = (int64_t)blockIdx.x * IND_TILE;
+// (whole CTA; `tr`: (halo_max + IND_TILE + IND_MAX_WINDOW + 8) doubles of shared memory; window i of `prm` goes to warp i % nwarp
+// and is written to out + ((sym * P + i) * N))
+__device__ __forceinline__ void atr_tile(const float* __restrict__ high, const float* __restrict__ low, const float* __restrict__ close,
+                                         int64_t N, int64_t ld, const BankParams& prm, int P, int halo_max,
+                                         float* __restrict__ out, double* __restrict__ tr, int sym, int64_t tile_start) {
     const int64_t tile_end = min(tile_start + (int64_t)IND_TILE, N);
     int64_t s0 = max((int64_t)0, tile_start - halo_max) & ~(int64_t)3;
     if (s0 < IND_MAX_WINDOW) s0 = 0;  // a pass that crosses a seed bar t = w-1 needs TR from bar 0
@@ -491,17 +507,22 @@ atr_bank_kernel(const float* __restrict__ high, const float* __restrict__ low, c
     }
 }
 
+__global__ void __launch_bounds__(IND_THREADS)
+atr_bank_kernel(const float* __restrict__ high, const float* __restrict__ low, const float* __restrict__ close,
+                int64_t N, int64_t ld, const __grid_constant__ BankParams prm, int P, int halo_max,
+                float* __restrict__ out) {
+    extern __shared__ float s_tr[];  // true range over [s0, tile_end), float64
+    atr_tile(high, low, close, N, ld, prm, P, halo_max, out, reinterpret_cast<double*>(s_tr), blockIdx.y, (int64_t)blockIdx.x * IND_TILE);
+}
+
 // ---------------------------------------------------------------------------------
 // VWAP (ta.volume.VolumeWeightedAveragePrice, window 14; :173-179):
 // sum_w(tp*v)/sum_w(v), tp = (h+l+c)/3.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(IND_THREADS)
-vwap_kernel(const float* __restrict__ high, const float* __restrict__ low, const float* __restrict__ close,
-            const float* __restrict__ volume, int64_t N, int64_t ld, int w, float* __restrict__ out) {
-    extern __shared__ double s_buf[];
-    __shared__ double s_warp[32];
-    const int sym = blockIdx.y;
-    const int64_t tile_start = (int64_t)blockIdx.x * IND_TILE;
+// (whole CTA; s_buf: 2 (IND_TILE + IND_MAX_WINDOW + 1) doubles, s_warp: 32 doubles of shared memory)
+__device__ __forceinline__ void vwap_tile(const float* __restrict__ high, const float* __restrict__ low, const float* __restrict__ close,
+                                          const float* __restrict__ volume, int64_t N, int64_t ld, int w, float* __restrict__ out,
+                                          double* __restrict__ s_buf, double* __restrict__ s_warp, int sym, int64_t tile_start) {
     const int64_t tile_end = min(tile_start + (int64_t)IND_TILE, N);
     const int64_t s0 = max((int64_t)0, tile_start - (w - 1));
     const int n = (int)(tile_end - s0);
@@ -527,6 +548,14 @@ vwap_kernel(const float* __restrict__ high, const float* __restrict__ low, const
         }
         out[(int64_t)sym * N + t] = v;
     }
+}
+
+__global__ void __launch_bounds__(IND_THREADS)
+vwap_kernel(const float* __restrict__ high, const float* __restrict__ low, const float* __restrict__ close,
+            const float* __restrict__ volume, int64_t N, int64_t ld, int w, float* __restrict__ out) {
+    extern __shared__ double s_buf[];
+    __shared__ double s_warp[32];
+    vwap_tile(high, low, close, volume, N, ld, w, out, s_buf, s_warp, blockIdx.y, (int64_t)blockIdx.x * IND_TILE);
 }
 
 // ---------------------------------------------------------------------------------
@@ -615,6 +644,270 @@ nanfill_apply_kernel(float* __restrict__ x, int64_t N, int tiles, const float* _
             r[lo + i] = v;
         }
     }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// TechnicalAnalyzer._calculate_all_indicators (binance_ml_strategy.py:40-182) in three launches.  Each launch stages its
+// inputs once per (symbol, tile) and writes every column that depends on them, with the reference's own windows:
+//   A  close                     -> ema_12, ema_26, macd, macd_signal, macd_diff (one warp), rsi_14 (second warp)
+//   B  close                     -> sma_20, sma_50, sma_200, bb_high, bb_mid, bb_low, bb_width, bb_position
+//   C  high, low, close, volume  -> stoch_k, stoch_d, williams_r, ichimoku_a, ichimoku_b, atr_14, vwap_14
+// Columns are [S][N] blocks of one [21][S][N] allocation in the order of b200bt_analyzer_column (include/b200bt.h).  The
+// leading undefined bars (t < window - 1) of the columns that cannot be undefined anywhere else are filled by the CTA of
+// tile 0 itself (bfill with the first defined value, 0 for a series shorter than the window: `_handle_nan_values` :28-38);
+// the five columns that can be undefined in mid-series (zero high-low range, zero Bollinger range, zero volume) sit at the
+// end of the allocation and go through the general ffill / bfill kernels in ONE batched call.
+// ---------------------------------------------------------------------------------
+struct LeadFill { float* col[8]; int first[8]; int n; };
+
+// CTA of tile 0, after a barrier: col[t] = col[first] for t < first (0 when the series ends before `first`)
+__device__ __forceinline__ void lead_fill(const LeadFill& lf, int sym, int64_t N) {
+    for (int c = 0; c < lf.n; ++c) {
+        float* o = lf.col[c] + (int64_t)sym * N;
+        const int f = lf.first[c];
+        const float v = f < N ? o[f] : 0.0f;
+        for (int64_t t = threadIdx.x; t < min((int64_t)f, N); t += blockDim.x) o[t] = v;
+    }
+}
+
+__global__ void __launch_bounds__(64)
+analyzer_a_kernel(const float* __restrict__ x, int64_t N, int64_t ld, int fast, int slow, int sign, int halo_ema, int halo_sig,
+                  int w_rsi, int halo_rsi, float* __restrict__ o_ef, float* __restrict__ o_es, float* __restrict__ o_line,
+                  float* __restrict__ o_sig, float* __restrict__ o_diff, float* __restrict__ o_rsi, const LeadFill lf) {
+    extern __shared__ double s_line[];
+    const int sym = blockIdx.y, lane = threadIdx.x & 31;
+    const int64_t tile_start = (int64_t)blockIdx.x * IND_TILE, tile_end = min(tile_start + (int64_t)IND_TILE, N);
+    if (threadIdx.x < 32) {
+        macd_tile(x, N, ld, fast, slow, sign, halo_ema, halo_sig, o_line, o_sig, o_diff, o_ef, o_es, s_line, sym, tile_start);
+    } else {
+        // RSI (ta.momentum.RSIIndicator, :112): Wilder averages of the up / down moves, y0 = x0 (both 0 at bar 0)
+        const float* row = x + (int64_t)sym * ld;
+        constexpr int K = 4;
+        const double alpha = 1.0 / (double)w_rsi;
+        AffineScan<K> sc;
+        sc.init(1.0 - alpha, lane);
+        const int64_t start = max((int64_t)0, tile_start - halo_rsi) & ~(int64_t)3;
+        double cu = 0.0, cd = 0.0;
+        for (int64_t base = start; base < tile_end; base += 32 * K) {
+            const int64_t t = base + lane * K;
+            double xs[K + 1], bu[K], bd[K], yu[K], yd[K];
+#pragma unroll
+            for (int j = 0; j <= K; ++j) {
+                int64_t tt = t - 1 + j;
+                tt = tt < 0 ? 0 : (tt >= N ? N - 1 : tt);
+                xs[j] = (double)__ldg(row + tt);
+            }
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const double df = xs[j + 1] - xs[j];
+                bu[j] = alpha * (df > 0.0 ? df : 0.0);
+                bd[j] = alpha * (df < 0.0 ? -df : 0.0);
+            }
+            sc.run(bu, cu, yu, lane);
+            sc.run(bd, cd, yd, lane);
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                if (t + j >= tile_start && t + j < tile_end) {
+                    const double v = (yd[j] == 0.0) ? 100.0 : 100.0 - 100.0 / (1.0 + yu[j] / yd[j]);
+                    o_rsi[(int64_t)sym * N + t + j] = (t + j >= w_rsi - 1) ? (float)v : nanf32();
+                }
+        }
+    }
+    if (tile_start == 0) {
+        __syncthreads();
+        lead_fill(lf, sym, N);
+    }
+}
+
+__global__ void __launch_bounds__(IND_THREADS)
+analyzer_b_kernel(const float* __restrict__ x, int64_t N, int64_t ld, int w0, int w1, int w2, int w_bb, double kdev,
+                  float* __restrict__ o_s0, float* __restrict__ o_s1, float* __restrict__ o_s2, float* __restrict__ o_high,
+                  float* __restrict__ o_mid, float* __restrict__ o_low, float* __restrict__ o_width, float* __restrict__ o_pos,
+                  int halo, const LeadFill lf) {
+    extern __shared__ double s_buf[];   // prefix of d = x - c, then prefix of d^2 (IND_TILE + IND_MAX_WINDOW + 1 each)
+    __shared__ double s_warp[32];
+    const int sym = blockIdx.y;
+    const int64_t tile_start = (int64_t)blockIdx.x * IND_TILE, tile_end = min(tile_start + (int64_t)IND_TILE, N);
+    const int64_t s0 = max((int64_t)0, tile_start - halo);
+    const int n = (int)(tile_end - s0);
+    double* p1 = s_buf;
+    double* p2 = s_buf + (IND_TILE + IND_MAX_WINDOW + 1);
+    const float* row = x + (int64_t)sym * ld;
+    const double c = (double)__ldg(row + tile_start);   // tile offset keeps the prefixes small (sum of squares without cancellation)
+    if (threadIdx.x == 0) { p1[0] = 0.0; p2[0] = 0.0; }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double d = (double)__ldg(row + s0 + i) - c;
+        p1[i + 1] = d;
+        p2[i + 1] = d * d;
+    }
+    __syncthreads();
+    block_prefix_sum(p1 + 1, n, s_warp);
+    block_prefix_sum(p2 + 1, n, s_warp);
+    const int ws[3] = {w0, w1, w2};
+    float* const os[3] = {o_s0, o_s1, o_s2};
+    for (int64_t t = tile_start + threadIdx.x; t < tile_end; t += blockDim.x) {
+        const int i = (int)(t - s0);
+        const int64_t o = (int64_t)sym * N + t;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)      // ta.trend.SMAIndicator (:67-76)
+            os[k][o] = (t >= ws[k] - 1) ? (float)((p1[i + 1] - p1[i + 1 - ws[k]]) / (double)ws[k] + c) : nanf32();
+        if (t < w_bb - 1) {              // ta.volatility.BollingerBands (:148-156)
+            o_high[o] = o_mid[o] = o_low[o] = o_width[o] = o_pos[o] = nanf32();
+            continue;
+        }
+        const double m1 = (p1[i + 1] - p1[i + 1 - w_bb]) / (double)w_bb;
+        const double m2 = (p2[i + 1] - p2[i + 1 - w_bb]) / (double)w_bb;
+        double var = m2 - m1 * m1;
+        if (var < 0.0) var = 0.0;
+        const double sd = sqrt(var), mid = m1 + c;
+        const double hi = mid + kdev * sd, lo = mid - kdev * sd;
+        const double rng = hi - lo;
+        const double close = (double)__ldg(row + t);
+        o_high[o] = (float)hi;
+        o_mid[o] = (float)mid;
+        o_low[o] = (float)lo;
+        o_width[o] = (float)(rng / mid);
+        o_pos[o] = rng == 0.0 ? nanf32() : (float)((close - lo) / rng);
+    }
+    if (tile_start == 0) {
+        __syncthreads();
+        lead_fill(lf, sym, N);
+    }
+}
+
+// C: one backward walk of the staged highs / lows per bar serves every window (the reference's are nested: 9 <= 14 <= 26 <= 52),
+// %D averages the float64 %K values kept in shared memory, the ATR recurrence runs on all eight warps (a 256-bar sub-tile
+// each, its own warm-up halo) instead of one, VWAP on block-wide prefix sums.  Phases reuse the shared memory.
+__global__ void __launch_bounds__(IND_THREADS)
+analyzer_c_kernel(const float* __restrict__ high, const float* __restrict__ low, const float* __restrict__ close,
+                  const float* __restrict__ volume, int64_t N, int64_t ld, int w_st, int smooth, int i1, int i2, int i3,
+                  int w_atr, int atr_halo, int w_vwap, float* __restrict__ o_k, float* __restrict__ o_d,
+                  float* __restrict__ o_wr, float* __restrict__ o_ia, float* __restrict__ o_ib, float* __restrict__ o_atr,
+                  float* __restrict__ o_vwap, const LeadFill lf) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ double s_warp[32];
+    const int sym = blockIdx.y;
+    const int64_t tile_start = (int64_t)blockIdx.x * IND_TILE, tile_end = min(tile_start + (int64_t)IND_TILE, N);
+    const int64_t ro = (int64_t)sym * ld;
+    // ---- phase 1: window extrema -> stochastic %K / %D, Williams %R, Ichimoku a / b ----
+    {
+        const int halo = max(i3 - 1, w_st - 1 + smooth - 1);
+        const int64_t s0 = max((int64_t)0, tile_start - halo);
+        const int n = (int)(tile_end - s0);
+        constexpr int CAP = IND_TILE + 256;                         // (the host checks halo <= 256)
+        float* sh = reinterpret_cast<float*>(s_raw);
+        float* sl = sh + CAP;
+        float* sc = sl + CAP;
+        double* skd = reinterpret_cast<double*>(sc + CAP);          // float64 %K of the staged bars
+        stage_row(high + ro, N, s0, n, sh);
+        stage_row(low + ro, N, s0, n, sl);
+        stage_row(close + ro, N, s0, n, sc);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int64_t t = s0 + i;
+            // running (max high, min low) over the last k bars, captured at the windows in ascending order
+            float mh = -INFINITY, ml = INFINITY;
+            int k = 0;
+            const int have = i + 1;                                  // staged bars at or before this one
+            auto upto = [&](int w) { const int lim = min(w, have); for (; k < lim; ++k) { mh = fmaxf(mh, sh[i - k]); ml = fminf(ml, sl[i - k]); } };
+            upto(i1);
+            const double h1 = (double)mh, l1 = (double)ml;
+            upto(w_st);
+            const double hs = (double)mh, ls = (double)ml;
+            upto(i2);
+            const double h2 = (double)mh, l2 = (double)ml;
+            upto(i3);
+            const double h3 = (double)mh, l3 = (double)ml;
+            const double c = (double)sc[i];
+            // (s0 == 0: "i >= w - 1" is "t >= w - 1"; s0 > 0: every window lies inside the staged halo)
+            const double kk = (i >= w_st - 1) ? 100.0 * (c - ls) / (hs - ls) : (double)nanf32();       // 0/0 -> NaN as in pandas
+            skd[i] = kk;
+            if (t >= tile_start) {
+                const int64_t o = (int64_t)sym * N + t;
+                o_k[o] = (float)kk;
+                o_wr[o] = (t >= w_st - 1) ? (float)(-100.0 * (hs - c) / (hs - ls)) : nanf32();
+                float a = nanf32(), b = nanf32();
+                if (t >= max(i1, i2) - 1) a = (float)(0.5 * (0.5 * (h1 + l1) + 0.5 * (h2 + l2)));
+                if (t >= i3 - 1) b = (float)(0.5 * (h3 + l3));
+                o_ia[o] = a;
+                o_ib[o] = b;
+            }
+        }
+        __syncthreads();
+        for (int64_t t = tile_start + threadIdx.x; t < tile_end; t += blockDim.x) {
+            const int i = (int)(t - s0);
+            float d = nanf32();
+            if (t >= w_st - 1 + smooth - 1) {
+                double acc = 0.0;
+                for (int q = 0; q < smooth; ++q) acc += skd[i - q];
+                d = (float)(acc / (double)smooth);
+            }
+            o_d[(int64_t)sym * N + t] = d;
+        }
+        __syncthreads();
+    }
+    // ---- phase 2: ATR (ta.volatility.AverageTrueRange; :164), a 256-bar sub-tile per warp ----
+    {
+        double* tr = reinterpret_cast<double*>(s_raw);
+        int64_t s0 = max((int64_t)0, tile_start - atr_halo) & ~(int64_t)3;
+        if (s0 < IND_MAX_WINDOW) s0 = 0;                             // a pass that crosses the seed bar t = w-1 needs TR from bar 0
+        const int n_stage = (int)(tile_start + IND_TILE - s0);
+        for (int i = threadIdx.x; i < n_stage; i += blockDim.x) {
+            const int64_t t = s0 + i;
+            double v = 0.0;
+            if (t < N) {
+                const double h = (double)__ldg(high + ro + t), l = (double)__ldg(low + ro + t);
+                v = h - l;
+                if (t > 0) {
+                    const double pc = (double)__ldg(close + ro + t - 1);
+                    v = fmax(v, fmax(fabs(h - pc), fabs(l - pc)));
+                }
+            }
+            tr[i] = v;
+        }
+        __syncthreads();
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+        constexpr int K = 4;
+        const int w = w_atr;
+        const double alpha = 1.0 / (double)w, om = ((double)w - 1.0) / (double)w;
+        AffineScan<K> scn;
+        scn.init(om, lane);
+        const int sub = IND_TILE / (int)nwarp;
+        const int64_t sub_start = tile_start + (int64_t)warp * sub, sub_end = min(sub_start + sub, tile_end);
+        if (sub_start < sub_end) {
+            int64_t start = max(s0, sub_start - atr_halo) & ~(int64_t)3;
+            const bool has_seed = (start <= w - 1);                  // this pass crosses the seed bar t = w-1
+            double seed = 0.0;
+            if (has_seed && w - 1 < N) {
+                for (int q = 0; q < w; ++q) seed += tr[(int)(q - s0)];   // s0 == 0 whenever has_seed
+                seed /= (double)w;
+            }
+            if (has_seed) start = 0;
+            double carry = 0.0;
+            for (int64_t base = start; base < sub_end; base += 32 * K) {
+                const int64_t t = base + lane * K;
+                double b[K], y[K];
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const int64_t tt = t + j;
+                    double v = alpha * tr[min((int)(tt - s0), n_stage - 1)];
+                    if (has_seed) v = tt < w - 1 ? 0.0 : (tt == w - 1 ? seed : v);   // zeros, then the seed, then the recurrence
+                    b[j] = v;
+                }
+                scn.run(b, carry, y, lane);
+#pragma unroll
+                for (int j = 0; j < K; ++j)
+                    if (t + j >= sub_start && t + j < sub_end) o_atr[(int64_t)sym * N + t + j] = (t + j >= w - 1) ? (float)y[j] : 0.0f;
+            }
+        }
+        __syncthreads();
+    }
+    // ---- phase 3: VWAP ----
+    vwap_tile(high, low, close, volume, N, ld, w_vwap, o_vwap, reinterpret_cast<double*>(s_raw), s_warp, sym, tile_start);
+    if (tile_start == 0) {
+        __syncthreads();
+        lead_fill(lf, sym, N);
     }
 }
 
@@ -802,4 +1095,83 @@ extern "C" int b200bt_vwap(const float* high, const float* low, const float* clo
     vwap_kernel<<<ind_grid(N, S), IND_THREADS, smem, (cudaStream_t)stream>>>(high, low, close, volume, N, ld, window, out);
     B200BT_LAUNCH_CHECK("vwap launch");
     return B200BT_OK;
+}
+
+// TechnicalAnalyzer._calculate_all_indicators for S symbols: three fused launches + one batched NaN-policy call.
+extern "C" int64_t b200bt_analyzer_workspace_floats(int S, int64_t N) {
+    return b200bt_nanfill_workspace_floats((int64_t)5 * S, N);
+}
+
+extern "C" int b200bt_analyzer(const float* high, const float* low, const float* close, const float* volume, int S, int64_t N,
+                               int64_t ld, float* cols, float* workspace, b200bt_stream_t stream) {
+    B200BT_REQUIRE(high && low && close && volume && cols && workspace, B200BT_EINVAL, "analyzer: null pointer");
+    IND_COMMON_CHECKS("analyzer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t plane = (int64_t)S * N;
+    auto col = [&](int c) { return cols + (int64_t)c * plane; };
+    // the reference's windows (binance_ml_strategy.py:67-179)
+    const int fast = 12, slow = 26, sign = 9, w_rsi = 14, w_bb = 20, w_st = 14, smooth = 3, w_wr = 14, w_atr = 14, w_vwap = 14;
+    const int sma_w[3] = {20, 50, 200}, ich[3] = {9, 26, 52};
+    // A: close -> ema_12, ema_26, macd, macd_signal, macd_diff, rsi
+    {
+        const int halo_ema = halo_for(1.0 - 2.0 / ((double)slow + 1.0)), halo_sig = halo_for(1.0 - 2.0 / ((double)sign + 1.0));
+        const int halo_rsi = halo_for(((double)w_rsi - 1.0) / (double)w_rsi);
+        const size_t smem = (size_t)(halo_sig + IND_TILE + 8) * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(analyzer_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e, "analyzer: cudaFuncSetAttribute");
+        LeadFill lf{};
+        const int cs[6] = {B200BT_COL_EMA_12, B200BT_COL_EMA_26, B200BT_COL_MACD, B200BT_COL_MACD_SIGNAL, B200BT_COL_MACD_DIFF, B200BT_COL_RSI};
+        const int fs[6] = {fast - 1, slow - 1, slow - 1, slow - 1 + sign - 1, slow - 1 + sign - 1, w_rsi - 1};
+        lf.n = 6;
+        for (int i = 0; i < 6; ++i) { lf.col[i] = col(cs[i]); lf.first[i] = fs[i]; }
+        analyzer_a_kernel<<<ind_grid(N, S), 64, smem, st>>>(close, N, ld, fast, slow, sign, halo_ema, halo_sig, w_rsi, halo_rsi,
+                                                           col(B200BT_COL_EMA_12), col(B200BT_COL_EMA_26), col(B200BT_COL_MACD),
+                                                           col(B200BT_COL_MACD_SIGNAL), col(B200BT_COL_MACD_DIFF), col(B200BT_COL_RSI), lf);
+        B200BT_LAUNCH_CHECK("analyzer A launch");
+    }
+    // B: close -> sma_20, sma_50, sma_200, Bollinger
+    {
+        const int halo = sma_w[2] - 1;
+        const size_t smem = (size_t)2 * (IND_TILE + IND_MAX_WINDOW + 1) * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(analyzer_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e, "analyzer: cudaFuncSetAttribute");
+        LeadFill lf{};
+        const int cs[7] = {B200BT_COL_SMA_20, B200BT_COL_SMA_50, B200BT_COL_SMA_200, B200BT_COL_BB_HIGH, B200BT_COL_BB_MID, B200BT_COL_BB_LOW,
+                           B200BT_COL_BB_WIDTH};
+        const int fs[7] = {sma_w[0] - 1, sma_w[1] - 1, sma_w[2] - 1, w_bb - 1, w_bb - 1, w_bb - 1, w_bb - 1};
+        lf.n = 7;
+        for (int i = 0; i < 7; ++i) { lf.col[i] = col(cs[i]); lf.first[i] = fs[i]; }
+        analyzer_b_kernel<<<ind_grid(N, S), IND_THREADS, smem, st>>>(close, N, ld, sma_w[0], sma_w[1], sma_w[2], w_bb, 2.0,
+                                                                    col(B200BT_COL_SMA_20), col(B200BT_COL_SMA_50), col(B200BT_COL_SMA_200),
+                                                                    col(B200BT_COL_BB_HIGH), col(B200BT_COL_BB_MID), col(B200BT_COL_BB_LOW),
+                                                                    col(B200BT_COL_BB_WIDTH), col(B200BT_COL_BB_POSITION), halo, lf);
+        B200BT_LAUNCH_CHECK("analyzer B launch");
+    }
+    // C: high, low, close, volume -> stochastic, Williams %R, Ichimoku, ATR, VWAP
+    {
+        B200BT_REQUIRE(w_wr == w_st && ich[0] <= w_st && w_st <= ich[1] && ich[1] <= ich[2], B200BT_EINVAL, "analyzer: windows must nest");
+        BankParams prm;
+        int atr_halo;
+        int rc = fill_bank_params(&w_atr, 1, true, prm, atr_halo, "analyzer");
+        if (rc) return rc;
+        B200BT_REQUIRE(ich[2] - 1 <= 256 && w_st + smooth - 2 <= 256, B200BT_ELIMIT, "analyzer: window too long");
+        size_t smem = (size_t)3 * (IND_TILE + 256) * sizeof(float) + (size_t)(IND_TILE + 256) * sizeof(double);
+        const size_t smem_atr = (size_t)(atr_halo + IND_TILE + IND_MAX_WINDOW + 8) * sizeof(double);
+        const size_t smem_vwap = (size_t)2 * (IND_TILE + IND_MAX_WINDOW + 1) * sizeof(double);
+        if (smem_atr > smem) smem = smem_atr;
+        if (smem_vwap > smem) smem = smem_vwap;
+        cudaError_t e = cudaFuncSetAttribute(analyzer_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e, "analyzer: cudaFuncSetAttribute");
+        LeadFill lf{};
+        lf.n = 2;
+        lf.col[0] = col(B200BT_COL_ICHIMOKU_A); lf.first[0] = ich[1] - 1;
+        lf.col[1] = col(B200BT_COL_ICHIMOKU_B); lf.first[1] = ich[2] - 1;
+        analyzer_c_kernel<<<ind_grid(N, S), IND_THREADS, smem, st>>>(high, low, close, volume, N, ld, w_st, smooth, ich[0], ich[1], ich[2],
+                                                                    w_atr, atr_halo, w_vwap, col(B200BT_COL_STOCH_K), col(B200BT_COL_STOCH_D),
+                                                                    col(B200BT_COL_WILLIAMS_R), col(B200BT_COL_ICHIMOKU_A),
+                                                                    col(B200BT_COL_ICHIMOKU_B), col(B200BT_COL_ATR), col(B200BT_COL_VWAP), lf);
+        B200BT_LAUNCH_CHECK("analyzer C launch");
+    }
+    // NaN policy of the five columns that can be undefined in mid-series (they are the last five of the allocation)
+    return b200bt_nanfill(col(B200BT_COL_VWAP), (int64_t)5 * S, N, workspace, stream);
 }

@@ -144,19 +144,16 @@ class TechnicalAnalyzer:
         assert isinstance(market, MarketData)
         self.market = market
         o, h, l, c, v = market.open, market.high, market.low, market.close, market.volume
-        d: Dict[str, torch.Tensor] = {}
-        sma = sma_bank(c, [20, 50, 200])                                   # :67-76
-        d["sma_20"], d["sma_50"], d["sma_200"] = sma[:, 0], sma[:, 1], sma[:, 2]
-        ema = ema_bank(c, [12, 26])                                        # :79-83
-        d["ema_12"], d["ema_26"] = ema[:, 0], ema[:, 1]
-        d["macd"], d["macd_signal"], d["macd_diff"] = macd(c)              # :91-94
-        d["ichimoku_a"], d["ichimoku_b"] = ichimoku(h, l)                  # :102-104
-        d["rsi"] = rsi_bank(c, [14])[:, 0]                                 # :112
-        d["stoch_k"], d["stoch_d"] = stochastic(h, l, c)                   # :121-127
-        d["williams_r"] = williams_r(h, l, c)                              # :135-140
-        d["bb_high"], d["bb_mid"], d["bb_low"], d["bb_width"], d["bb_position"] = bollinger(c)   # :148-156
-        d["atr"] = atr_bank(h, l, c, [14])[:, 0]                           # :164
-        d["vwap"] = vwap(h, l, c, v)                                       # :173-179
+        S, N = _check(h, l, c, v)
+        # all 21 columns of _calculate_all_indicators (:40-182) + _handle_nan_values in three fused launches and one batched
+        # NaN-policy call (b200bt_analyzer): one [21][S][N] allocation, self.data[name] = its [S][N] block
+        lib = _lib.load()
+        cols = torch.empty((len(_lib.ANALYZER_COLUMNS), S, N), dtype=torch.float32, device=c.device)
+        ws = torch.empty(int(lib.b200bt_analyzer_workspace_floats(S, N)), dtype=torch.float32, device=c.device)
+        with torch.cuda.device(c.device):
+            _lib.call("b200bt_analyzer", h.data_ptr(), l.data_ptr(), c.data_ptr(), v.data_ptr(), S, N, _lib.ld(c), cols.data_ptr(),
+                      ws.data_ptr(), _lib.current_stream())
+        d: Dict[str, torch.Tensor] = {name: cols[i] for i, name in enumerate(_lib.ANALYZER_COLUMNS)}
         self.data = d
         last = torch.stack([d[k][:, -1] for k in self.COLUMNS] + [c[:, -1], h[:, -1], l[:, -1]], dim=1)
         self._last = last.double().cpu().numpy()                           # [S][len(COLUMNS)+3]

@@ -60,6 +60,23 @@ int b200bt_rsi_bank(const float* close, int S, int64_t N, int64_t ld,
                     const int* periods_host, int P, int fill,
                     float* out, b200bt_stream_t stream);
 
+/* TechnicalAnalyzer._calculate_all_indicators + _handle_nan_values (binance_ml_strategy.py:28-182) for S symbols in three
+ * fused launches (close -> EMA / MACD / RSI; close -> SMA / Bollinger; high, low, close, volume -> stochastic / Williams %R /
+ * Ichimoku / ATR / VWAP) plus one batched NaN-policy call, with the reference's windows (20/50/200, 12/26/9, 9/26/52, 14, 14/3,
+ * 14, 20 x 2.0, 14, 14).  cols: [B200BT_ANALYZER_COLUMNS][S][N] fp32 (device, out), column c at cols + c * S * N in the order
+ * below; workspace: b200bt_analyzer_workspace_floats(S, N) floats (device). */
+enum b200bt_analyzer_column {
+    B200BT_COL_SMA_20 = 0, B200BT_COL_SMA_50, B200BT_COL_SMA_200, B200BT_COL_EMA_12, B200BT_COL_EMA_26, B200BT_COL_MACD,
+    B200BT_COL_MACD_SIGNAL, B200BT_COL_MACD_DIFF, B200BT_COL_ICHIMOKU_A, B200BT_COL_ICHIMOKU_B, B200BT_COL_RSI, B200BT_COL_BB_HIGH,
+    B200BT_COL_BB_MID, B200BT_COL_BB_LOW, B200BT_COL_BB_WIDTH, B200BT_COL_ATR,
+    /* columns that can be undefined in mid-series (zero volume / zero range): general ffill-bfill pass */
+    B200BT_COL_VWAP, B200BT_COL_STOCH_K, B200BT_COL_STOCH_D, B200BT_COL_WILLIAMS_R, B200BT_COL_BB_POSITION,
+    B200BT_ANALYZER_COLUMNS
+};
+int64_t b200bt_analyzer_workspace_floats(int S, int64_t N);
+int b200bt_analyzer(const float* high, const float* low, const float* close, const float* volume, int S, int64_t N, int64_t ld,
+                    float* cols, float* workspace, b200bt_stream_t stream);
+
 /* b200bt_rsi_bank (NaN policy applied) that also writes the bank's rows of a sweep zone map (see b200bt_zone_map: row 0 =
  * the close prices, rows 1..P = the RSI rows) while the values are in registers, so that the first sweep of a fresh bank can
  * already skip quiet blocks.  `zones` is the WHOLE zone map of S_total symbols (b200bt_zone_map_floats(P, S_total, N) floats);

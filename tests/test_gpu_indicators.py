@@ -186,3 +186,40 @@ def test_multi_timeframe_recipe(gpu):
     for k, v in want.items():
         assert got[k] == pytest.approx(v, rel=3e-5, abs=3e-6), k
     assert got["price_change_15m"] == pytest.approx((last(df["close"]) - last(d15["open"])) / last(d15["open"]) * 100, rel=1e-5)
+
+
+@pytest.mark.parametrize("n_bars", [1, 5, 13, 19, 33, 60, 255, 2048, 2049, 5000, 70001])
+def test_fused_analyzer_columns_match_the_reference_policy(gpu, n_bars):
+    """TechnicalAnalyzer (three fused launches + one batched NaN-policy call) against the float64 restatement of
+    _calculate_all_indicators + _handle_nan_values, all 21 columns, incl. series shorter than the windows (all-NaN -> 0),
+    a flat stretch (zero ranges: stochastic / Williams / bb_position undefined in mid-series -> ffill)."""
+    torch = gpu
+    from ai_crypto_trader_b200 import synth
+    from ai_crypto_trader_b200.indicators import TechnicalAnalyzer
+    from ai_crypto_trader_b200.sweep import MarketData
+    from oracle import indicators_ref as ref
+    S = 2
+    ohlcv = synth.synth_ohlcv(S, n_bars, first_symbol=6)
+    if n_bars >= 255:
+        a, b = n_bars // 3, n_bars // 3 + 70            # a flat stretch on symbol 1: open == high == low == close
+        flat = ohlcv[3, 1, a]
+        ohlcv[0:4, 1, a:b] = flat                       # (volume stays positive: a window without volume makes the reference's
+                                                        #  VWAP 0/0 on pandas' rolling-sum residue, inf or garbage)
+    ta = TechnicalAnalyzer(MarketData(ohlcv))
+    assert set(ta.data) == set(TechnicalAnalyzer.COLUMNS)
+    for s in range(S):
+        so, sh, sl, sc, sv = _series(ohlcv, s)
+        want = ref.analyzer_columns(so, sh, sl, sc, sv)
+        for name, w in want.items():
+            tol = dict(macd_diff=(1e-4, 2e-7), bb_width=(2e-5, 1e-7), bb_position=(2e-5, 1e-6), stoch_k=(RTOL, 1e-5), stoch_d=(RTOL, 1e-5),
+                       williams_r=(RTOL, 1e-5), macd=(RTOL, 1e-9), macd_signal=(RTOL, 1e-9)).get(name, (RTOL, 1e-12))
+            got = ta.data[name][s].cpu().numpy()
+            assert not np.isnan(got).any(), (name, "NaN left after the policy")
+            w = w.to_numpy()
+            if name == "bb_position":
+                # 0/0 where the 20-bar window is exactly flat in mid-series: pandas' online variance leaves a rounding residue
+                # there (std ~1e-9 of the price, position = residue / residue = 0.5), the kernel's prefix differences give an exact zero range
+                # (-> NaN -> ffill).  Neither is "the" value; compare where the range is a number.
+                ill = (want["bb_high"] - want["bb_low"]).to_numpy() <= 1e-7 * want["bb_mid"].to_numpy()
+                got, w = got[~ill], w[~ill]
+            _cmp(got, w, f"{name} (symbol {s}, N={n_bars})", rtol=tol[0], atol=tol[1])
