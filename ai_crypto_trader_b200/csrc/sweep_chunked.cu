@@ -294,6 +294,7 @@ struct LaneScanArgs {
     const b200bt_individual* indiv; const int32_t* slots; int n_slots; int pop; int K; int warm;
     uint2* pool; int pool_blocks; int* next; unsigned* alloc;
     int* seg_first; unsigned* seg_count; int2* seg_in; int2* seg_out; int* overflow;
+    unsigned* work;      // work-item counter of the persistent scan (zero at launch)
 };
 
 __device__ __forceinline__ int sym_of_block(unsigned bx, int S) { return (int)(bx % (unsigned)S); }
@@ -338,30 +339,22 @@ static_assert(LS_ZONE == ZONE_BLOCK && LS_T == ZONE_TILE, "zone map layout (comm
 // CTA, two CTA barriers per tile) showed a third of the warp time parked at those barriers behind the CTA's busiest warp
 // and 18 % of the instructions computing cp.async addresses -- and the bytes moved per machine stay what they were,
 // because a CTA-wide tile staged P + 1 rows for 256 machines and a warp stages 3 for 32.
+// One work item: the 32 machines of warp-slot `wslot` (thread slots wslot * 32 ...) on symbol `sym`, chunk `c`.
 template <bool ZONES>
-__global__ void __launch_bounds__(LS_THREADS, B200BT_LS_MIN_BLOCKS)
-lane_scan_kernel(const LaneScanArgs A, const bool vec16) {   // by value, not __grid_constant__ (see sweep.cu)
-    // [LS_WARPS][LS_STAGES][LS_ROWS][LS_STRIDE] floats, then (ZONES) per warp and stage [LS_ROWS][LS_T / 32 + LS_T / 4] float2
-    extern __shared__ __align__(16) float ls_tile[];
-    __shared__ __align__(8) unsigned long long ls_full[LS_WARPS][LS_STAGES];   // "tile landed" (1 arrival + the copies' bytes)
+__device__ __forceinline__ void lane_scan_item(const LaneScanArgs& A, const bool vec16, const int wslot, const int sym, const int c,
+                                               float* const wtile, float2* const wzone, unsigned long long* const full,
+                                               float (*ls_mul)[LS_THREADS], const void* (*ls_src_w)[3]) {
     constexpr int ZB = LS_T / LS_ZONE;                  // zone blocks per tile
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* const wtile = ls_tile + (size_t)warp * LS_STAGES * LS_ROWS * LS_STRIDE;
     constexpr int FG = LS_T / 4;                        // 4-bar groups per tile
     constexpr int ZR = ZB + FG;                         // float2 per staged row: coarse ranges, then fine ranges
-    float2* const wzone = reinterpret_cast<float2*>(ls_tile + (size_t)LS_WARPS * LS_STAGES * LS_ROWS * LS_STRIDE) + (size_t)warp * LS_STAGES * LS_ROWS * ZR;
-    unsigned long long* const full = ls_full[warp];
-    const int sym = (int)(blockIdx.x % (unsigned)A.S);
-    const int c = (int)((blockIdx.x / (unsigned)A.S) % (unsigned)A.K);
-    const int blk = (int)(blockIdx.x / ((unsigned)A.S * (unsigned)A.K));
-    const int k = blk * LS_THREADS + (int)threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int k = wslot * 32 + lane;
     const int slot = k < A.n_slots ? (A.slots ? A.slots[k] : (k < A.pop ? k : -1)) : -1;
     const bool active = slot >= 0;
     const int ind = active ? slot : 0;
     const b200bt_individual iv = A.indiv[ind];
     // the screening multipliers are needed on events only: shared memory, [multiplier][thread] (conflict-free),
     // side-major so that the side selects an address instead of a value: long hi_c lo_c hi_d lo_d, short ...
-    __shared__ float ls_mul[8][LS_THREADS];
     const float os_f = iv.rsi_lo, ob_f = iv.rsi_hi;
     {
         ScanConst sc;
@@ -370,9 +363,11 @@ lane_scan_kernel(const LaneScanArgs A, const bool vec16) {   // by value, not __
         m[0 * LS_THREADS] = sc.hiL_c; m[1 * LS_THREADS] = sc.loL_c; m[2 * LS_THREADS] = sc.hiL_d; m[3 * LS_THREADS] = sc.loL_d;
         m[4 * LS_THREADS] = sc.hiS_c; m[5 * LS_THREADS] = sc.loS_c; m[6 * LS_THREADS] = sc.hiS_d; m[7 * LS_THREADS] = sc.loS_d;
     }
+    __syncwarp();
     if (lane == 0) {
+        // (re)arm the ring's barriers: every copy of the previous item has landed and been waited for
 #pragma unroll
-        for (int s = 0; s < LS_STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < LS_STAGES; ++s) { mbar_inval(&full[s]); mbar_init(&full[s], 1); }
         mbar_fence_init();
         fence_proxy_async();
     }
@@ -411,11 +406,10 @@ lane_scan_kernel(const LaneScanArgs A, const bool vec16) {   // by value, not __
     const int zrow = (lane == 0 || !issuer) ? 0 : 1 + row_of_lane;      // row of the zone map (0 = price)
     // source rows of the warp's staged rows: a small table in shared memory (read by the issuing lanes only: three
     // 64-bit pointers per thread would not fit the register budget of the scan loop)
-    __shared__ const void* ls_src[LS_WARPS][LS_ROWS][3];
     if (issuer) {
-        ls_src[warp][lane][0] = (lane == 0) ? A.price + (int64_t)sym * A.ld_price : A.rsi + ((int64_t)sym * A.P + row_of_lane) * A.ld_rsi;
-        ls_src[warp][lane][1] = ZONES ? A.zones + ((int64_t)sym * (A.P + 1) + zrow) * A.n_zone_blocks : nullptr;   // (n_zone_blocks = row stride)
-        ls_src[warp][lane][2] = ZONES ? A.fine + ((int64_t)sym * (A.P + 1) + zrow) * A.n_fine : nullptr;
+        ls_src_w[lane][0] = (lane == 0) ? A.price + (int64_t)sym * A.ld_price : A.rsi + ((int64_t)sym * A.P + row_of_lane) * A.ld_rsi;
+        ls_src_w[lane][1] = ZONES ? A.zones + ((int64_t)sym * (A.P + 1) + zrow) * A.n_zone_blocks : nullptr;   // (n_zone_blocks = row stride)
+        ls_src_w[lane][2] = ZONES ? A.fine + ((int64_t)sym * (A.P + 1) + zrow) * A.n_fine : nullptr;
     }
     __syncwarp();
     const unsigned stage_bytes = (unsigned)(1 + n_rsi) * (LS_T * 4 + (ZONES ? ZR * 8 : 0));
@@ -430,20 +424,20 @@ lane_scan_kernel(const LaneScanArgs A, const bool vec16) {   // by value, not __
             __syncwarp();
             if (issuer) {
                 fence_proxy_async();      // the warp's reads of the stage (generic proxy) are ordered before the async writes
-                bulk_g2s(dst0 + lane * LS_STRIDE, static_cast<const float*>(ls_src[warp][lane][0]) + t0, LS_T * 4, &full[stage]);
+                bulk_g2s(dst0 + lane * LS_STRIDE, static_cast<const float*>(ls_src_w[lane][0]) + t0, LS_T * 4, &full[stage]);
                 if (ZONES) {
-                    bulk_g2s(zdst + lane * ZR, static_cast<const float2*>(ls_src[warp][lane][1]) + (int64_t)tl * ZB, ZB * 8, &full[stage]);
-                    bulk_g2s(zdst + lane * ZR + ZB, static_cast<const float2*>(ls_src[warp][lane][2]) + (int64_t)tl * FG, FG * 8, &full[stage]);
+                    bulk_g2s(zdst + lane * ZR, static_cast<const float2*>(ls_src_w[lane][1]) + (int64_t)tl * ZB, ZB * 8, &full[stage]);
+                    bulk_g2s(zdst + lane * ZR + ZB, static_cast<const float2*>(ls_src_w[lane][2]) + (int64_t)tl * FG, FG * 8, &full[stage]);
                 }
             }
         } else {
             const float qnan = __int_as_float(0x7fc00000);   // unaligned input or the ragged last tile: plain copies
             for (int r = 0; r <= n_rsi; ++r) {
-                const float* src = static_cast<const float*>(ls_src[warp][r][0]);
+                const float* src = static_cast<const float*>(ls_src_w[r][0]);
                 for (int col = lane; col < LS_T; col += 32) dst0[r * LS_STRIDE + col] = (t0 + col < n) ? __ldg(src + t0 + col) : qnan;
                 if (ZONES) {
-                    const float2* zs = static_cast<const float2*>(ls_src[warp][r][1]);
-                    const float2* fs = static_cast<const float2*>(ls_src[warp][r][2]);
+                    const float2* zs = static_cast<const float2*>(ls_src_w[r][1]);
+                    const float2* fs = static_cast<const float2*>(ls_src_w[r][2]);
                     if (lane < ZB) {
                         const int64_t zblk = (int64_t)tl * ZB + lane;
                         zdst[r * ZR + lane] = (zblk * LS_ZONE < n) ? zs[zblk] : make_float2(qnan, qnan);
@@ -581,6 +575,41 @@ lane_scan_kernel(const LaneScanArgs A, const bool vec16) {   // by value, not __
         ++count;
     }
     A.seg_count[seg] = dead ? 0xffffffffu : count;
+}
+
+// Persistent form: the grid is one resident set of CTAs; every WARP takes work items -- (warp-slot, chunk, symbol), the
+// most expensive warp-slots first -- from a global counter until none is left, so all warp slots of the GPU stay busy until
+// the queue is empty and the last items to run are the cheapest ones (a static grid left the busiest CTAs running alone
+// at the end while the rest of their SM sat idle).
+template <bool ZONES>
+__global__ void __launch_bounds__(LS_THREADS, B200BT_LS_MIN_BLOCKS)
+lane_scan_kernel(const LaneScanArgs A, const bool vec16) {   // by value, not __grid_constant__ (see sweep.cu)
+    // [LS_WARPS][LS_STAGES][LS_ROWS][LS_STRIDE] floats, then (ZONES) per warp and stage [LS_ROWS][LS_T / 32 + LS_T / 4] float2
+    extern __shared__ __align__(16) float ls_tile[];
+    __shared__ __align__(8) unsigned long long ls_full[LS_WARPS][LS_STAGES];   // "tile landed" (1 arrival + the copies' bytes)
+    __shared__ float ls_mul[8][LS_THREADS];
+    __shared__ const void* ls_src[LS_WARPS][LS_ROWS][3];
+    constexpr int ZR = LS_T / LS_ZONE + LS_T / 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* const wtile = ls_tile + (size_t)warp * LS_STAGES * LS_ROWS * LS_STRIDE;
+    float2* const wzone = reinterpret_cast<float2*>(ls_tile + (size_t)LS_WARPS * LS_STAGES * LS_ROWS * LS_STRIDE) + (size_t)warp * LS_STAGES * LS_ROWS * ZR;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < LS_STAGES; ++s) mbar_init(&ls_full[warp][s], 1);
+    }
+    __syncwarp();
+    const int per_slot = A.K * A.S;
+    const int n_items = (A.n_slots / 32) * per_slot;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = (int)atomicAdd(A.work, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= n_items) break;
+        const int wslot = item / per_slot, rest = item - wslot * per_slot;
+        const int c = rest / A.S, sym = rest - c * A.S;
+        lane_scan_item<ZONES>(A, vec16, wslot, sym, c, wtile, wzone, ls_full[warp], ls_mul, ls_src[warp]);
+        __syncwarp();
+    }
 }
 
 // One thread per (individual, symbol): list every chunk whose assumed state differs from the end state
@@ -1321,8 +1350,17 @@ extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const fl
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return cuda_status(e, "sweep_tiled: cudaFuncSetAttribute");
-    const int64_t blocks = (int64_t)((n_slots + LS_THREADS - 1) / LS_THREADS) * K * S;
-    B200BT_REQUIRE(blocks < (1ll << 31), B200BT_ELIMIT, "sweep_tiled: too many work items");
+    const int64_t n_items = (int64_t)(n_slots / 32) * K * S;
+    B200BT_REQUIRE(n_items < (1ll << 30), B200BT_ELIMIT, "sweep_tiled: too many work items");
+    L.work = w.n_repair + REPAIR_COUNTERS - 1;      // (a counter no repair round uses; zeroed with the rest above)
+    // persistent grid: one resident set of CTAs (warps take work items from the counter), no more CTAs than items need
+    int dev = 0, sms = 0, per_sm = 0;
+    e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LS_THREADS, smem);
+    if (e != cudaSuccess) return cuda_status(e, "sweep_tiled: occupancy");
+    int64_t blocks = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
+    if (blocks > (n_items + LS_WARPS - 1) / LS_WARPS) blocks = (n_items + LS_WARPS - 1) / LS_WARPS;
     kern<<<(unsigned)blocks, LS_THREADS, smem, st>>>(L, vec16);
     B200BT_LAUNCH_CHECK("lane_scan launch");
 

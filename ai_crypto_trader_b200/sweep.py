@@ -383,12 +383,13 @@ class TilePlan:
     @classmethod
     def chunks_for(cls, pop: int, n_bars: int, n_symbols: int, device, warm: int = 8192, max_chunks: int = 64,
                    n_slots: Optional[int] = None) -> int:
-        """About 1.75 resident sets of CTAs (measured optimum on the C2 workload, flat from 1.6 to 1.9: heavy CTAs
-        run longer, so whole "waves" do not exist), chunks at least 4 warm-ups long."""
+        """About 2.15 work items per resident warp slot (the scan is persistent: warps take (warp-slot, chunk, symbol) items
+        from a counter, the most expensive first; measured on configs[1]: K = 20 9.5 ms, 26 8.25, 32 8.15, 40 8.4 -- more
+        chunks balance better but every chunk pays its warm-up), chunks at least 4 warm-ups long."""
         kmax = max(1, min(max_chunks, n_bars // max(4 * warm, 2048)))
         slots = _sm_count(device) * cls.CTAS_PER_SM
         groups = -(-(n_slots if n_slots is not None else pop) // cls.THREADS) * n_symbols
-        return min(kmax, max(1, round(1.75 * slots / groups)))
+        return min(kmax, max(1, round(2.15 * slots / groups)))
 
     def __init__(self, population: List[Dict], n_bars: int, n_symbols: int, device, warm: int = 8192,
                  max_chunks: int = 64, chunks: Optional[int] = None, pool_scale: float = 1.5,
