@@ -43,6 +43,18 @@ constexpr int ZONE_TILE = 128;          // bars per tile of the thread-per-lane 
 __host__ __device__ constexpr int64_t zone_row_stride(int64_t N) { return (((N + ZONE_BLOCK - 1) / ZONE_BLOCK) + 1) & ~(int64_t)1; }
 __host__ __device__ constexpr int64_t zone_fine_stride(int64_t N) { return ((N + ZONE_TILE - 1) / ZONE_TILE) * (ZONE_TILE / 4); }
 
+// RSI from the two Wilder averages, ta.momentum.RSIIndicator: 100 if D == 0 else 100 - 100 / (1 + U / D), rounded to fp32.
+// Evaluated as 100 U / (U + D) with ONE reciprocal: the two float64 divisions of the literal form were half of the RSI
+// bank kernel's instructions.  The forms agree to ~2e-14 absolute (1.5 ulp each), so they round to the same fp32 value
+// except on a ~1e-8 fraction of double-rounding ties -- below the 2e-6 the bank is tested at against float64 pandas.
+// A sum in the denormal range (thousands of flat bars) takes the literal form.
+__device__ __forceinline__ float rsi_value(double U, double D) {
+    if (D == 0.0) return 100.0f;
+    const double S = U + D;
+    if (S < 1e-290) return (float)(100.0 - 100.0 / (1.0 + U / D));
+    return (float)((100.0 * U) * __drcp_rn(S));
+}
+
 __device__ __forceinline__ double shfl_up_d(double v, int d) {
     return __shfl_up_sync(FULL, v, d);
 }

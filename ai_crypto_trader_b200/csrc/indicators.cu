@@ -35,7 +35,10 @@ struct RsiBankParams {
 // rows of P_all + 1 entries per symbol with row 0 = price): the bank's (min, max) ranges are produced from the values in
 // registers while they are written -- a lane's four bars ARE one 4-bar group, eight lanes one 32-bar block -- and the price
 // row's from the staged closes, so the first sweep of a fresh bank already skips quiet blocks.
-__global__ void __launch_bounds__(256)
+#ifndef B200BT_RSI_MIN_BLOCKS
+#define B200BT_RSI_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, B200BT_RSI_MIN_BLOCKS)
 rsi_bank_kernel(const float* __restrict__ close, int64_t N, int64_t ld,
                 const __grid_constant__ RsiBankParams prm, int P, int fill, int halo_max,
                 float* __restrict__ out, int vec_ok, float2* __restrict__ zc, float2* __restrict__ zf, int P_all, int p0) {
@@ -140,8 +143,7 @@ rsi_bank_kernel(const float* __restrict__ close, int64_t N, int64_t ld,
             for (int j = 0; j < RSI_K; ++j) {
                 U = U * om + alpha * u[j];
                 D = D * om + alpha * d[j];
-                double v = (D == 0.0) ? 100.0 : 100.0 - 100.0 / (1.0 + U / D);
-                r[j] = (float)v;
+                r[j] = rsi_value(U, D);
             }
             const bool mine = t >= tile_start && t < tile_end;
             if (mine) {

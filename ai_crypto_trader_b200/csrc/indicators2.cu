@@ -709,8 +709,7 @@ analyzer_a_kernel(const float* __restrict__ x, int64_t N, int64_t ld, int fast, 
 #pragma unroll
             for (int j = 0; j < K; ++j)
                 if (t + j >= tile_start && t + j < tile_end) {
-                    const double v = (yd[j] == 0.0) ? 100.0 : 100.0 - 100.0 / (1.0 + yu[j] / yd[j]);
-                    o_rsi[(int64_t)sym * N + t + j] = (t + j >= w_rsi - 1) ? (float)v : nanf32();
+                    o_rsi[(int64_t)sym * N + t + j] = (t + j >= w_rsi - 1) ? rsi_value(yu[j], yd[j]) : nanf32();
                 }
         }
     }

@@ -1304,6 +1304,14 @@ extern "C" int64_t b200bt_sweep_tiled_workspace_bytes(int pool_blocks, int S, in
     return chunk_workspace_bytes(pool_blocks, S * n_seg, (int)n_seg, pop) + 16 + n_seg * 16 + (int64_t)pop * 8;
 }
 
+// measurement hook: a pair of caller-owned CUDA events recorded around the scan kernel of the next b200bt_sweep_tiled calls
+static cudaEvent_t g_scan_ev[2] = {nullptr, nullptr};
+extern "C" int b200bt_sweep_scan_timing(void* start_event, void* stop_event) {
+    g_scan_ev[0] = (cudaEvent_t)start_event;
+    g_scan_ev[1] = (cudaEvent_t)stop_event;
+    return B200BT_OK;
+}
+
 extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const float* rsi, int64_t ld_rsi, int P, int S,
                                   int64_t N, const float* zones_or_null, const b200bt_individual* indiv, const int32_t* slots,
                                   int n_slots, const int32_t* order, int pop, int K, int warm, int max_repair_rounds, int pool_blocks, void* workspace,
@@ -1361,7 +1369,9 @@ extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const fl
     if (e != cudaSuccess) return cuda_status(e, "sweep_tiled: occupancy");
     int64_t blocks = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
     if (blocks > (n_items + LS_WARPS - 1) / LS_WARPS) blocks = (n_items + LS_WARPS - 1) / LS_WARPS;
+    if (g_scan_ev[0]) cudaEventRecord(g_scan_ev[0], st);
     kern<<<(unsigned)blocks, LS_THREADS, smem, st>>>(L, vec16);
+    if (g_scan_ev[1]) cudaEventRecord(g_scan_ev[1], st);
     B200BT_LAUNCH_CHECK("lane_scan launch");
 
     ChunkScanArgs A;   // for the shared repair / metrics kernels

@@ -385,8 +385,8 @@ class TilePlan:
                    n_slots: Optional[int] = None) -> int:
         """About 2.15 work items per resident warp slot (the scan is persistent: warps take (warp-slot, chunk, symbol) items
         from a counter, the most expensive first; measured on configs[1]: K = 20 9.5 ms, 26 8.25, 32 8.15, 40 8.4 -- more
-        chunks balance better but every chunk pays its warm-up), chunks at least 4 warm-ups long."""
-        kmax = max(1, min(max_chunks, n_bars // max(4 * warm, 2048)))
+        chunks balance better but every chunk pays its warm-up), chunks at least 3 warm-ups long."""
+        kmax = max(1, min(max_chunks, n_bars // max(3 * warm, 2048)))
         slots = _sm_count(device) * cls.CTAS_PER_SM
         groups = -(-(n_slots if n_slots is not None else pop) // cls.THREADS) * n_symbols
         return min(kmax, max(1, round(2.15 * slots / groups)))

@@ -37,8 +37,8 @@ BYTES_PER_EVAL = 8  # price 4 B + RSI 4 B per (individual, symbol, 
 # the committed `ncu --set full` capture named in "source"; "scan_share" = the kernel's share of the sweep's kernel time in
 # the committed launch list of this bench command.  Valid for exactly that workload (the kernels are deterministic).
 NCU_C2 = {
-    "tiled": {"warp_inst": 3.7396e9, "threads_per_inst": 14.01, "dram_bytes": 3.998e9 + 1.031e9, "scan_share": 0.605,
-              "issue_active_pct": 67.1, "alu_pipe_pct": 51.9,
+    "tiled": {"warp_inst": 3.8631e9, "threads_per_inst": 14.18, "dram_bytes": 5.310e9 + 1.086e9, "scan_share": 0.595,
+              "issue_active_pct": 71.6, "alu_pipe_pct": 55.0,
               "source": "profiles/r2_lane_scan_ncu.txt (ncu --set full), profiles/r2_launches.csv (launch list of `bench.py --steps 2 --warmup 3 --skip-extras`)"},
 }
 
@@ -480,12 +480,20 @@ def main():
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        # the dominant kernel (lane_scan_kernel) is bracketed by its own pair of events, recorded by the library on the
+        # stream it launches on (b200bt_sweep_scan_timing); a first record() makes torch create the cudaEvent_t
+        s_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in s_ev:
+            a.record(); b.record()
+        handle = lambda e: (e.cuda_event.value if hasattr(e.cuda_event, "value") else int(e.cuda_event))
+        lib = _lib.load()
         launches0 = _lib.launch_count()
         t_wall0 = time.time()
         ev0.record()
         for i in range(args.steps):
             # the sweep (scan, verify / repair, metrics, fitness reduction) is bracketed by its own events inside the
             # timed region; the all-gather follows
+            lib.b200bt_sweep_scan_timing(handle(s_ev[i][0]), handle(s_ev[i][1]))
             k_ev[i][0].record()
             sweep.evaluate_device(indiv, order_d, pop_local, fit_local, plan=pl)
             k_ev[i][1].record()
@@ -498,11 +506,15 @@ def main():
         t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lib.b200bt_sweep_scan_timing(None, None)
         ms_k = statistics.mean(a.elapsed_time(b) for a, b in k_ev)
+        scan = [a.elapsed_time(b) for a, b in s_ev]
+        timed_sweeps.scan_ms = statistics.mean(scan) if min(scan) > 1e-3 else None     # (None: the plan has no scan kernel)
         return float(t.item()), ms_k, n_launch, (sampler.stop(t_wall0, t_wall1) if sampler else None)
 
     # ---- device-resident leg ------------------------------------------------
     ms_total, ms_kernel, launches, clocks = timed_sweeps(indiv_dev, order_dev, plan, sample_clocks=True)
+    scan_ms_live = timed_sweeps.scan_ms
     evals_per_step_global = pop_global * S * N
     value = evals_per_step_global * args.steps / (ms_total * 1e-3)
     fit_random = fit_local.clone()
@@ -563,17 +575,18 @@ def main():
                     "algorithmic_gbps": algorithmic_gbps, "bytes_per_eval": BYTES_PER_EVAL,
                     "hbm_peak_gbs": peak, "hbm_peak_source": peak_src}
         if ncu:
-            scan_ms = ms_kernel * ncu["scan_share"]
+            scan_ms = scan_ms_live if scan_ms_live else ms_kernel * ncu["scan_share"]
             achieved = ncu["warp_inst"] / (scan_ms * 1e-3) / 1e9
             roofline.update({
                 "achieved": achieved, "frac": achieved / issue_peak,
                 "warp_inst_per_launch": ncu["warp_inst"], "warp_inst_per_eval": ncu["warp_inst"] / lanes_evals,
-                "threads_per_inst": ncu["threads_per_inst"], "dominant_kernel_share_of_step": ncu["scan_share"],
+                "threads_per_inst": ncu["threads_per_inst"], "dominant_kernel_ms": scan_ms,
+                "dominant_kernel_share_of_step": scan_ms / ms_kernel, "dominant_kernel_share_in_launch_list": ncu["scan_share"],
                 "issue_active_pct_ncu": ncu["issue_active_pct"], "alu_pipe_pct_ncu": ncu["alu_pipe_pct"],
                 "traffic": ncu["dram_bytes"], "traffic_unit": "DRAM bytes per launch of the dominant kernel (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                 "dram_frac": ncu["dram_bytes"] / (scan_ms * 1e-3) / 1e9 / peak, "compulsory_bytes": (S * N * 4 + sweep.bank.numel() * 4),
                 "source": ncu["source"],
-                "note": "achieved = warp-instructions of lane_scan_kernel per launch (ncu, this workload) / (its share of the live CUDA-event time of the sweep kernels); algorithmic_gbps = SURVEY 8(d)'s 8 B x evals / kernel time, a throughput figure, not a bound"})
+                "note": "achieved = warp-instructions of lane_scan_kernel per launch (ncu, this workload) / its mean duration in the timed region (CUDA events recorded by the library around the kernel, on its stream); algorithmic_gbps = SURVEY 8(d)'s 8 B x evals / kernel time, a throughput figure, not a bound"})
         else:
             roofline.update({"achieved": None, "frac": None, "traffic": None,
                              "note": "no committed ncu capture for this workload size: only the algorithmic throughput is reported"})

@@ -324,6 +324,10 @@ int b200bt_sweep_tiled(const float* price, int64_t ld_price, const float* rsi, i
                        int64_t event_cap, unsigned char* lane_invalid, int* overflow_host_or_null,
                        b200bt_stream_t stream);
 
+/* Measurement hook (bench.py's roofline): a pair of caller-owned cudaEvent_t that the following b200bt_sweep_tiled calls of
+ * this process record on their stream immediately before and after the scan kernel (lane_scan_kernel); NULL, NULL switches
+ * it off.  The caller reads cudaEventElapsedTime after synchronising.  Not thread-safe (one measuring thread). */
+int b200bt_sweep_scan_timing(void* start_event, void* stop_event);
 
 /* fitness[i] = mean over symbols of stats[i][s].score  (float64, device). */
 int b200bt_fitness_reduce(const b200bt_lane_stats* stats, int pop, int S,

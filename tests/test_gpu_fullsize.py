@@ -51,7 +51,7 @@ def test_c2_full_parity(cuda):
     population = synth.random_population(POP, seed=42)
     plan = sweep.plan(population)
     assert plan is not None and isinstance(plan[0], TilePlan) and len(plan) == 1
-    assert plan[0].K == 32, plan[0].K                       # the bench configuration (148 SMs: 2.15 items per warp slot)
+    assert plan[0].K >= 24, plan[0].K                       # the bench configuration: ~2 work items per resident warp slot
     f1 = sweep.evaluate(population)
     h1 = sweep.lane_stats()["trade_hash"].copy()
     f2 = sweep.evaluate(population)                          # second sweep of the bank: zone map on
