@@ -28,6 +28,7 @@
 namespace b200bt {
 
 constexpr int CK_BLOCK = 256;   // events per pool block
+constexpr unsigned EVENT_BAR_MASK = ~(B200BT_EVENT_EXIT | B200BT_EVENT_SELL);   // event word = bar | flags
 
 struct ChunkScanArgs {
     const float* price; int64_t ld_price;
@@ -95,6 +96,21 @@ __device__ __forceinline__ void chunk_scan_item(const ChunkScanArgs& A, const b2
                 m.phi = e * c.hiS_c; m.plo = e * c.loS_c;
             }
         }
+    }
+
+    // REPAIR: the chain the speculative scan recorded for this chunk and the state it assumed at T0.  Two trajectories that
+    // are in the same state at the same bar coincide from there on, so the re-scan stops at the first group boundary at
+    // which its state equals the recorded trajectory's and splices the rest of the recorded events (below).
+    int old_block = -1, old_idx = 0, old_pos = 0, old_ebar = -1;
+    unsigned old_left = 0;
+    bool old_ok = false, spliced = false;
+    if (REPAIR) {
+        const unsigned oc = A.seg_count[seg];
+        const int2 oin = A.seg_in[seg];
+        old_ok = oc != 0xffffffffu;     // (a chunk whose events were dropped has no chain to splice)
+        old_left = old_ok ? oc : 0u;
+        old_block = A.seg_first[seg];
+        old_pos = oin.x; old_ebar = oin.x != 0 ? oin.y : -1;
     }
 
     // event sink: 32 queued events -> one coalesced 256-byte store into the chunk's current pool block
@@ -167,6 +183,39 @@ __device__ __forceinline__ void chunk_scan_item(const ChunkScanArgs& A, const b2
         __syncwarp();
         const bool emit = g * G >= T0;
         if (g * G == T0 && lane == 0) A.seg_in[seg] = make_int2(m.pos, m.pos != 0 ? m.entry_bar : -1);
+        if (REPAIR && old_ok && g > g_begin) {
+            // state of the recorded trajectory before bar tb = g * G: consume its events with bar < tb
+            const unsigned tb = (unsigned)(g * G);
+            while (old_left) {
+                const int n_here = (int)min(min(32u, old_left), (unsigned)(CK_BLOCK - old_idx));
+                const unsigned word = lane < n_here ? A.pool[(int64_t)old_block * CK_BLOCK + old_idx + lane].x : 0xffffffffu;
+                const int k = __popc(__ballot_sync(FULL, lane < n_here && (word & EVENT_BAR_MASK) < tb));    // (bars ascend: a prefix)
+                if (k) {
+                    const unsigned last = __shfl_sync(FULL, word, k - 1);
+                    old_pos = (last & B200BT_EVENT_EXIT) ? 0 : ((last & B200BT_EVENT_SELL) ? -1 : 1);
+                    old_ebar = (last & B200BT_EVENT_EXIT) ? -1 : (int)(last & EVENT_BAR_MASK);
+                    old_idx += k; old_left -= (unsigned)k;
+                    if (old_idx == CK_BLOCK && old_left) { old_block = A.next[old_block]; old_idx = 0; }
+                }
+                if (k < n_here) break;
+            }
+            if (m.pos == old_pos && (m.pos == 0 || m.entry_bar == old_ebar)) {
+                // same state at the same bar: the rest of the recorded chain is this trajectory's; copy it behind the
+                // re-scanned events (the chunk's end state, and with it every later chunk, stands as recorded)
+                while (old_left) {
+                    const int n_here = (int)min(min(32u, old_left), (unsigned)(CK_BLOCK - old_idx));
+                    if (lane < n_here) ws->evq[(m.qhead + lane) & (SW_EVQ - 1)] = A.pool[(int64_t)old_block * CK_BLOCK + old_idx + lane];
+                    m.qhead += (unsigned)n_here;
+                    old_idx += n_here; old_left -= (unsigned)n_here;
+                    if (old_idx == CK_BLOCK && old_left) { old_block = A.next[old_block]; old_idx = 0; }
+                    __syncwarp();
+                    while (m.qhead - qtail >= 32) flush(32);
+                    __syncwarp();
+                }
+                spliced = true;
+                break;
+            }
+        }
         const float* w = cur;
         int t0 = g * G;
 #pragma unroll 1
@@ -188,12 +237,12 @@ __device__ __forceinline__ void chunk_scan_item(const ChunkScanArgs& A, const b2
         if (++cstage == SW_STAGES) { cstage = 0; cur -= (SW_STAGES - 1) * (2 * G); } else cur += 2 * G;
     }
     cp_async_wait<0>();
-    if (lane == 0) {
+    if (lane == 0 && !spliced) {
         const int2 st = make_int2(m.pos, m.pos != 0 ? m.entry_bar : -1);
         A.seg_out[seg] = st;
         if (T0 >= T1) A.seg_in[seg] = st;   // empty chunk: its assumed state is the state after the warm-up
     }
-    if (item.chunk == item.n_chunks - 1 && m.pos != 0) {
+    if (!spliced && item.chunk == item.n_chunks - 1 && m.pos != 0) {
         // force-close at the last bar (:849-876)
         const float pl = __ldg(pr + (A.N - 1));
         const unsigned word = (unsigned)(A.N - 1) | B200BT_EVENT_EXIT | (m.pos > 0 ? B200BT_EVENT_SELL : 0u);
@@ -315,7 +364,7 @@ __global__ void lane_tables_kernel(int pop, int K, const int32_t* __restrict__ o
 }
 
 #ifndef B200BT_LS_MIN_BLOCKS
-#define B200BT_LS_MIN_BLOCKS 4
+#define B200BT_LS_MIN_BLOCKS 3      // 85 registers: at 4 CTAs/SM (64) the scan loop spilled 18 words and ran 3 % slower
 #endif
 #ifndef B200BT_LS_STAGES
 #define B200BT_LS_STAGES 2
@@ -628,11 +677,15 @@ __global__ void chunk_verify_kernel(int pop, int S, const int32_t* __restrict__ 
     const int K = n_chunks[ind];
     const int base = sym * n_seg + seg_base[ind];
     bool prev_bad = false;
+    const bool all = n_prev == nullptr;
     for (int c = 1; c < K; ++c) {
         const int2 a = seg_in[base + c], z = seg_out[base + c - 1];
         const bool bad = (a.x != z.x) || (a.y != z.y);
         const bool usable = seg_count[base + c - 1] != 0xffffffffu;   // predecessor did not lose events to a full pool
-        if (bad && !prev_bad && usable) repair[atomicAdd(n_repair, 1u)] = make_int4(ind, c, seg_base[ind] + c, sym);
+        // first round: every mismatching chunk at once -- a re-scan that finds its way back to the recorded trajectory keeps
+        // the chunk's recorded end state (splice in chunk_scan_item), so the successor's true start state is almost always
+        // the recorded one already; later rounds: only chunks whose predecessor is consistent (its end state is the truth)
+        if (bad && (all || !prev_bad) && usable) repair[atomicAdd(n_repair, 1u)] = make_int4(ind, c, seg_base[ind] + c, sym);
         prev_bad = bad;
     }
 }

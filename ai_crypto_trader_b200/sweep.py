@@ -378,20 +378,24 @@ class TilePlan:
     individual gets the same K time chunks, chosen so that the CTAs fill whole waves of the GPU."""
 
     THREADS = int(os.environ.get("B200BT_LS_THREADS", 256))     # individuals per CTA (csrc/sweep_chunked.cu LS_THREADS)
-    CTAS_PER_SM = int(os.environ.get("B200BT_LS_CTAS", 4))
+    CTAS_PER_SM = int(os.environ.get("B200BT_LS_CTAS", 3))     # resident CTAs of lane_scan_kernel per SM (__launch_bounds__(256, 3))
+    WARM = 2048          # warm-up bars of a speculative chunk
 
     @classmethod
-    def chunks_for(cls, pop: int, n_bars: int, n_symbols: int, device, warm: int = 8192, max_chunks: int = 64,
+    def chunks_for(cls, pop: int, n_bars: int, n_symbols: int, device, warm: int = WARM, max_chunks: int = 64,
                    n_slots: Optional[int] = None) -> int:
-        """About 2.15 work items per resident warp slot (the scan is persistent: warps take (warp-slot, chunk, symbol) items
-        from a counter, the most expensive first; measured on configs[1]: K = 20 9.5 ms, 26 8.25, 32 8.15, 40 8.4 -- more
-        chunks balance better but every chunk pays its warm-up), chunks at least 3 warm-ups long."""
+        """About 2.5 work items per resident warp slot (the scan is persistent: warps take (warp-slot, chunk, symbol) items
+        from a counter, the most expensive first; more chunks balance better but every chunk pays its warm-up and its share of
+        the per-chunk metrics overhead), chunks at least 3 warm-ups long.  Measured on configs[1] (3 CTAs/SM): a plateau of
+        7.4-7.45 ms for K = 26..30 and warm-ups of 1536..3072 bars; K = 34 7.7 ms, K = 24 7.6 ms.  A short warm-up is affordable
+        because a mis-speculated chunk is re-scanned only until it meets its recorded trajectory again (chunk_scan_item,
+        REPAIR): at 2048 bars ~10 % of the chunks start in the wrong state and take ~3500 bars each to come back."""
         kmax = max(1, min(max_chunks, n_bars // max(3 * warm, 2048)))
         slots = _sm_count(device) * cls.CTAS_PER_SM
         groups = -(-(n_slots if n_slots is not None else pop) // cls.THREADS) * n_symbols
-        return min(kmax, max(1, round(2.15 * slots / groups)))
+        return min(kmax, max(1, round(2.5 * slots / groups)))
 
-    def __init__(self, population: List[Dict], n_bars: int, n_symbols: int, device, warm: int = 8192,
+    def __init__(self, population: List[Dict], n_bars: int, n_symbols: int, device, warm: int = WARM,
                  max_chunks: int = 64, chunks: Optional[int] = None, pool_scale: float = 1.5,
                  pool_blocks: Optional[int] = None, max_repair_rounds: Optional[int] = None, lo: int = 0,
                  workspace: Optional[torch.Tensor] = None, order_by: str = "row_cost", pred: Optional[np.ndarray] = None,
@@ -406,7 +410,7 @@ class TilePlan:
             chunks = self.chunks_for(pop, n_bars, n_symbols, device, warm, max_chunks, n_slots=len(self.slots))
         self.K = int(chunks)
         # a lane that holds one position across many chunks needs one repair round per boundary
-        self.max_repair_rounds = int(max_repair_rounds) if max_repair_rounds is not None else min(self.K, 24)
+        self.max_repair_rounds = int(max_repair_rounds) if max_repair_rounds is not None else min(self.K, 64)
         self.n_seg = pop * self.K
         # every segment owns at least one block, and a repaired segment abandons its first chain
         self.pred_blocks = float(pred.sum()) * n_symbols / 256
@@ -713,7 +717,7 @@ class PopulationSweep:
             # thread-per-lane needs many machines: enough chunks per lane, or enough lanes (tools/mode_crossover.py:
             # at 200k bars the warp-per-chunk path is faster below ~2000 individuals x 10 symbols)
             k = TilePlan.chunks_for(len(population), self.market.N, self.market.S, self.market.device,
-                                    self.chunk_options.get("warm", 8192), self.chunk_options.get("max_chunks", 64))
+                                    self.chunk_options.get("warm", TilePlan.WARM), self.chunk_options.get("max_chunks", 64))
             tiled = k >= 16 or len(population) * self.market.S * k >= 100_000
         if not (tiled or self.mode == "chunked" or (self.mode == "auto" and long_enough)):
             return None

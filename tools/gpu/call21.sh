@@ -1,10 +1,10 @@
 #!/bin/bash
 set -u
-O=gpurun_out/r2t; mkdir -p $O
+O=gpurun_out/r2z; mkdir -p $O
 ( time python -m pytest tests -m gpu -q --durations=6 ) > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
 ( time python __graft_entry__.py --smoke ) > $O/smoke.log 2>&1; echo "smoke rc=$?" >> $O/smoke.log
 ( time python bench.py --steps 10 --warmup 3 ) > $O/bench.json 2> $O/bench.err
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:lane_scan -s 1 -c 1 -o $O/lane -f python tools/tile_profile.py 0 8192 > $O/ncu_lane.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:lane_scan -s 1 -c 1 -o $O/lane -f python tools/tile_profile.py 0 2048 > $O/ncu_lane.log 2>&1
 python tools/ncu_summary.py $O/lane.ncu-rep > $O/lane_summary.txt 2>&1
 ncu -i $O/lane.ncu-rep --page raw --csv > $O/lane_raw.csv 2>/dev/null
 rm -f $O/lane.ncu-rep
