@@ -239,6 +239,34 @@ def cpu_baseline_inline():
     st = tester_ref.backtest(df)
     py["configs0_backtest"] = {"cpu_ms": (time.perf_counter() - t0) * 1e3, "bars": len(df), "trades": int(st["total_trades"]),
                                "sample": "1 strategy x 1 symbol x 10 000 bars, oracle/tester_ref.py, 1 core"}
+    # BASELINE configs[2] on the CPU: the reference's NumPy GBM loop + per-path drawdowns, float64, at
+    # 10^5 paths x 1 000 steps (the full 10^6 x 10^4 would need an 80 GB array), one core like the reference
+    import numpy as np
+    from oracle import mc_ref
+    ret = np.random.default_rng(7).normal(5e-4, 0.02, 60)
+    mu, sigma = float(np.mean(ret) * 252), float(np.std(ret, ddof=1) * np.sqrt(252))
+    t0 = time.perf_counter()
+    fin, mdd = mc_ref.numpy_gbm_reference(100.0, mu, sigma, 1001, 100_000, seed=1)
+    mc_ref.risk_statistics(fin, mdd, 100.0, 0.95)
+    dt = time.perf_counter() - t0
+    py["mc_gbm_numpy"] = {"path_steps_per_s": 100_000 * 1000 / dt, "seconds": dt, "cores": 1,
+                          "sample": "100 000 paths x 1 000 steps, float64 (days, n) array stepped in time + drawdowns + percentiles (oracle/mc_ref.numpy_gbm_reference = monte_carlo_service.py:266-336)"}
+    # GA operators on the host: the reference's own selection / crossover / mutation for one generation
+    try:
+        from oracle import make_ref
+        from ai_crypto_trader_b200 import synth
+        _, _, RefGA = make_ref.load()
+        ga = RefGA(synth.param_ranges(), lambda ind: float(ind["rsi_period"]), population_size=POP_PER_GPU, generations=1, random_seed=42)
+        ga.initialize_population()
+        ga.evaluate_population()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ga.evolve_generation()
+            ga.evaluate_population()
+        py["ga_operators_reference_ms"] = {"value": (time.perf_counter() - t0) / 3 * 1e3, "population": POP_PER_GPU,
+                                           "sample": "services/genetic_algorithm.py evolve_generation (oracle/_ref, unmodified) with a trivial fitness, 1 core"}
+    except Exception as e:      # oracle/_ref absent: the leg is skipped, never replaced
+        py["ga_operators_reference_ms"] = {"unavailable": f"{type(e).__name__}: {e}"}
     return py
 
 
@@ -391,7 +419,7 @@ def run_extras(args, world, rank, dev, sweep, population, pop_local, timed_sweep
     reps = 3
     t, st = wall(lambda: [mc_job() for _ in range(reps)][-1])
     out["mc_c3_ms"] = {"value": 1e3 * t / reps, "path_steps_per_s": n_paths * steps / (t / reps), "paths": n_paths, "steps": steps,
-                       "var_pct": abs(st["var"]), "mdd_mean": st["mdd_mean"], "scaling": "strong",
+                       "var_pct": abs(st["var"]), "mdd_mean": st["mdd_mean"], "mu": mu, "sigma": sigma, "dt": 1 / 252, "scaling": "strong",
                        "what": "paths sharded by rank (Philox keyed by the global path index), one all-gather of finals + drawdowns, exact radix-select percentiles and moments on every rank; wall ms per run, max over ranks"}
     return out
 

@@ -142,3 +142,18 @@ def drift_and_vol(returns, scenario_params=None):
     sigma = r.std() * np.sqrt(252)
     sp = scenario_params or {}
     return mu * sp.get("drift_factor", 1.0), sigma * sp.get("volatility_factor", 1.0)
+
+
+def numpy_gbm_reference(s0, mu, sigma, days, n_paths, seed=0):
+    """The reference's OWN arithmetic and generator for the GBM mode (monte_carlo_service.py:266-273 paths, :327-336 per-path
+    drawdowns, in its vectorised form): a float64 (days, n) array stepped serially in time with NumPy's standard normals.
+    Used as the CPU baseline of the Monte-Carlo leg (bench.py) and for distribution-level tests -- its stream is NumPy's,
+    not Philox, so it is comparable with the kernels only statistically.  -> (finals, max drawdowns)"""
+    rng = np.random.RandomState(seed)
+    dt = 1.0 / 252
+    paths = np.zeros((days, n_paths))
+    paths[0] = s0
+    for t in range(1, days):
+        z = rng.standard_normal(n_paths)
+        paths[t] = paths[t - 1] * np.exp((mu - 0.5 * sigma ** 2) * dt + sigma * np.sqrt(dt) * z)
+    return paths[-1], path_drawdowns(paths)
