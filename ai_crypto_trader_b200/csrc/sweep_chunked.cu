@@ -14,9 +14,10 @@
 //                   THREAD per (individual, symbol, chunk) (b200bt_sweep_tiled, see "thread-per-lane scan").
 //                   Events -> blocks of a global pool (bump allocator, singly linked per chunk), plus the
 //                   chunk's assumed state at T_c and its end state.
-//   verify / repair chunk_verify_kernel lists chunks whose assumed state differs from the predecessor's end state;
-//                   chunk_scan_kernel<REPAIR> re-scans them from the true state.  The first rounds are on the
-//                   critical path, later ones run on a side stream beside the metrics kernels (finish_chunks).
+//   verify / repair lane_repair_kernel: one warp per lane walks the chunk boundaries in time order and re-scans a chunk
+//                   whose assumed state differs from its predecessor's end state (chunk_scan_item<REPAIR>: from the true
+//                   state, until the trajectory meets the recorded one; the rest of the recorded chain is spliced on).
+//                   A bounded pass on the critical path, an unbounded one beside the metrics kernels (finish_chunks).
 //   metrics kernels one warp per (individual, symbol, chunk) again (see "metrics, chunk-parallel" below), then
 //                   one thread per (individual, symbol) checks end state of chunk c-1 == assumed state
 //                   of chunk c for every boundary and merges the chunks' partial metrics.
@@ -39,10 +40,8 @@ struct ChunkScanArgs {
     int warm;
     uint2* pool; int pool_blocks; int* next; unsigned* alloc;
     int* seg_first; unsigned* seg_count; int2* seg_in; int2* seg_out; int* overflow;
-    const int4* repair;   // REPAIR launches: (individual, chunk, segment, symbol) per work item
-    const unsigned* n_repair_dev;   // REPAIR launches: length of the work list (device)
     const int32_t* n_chunks;
-    unsigned char* redo;  // REPAIR launches of the overlapped tail: individuals whose metrics must be recomputed
+    unsigned char* redo;  // repair pass of the overlapped tail: individuals whose metrics must be recomputed
 };
 
 __device__ __forceinline__ int64_t chunk_begin(int64_t N, int c, int K) {
@@ -54,7 +53,7 @@ __device__ __forceinline__ int64_t chunk_begin(int64_t N, int c, int K) {
 // REPAIR = true : re-scan of chunks whose assumed state was wrong, started AT T_c from the now known
 //                 true state (end state of the preceding chunk); one work item per listed chunk.
 template <bool VEC16, bool REPAIR>
-__device__ __forceinline__ void chunk_scan_item(const ChunkScanArgs& A, const b200bt_chunk_item item, const int sym, WarpShared* ws) {
+__device__ __forceinline__ bool chunk_scan_item(const ChunkScanArgs& A, const b200bt_chunk_item item, const int sym, WarpShared* ws) {
     const int lane = threadIdx.x & 31;
     const b200bt_individual iv = A.indiv[item.individual];
     if (lane == 0) {
@@ -253,29 +252,84 @@ __device__ __forceinline__ void chunk_scan_item(const ChunkScanArgs& A, const b2
     while (m.qhead != qtail) flush((int)min(32u, m.qhead - qtail));
     if (lane == 0) A.seg_count[seg] = dead ? 0xffffffffu : m.qhead;
     __syncwarp();
+    return spliced;      // REPAIR: the chunk's recorded end state stands
 }
 
-template <bool VEC16, bool REPAIR>
+template <bool VEC16>
 __global__ void __launch_bounds__(SW_WARPS * 32, 3)
 chunk_scan_kernel(const ChunkScanArgs A) {   // by value, not __grid_constant__ (see sweep.cu)
     extern __shared__ __align__(16) unsigned char s_raw[];
     WarpShared* ws = reinterpret_cast<WarpShared*>(s_raw) + (threadIdx.x >> 5);
-    if (REPAIR) {
-        // the work list and its length live on the device (written by chunk_verify_kernel of the same round): the grid has
-        // a fixed size and strides over the list, so the host never reads the count back
-        const int n = (int)*A.n_repair_dev;
-        for (int it = (int)blockIdx.x * SW_WARPS + (threadIdx.x >> 5); it < n; it += (int)gridDim.x * SW_WARPS) {
-            const int4 r = A.repair[it];
-            b200bt_chunk_item item;
-            item.individual = r.x; item.chunk = r.y; item.segment = r.z; item.n_chunks = A.n_chunks[r.x];
-            if (A.redo && (threadIdx.x & 31) == 0) A.redo[r.x] = 1;
-            chunk_scan_item<VEC16, true>(A, item, r.w, ws);
+    const int sym = (int)(blockIdx.x % (unsigned)A.S);
+    const int it = (int)(blockIdx.x / (unsigned)A.S) * SW_WARPS + (threadIdx.x >> 5);
+    if (it >= A.n_items) return;
+    chunk_scan_item<VEC16, false>(A, A.items[it], sym, ws);
+}
+
+// Verification and repair.  Two kernels share chunk_scan_item<REPAIR> (re-scan from the true state until the trajectory
+// meets the recorded one, then splice the recorded chain on); neither needs a work list or anything read by the host.
+//
+// chunk_repair_kernel (critical path): one warp per (chunk, symbol), handed out by a counter.  The warp compares its chunk's
+// assumed start state with the predecessor's recorded end state and re-scans on a mismatch.  All wrong chunks of a lane are
+// repaired CONCURRENTLY, each trusting its predecessor's recorded end state -- which stands whenever the predecessor's own
+// re-scan finds its way back to the recorded trajectory, i.e. almost always.  (A predecessor that is being rewritten at
+// the same moment is a benign race on an aligned 8-byte word: whichever value is read becomes the chunk's published start
+// state, and the boundary is checked again below and in lane_combine_kernel.)
+template <bool VEC16>
+__global__ void __launch_bounds__(SW_WARPS * 32, 3)
+chunk_repair_kernel(const ChunkScanArgs A, unsigned* __restrict__ work) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    WarpShared* ws = reinterpret_cast<WarpShared*>(s_raw) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int64_t total = (int64_t)A.n_items * A.S;
+    for (;;) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(work, 1u);
+        t = __shfl_sync(FULL, t, 0);
+        if ((int64_t)t >= total) break;
+        const int it = (int)(t / (unsigned)A.S), sym = (int)(t - (unsigned)it * (unsigned)A.S);
+        const b200bt_chunk_item item = A.items[it];
+        if (item.chunk == 0) continue;
+        const int seg = sym * A.n_seg + item.segment;
+        const int2 a = A.seg_in[seg], z = A.seg_out[seg - 1];
+        if ((a.x != z.x || a.y != z.y) && A.seg_count[seg - 1] != 0xffffffffu) chunk_scan_item<VEC16, true>(A, item, sym, ws);
+    }
+}
+
+// lane_repair_kernel (beside the metrics kernels): one warp per (individual, symbol) lane walks the lane's boundaries in
+// time order and re-scans where a chunk does not follow from its predecessor, checking the next boundary against the end
+// state it has just produced -- so the lane is consistent when the warp leaves it, however many chunks in a row a re-scan
+// runs through without meeting its recorded trajectory (lanes that hold one position across many chunks).  After
+// chunk_repair_kernel only those cascades are left.  Individuals it touches are flagged in A.redo (metrics recomputed).
+template <bool VEC16>
+__global__ void __launch_bounds__(SW_WARPS * 32, 3)
+lane_repair_kernel(const ChunkScanArgs A, const int pop, const int32_t* __restrict__ seg_base, unsigned* __restrict__ work) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    WarpShared* ws = reinterpret_cast<WarpShared*>(s_raw) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int lanes = pop * A.S;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = (int)atomicAdd(work, 1u);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= lanes) break;
+        const int ind = t / A.S, sym = t - ind * A.S;
+        const int K = A.n_chunks[ind];
+        const int sb = seg_base[ind];
+        const int base = sym * A.n_seg + sb;
+        int2 prev = A.seg_out[base];
+        bool usable = A.seg_count[base] != 0xffffffffu;      // (a chunk that lost events to a full pool ends the walk: the lane is flagged later)
+        for (int c = 1; c < K && usable; ++c) {
+            const int2 a = A.seg_in[base + c];
+            if (a.x != prev.x || a.y != prev.y) {
+                b200bt_chunk_item item;
+                item.individual = ind; item.chunk = c; item.segment = sb + c; item.n_chunks = K;
+                if (A.redo && lane == 0) A.redo[ind] = 1;
+                chunk_scan_item<VEC16, true>(A, item, sym, ws);      // (ends with a __syncwarp: its stores are visible to the warp)
+            }
+            prev = A.seg_out[base + c];
+            usable = A.seg_count[base + c] != 0xffffffffu;
         }
-    } else {
-        const int sym = (int)(blockIdx.x % (unsigned)A.S);
-        const int it = (int)(blockIdx.x / (unsigned)A.S) * SW_WARPS + (threadIdx.x >> 5);
-        if (it >= A.n_items) return;
-        chunk_scan_item<VEC16, false>(A, A.items[it], sym, ws);
     }
 }
 
@@ -658,35 +712,6 @@ lane_scan_kernel(const LaneScanArgs A, const bool vec16) {   // by value, not __
         const int c = rest / A.S, sym = rest - c * A.S;
         lane_scan_item<ZONES>(A, vec16, wslot, sym, c, wtile, wzone, ls_full[warp], ls_mul, ls_src[warp]);
         __syncwarp();
-    }
-}
-
-// One thread per (individual, symbol): list every chunk whose assumed state differs from the end state
-// of its predecessor while that predecessor is itself consistent (so its end state is the truth).
-// `n_repair` points at this round's counter (zero on entry); `n_prev` at the previous round's (NULL for the first
-// round): when the previous round found nothing to repair every boundary is consistent and the round is a no-op --
-// all rounds are launched unconditionally, the host never reads a count back.
-__global__ void chunk_verify_kernel(int pop, int S, const int32_t* __restrict__ seg_base,
-                                    const int32_t* __restrict__ n_chunks, int n_seg, const unsigned* __restrict__ seg_count,
-                                    const int2* __restrict__ seg_in, const int2* __restrict__ seg_out,
-                                    int4* __restrict__ repair, unsigned* __restrict__ n_repair, const unsigned* __restrict__ n_prev) {
-    if (n_prev && *n_prev == 0u) return;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)pop * S) return;
-    const int ind = (int)(t / S), sym = (int)(t % S);
-    const int K = n_chunks[ind];
-    const int base = sym * n_seg + seg_base[ind];
-    bool prev_bad = false;
-    const bool all = n_prev == nullptr;
-    for (int c = 1; c < K; ++c) {
-        const int2 a = seg_in[base + c], z = seg_out[base + c - 1];
-        const bool bad = (a.x != z.x) || (a.y != z.y);
-        const bool usable = seg_count[base + c - 1] != 0xffffffffu;   // predecessor did not lose events to a full pool
-        // first round: every mismatching chunk at once -- a re-scan that finds its way back to the recorded trajectory keeps
-        // the chunk's recorded end state (splice in chunk_scan_item), so the successor's true start state is almost always
-        // the recorded one already; later rounds: only chunks whose predecessor is consistent (its end state is the truth)
-        if (bad && (all || !prev_bad) && usable) repair[atomicAdd(n_repair, 1u)] = make_int4(ind, c, seg_base[ind] + c, sym);
-        prev_bad = bad;
     }
 }
 
@@ -1097,7 +1122,7 @@ using namespace b200bt;
 
 namespace {
 
-constexpr int REPAIR_COUNTERS = 130;   // >= the largest max_repair_rounds (K <= 120) + 2, and 2 + REPAIR_COUNTERS a multiple of 4 (alignment)
+constexpr int REPAIR_COUNTERS = 130;   // work counters: [0] bounded repair pass, [1] overlapped pass, [last] the scan; 2 + REPAIR_COUNTERS a multiple of 4 (alignment)
 struct ChunkWorkspace {
     uint2* pool; int2* seg_in; int2* seg_out; int* seg_first; unsigned* seg_count; unsigned* alloc; int* overflow;
     unsigned* n_repair; int4* repair; int* next; ChunkPartial* partial; double* seg_sum; double* seg_max;
@@ -1106,7 +1131,7 @@ struct ChunkWorkspace {
 };
 
 // pool[pool_blocks][256] uint2 | seg_in[segs] int2 | seg_out[segs] int2 | seg_first[segs] | seg_count[segs] |
-// alloc, overflow, n_repair[REPAIR_COUNTERS] (one per round) | repair[segs] int4 | next[pool_blocks] | (16-byte aligned) partial[segs] (128 B) |
+// alloc, overflow, n_repair[REPAIR_COUNTERS] (work counters) | repair[segs] int4 (reserved) | next[pool_blocks] | (16-byte aligned) partial[segs] (128 B) |
 // seg_sum[segs] | seg_max[segs] | fix_items[n_seg] (16 B) | n_fix (16 B) | redo[pop]
 // (wide types first: the base must be 16-byte aligned)
 ChunkWorkspace carve(void* workspace, int pool_blocks, int64_t segs, int n_seg, int pop) {
@@ -1157,49 +1182,50 @@ int side_stream(SideStream** out) {
     return B200BT_OK;
 }
 
-// rounds on the critical path; later ones run beside the metrics kernels (B200BT_MAIN_REPAIR_ROUNDS overrides, for tuning)
+// the bounded repair pass on the critical path can be switched off (B200BT_MAIN_REPAIR=0: everything in the overlapped pass)
 int main_repair_rounds() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("B200BT_MAIN_REPAIR_ROUNDS");
-        v = e ? atoi(e) : 2;
+        const char* e = getenv("B200BT_MAIN_REPAIR");
+        v = e ? atoi(e) : 1;
     }
     return v;
 }
 
-// Everything after the speculative scan: verify -> repair rounds -> chunk-parallel metrics.
+// Everything after the speculative scan: verify + repair (lane_repair_kernel) -> chunk-parallel metrics.
 //
-// Almost all wrong chunks are fixed by the first two rounds; what remains is a handful of lanes whose
-// trajectories never merge (always in the market) and which are re-scanned chunk after chunk, one round per
-// chunk, by a single warp each.  Those rounds run on a second stream BESIDE the metrics kernels of all lanes;
-// the individuals they touch are flagged and only their metrics are recomputed afterwards.
+// chunk_repair_kernel on the critical path makes almost every lane consistent; what it leaves is a handful of lanes whose
+// trajectories do not meet the recorded ones inside a chunk (always in the market) and which have to be re-scanned chunk
+// after chunk by a single warp each.  That is lane_repair_kernel, on another stream BESIDE the metrics kernels of all
+// lanes; the individuals it touches are flagged and only their metrics are recomputed afterwards.
+// max_repair_rounds: 0 = no repair (every inconsistent lane takes the exact fallback), 1 = chunk_repair_kernel only, >= 2 = both.
 int finish_chunks(const ChunkScanArgs& A, const ChunkWorkspace& w, const b200bt_chunk_item* items, int n_items,
                   const int32_t* seg_base, int pop, int max_repair_rounds, const b200bt_sweep_config* cfg_host,
                   b200bt_lane_stats* stats, uint32_t* events, int64_t event_cap, unsigned char* lane_invalid,
                   int* overflow_host_or_null, cudaStream_t st) {
     const int S = A.S, n_seg = A.n_seg;
     const bool vec16 = (((uintptr_t)A.price | (uintptr_t)A.rsi) & 15) == 0 && A.ld_price % 4 == 0 && A.ld_rsi % 4 == 0;
-    auto kern_fix = vec16 ? chunk_scan_kernel<true, true> : chunk_scan_kernel<false, true>;
+    auto kern_fix = vec16 ? chunk_repair_kernel<true> : chunk_repair_kernel<false>;
+    auto kern_walk = vec16 ? lane_repair_kernel<true> : lane_repair_kernel<false>;
     const size_t smem = sizeof(WarpShared) * SW_WARPS;
     cudaError_t e = cudaFuncSetAttribute(kern_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: cudaFuncSetAttribute");
     const int64_t lanes = (int64_t)pop * S;
     const int64_t mblocks = (int64_t)((n_items + 3) / 4) * S;
     B200BT_REQUIRE(mblocks < (1ll << 31), B200BT_ELIMIT, "sweep_chunked: too many work items");
+    B200BT_REQUIRE(lanes < (1ll << 30), B200BT_ELIMIT, "sweep_chunked: too many lanes");
 
-    // One verify -> repair round on stream `rs`.  Nothing is read back: the verify kernel leaves the round's work list and
-    // its length on the device, the repair kernel (fixed grid) strides over it, and a round after a clean one is a no-op.
-    const unsigned repair_grid = 3u * 148u;
-    auto repair_round = [&](cudaStream_t rs, int round, unsigned char* redo) -> int {
-        chunk_verify_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, rs>>>(pop, S, seg_base, A.n_chunks, n_seg, w.seg_count,
-                                                                             w.seg_in, w.seg_out, w.repair, w.n_repair + round,
-                                                                             round ? w.n_repair + round - 1 : nullptr);
-        B200BT_LAUNCH_CHECK("chunk_verify launch");
+    // Both repair kernels run a persistent grid (3 CTAs per SM) whose warps take work from a counter (n_repair[0], [1]).
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned repair_grid = 3u * (unsigned)sms;
+    auto repair_pass = [&](cudaStream_t rs, int pass, unsigned char* redo) -> int {
         ChunkScanArgs R = A;
-        R.n_repair_dev = w.n_repair + round;
         R.redo = redo;
-        kern_fix<<<repair_grid, SW_WARPS * 32, smem, rs>>>(R);
-        B200BT_LAUNCH_CHECK("chunk_repair launch");
+        if (pass == 0) kern_fix<<<repair_grid, SW_WARPS * 32, smem, rs>>>(R, w.n_repair);
+        else kern_walk<<<repair_grid, SW_WARPS * 32, smem, rs>>>(R, pop, seg_base, w.n_repair + 1);
+        B200BT_LAUNCH_CHECK("repair launch");
         return B200BT_OK;
     };
     // (the fix-up pass reuses the full-size grid with a device-side item count: CTAs beyond it leave at once)
@@ -1214,14 +1240,10 @@ int finish_chunks(const ChunkScanArgs& A, const ChunkWorkspace& w, const b200bt_
         return B200BT_OK;
     };
 
-    // Rounds on the critical path, then the rest on a second stream BESIDE the metrics kernels of all lanes: what remains
-    // after two rounds is a handful of lanes whose trajectories never merge and which are re-scanned chunk after chunk by
-    // one warp each; the individuals those rounds touch are flagged and only their metrics are recomputed afterwards.
-    int rc = B200BT_OK, round = 0;
-    B200BT_REQUIRE(max_repair_rounds + 1 < REPAIR_COUNTERS, B200BT_ELIMIT, "sweep_chunked: at most %d repair rounds", REPAIR_COUNTERS - 2);
-    for (; round < max_repair_rounds && round < main_repair_rounds(); ++round)
-        if ((rc = repair_round(st, round, nullptr))) return rc;
-    const bool tail = round < max_repair_rounds;
+    int rc = B200BT_OK;
+    const bool main_pass = max_repair_rounds >= 1 && main_repair_rounds() != 0;
+    const bool tail = max_repair_rounds >= 2 || (max_repair_rounds >= 1 && !main_pass);
+    if (main_pass && (rc = repair_pass(st, 0, nullptr))) return rc;
     SideStream* side = nullptr;
     e = cudaMemsetAsync(w.n_fix, 0, 16 + ((pop + 15) & ~15), st);   // n_fix, redo-list length, flagged lanes + redo flags
     if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: memset");
@@ -1234,8 +1256,7 @@ int finish_chunks(const ChunkScanArgs& A, const ChunkWorkspace& w, const b200bt_
     if (tail) {
         e = cudaStreamWaitEvent(side->stream, side->fork, 0);
         if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: side wait");
-        for (; round < max_repair_rounds; ++round)
-            if ((rc = repair_round(side->stream, round, w.redo))) return rc;
+        if ((rc = repair_pass(side->stream, 1, w.redo))) return rc;
         e = cudaEventRecord(side->join, side->stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(st, side->join, 0);
         if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: join");
@@ -1315,9 +1336,9 @@ extern "C" int b200bt_sweep_chunked(const float* price, int64_t ld_price, const 
     A.indiv = indiv; A.items = items; A.n_items = n_items; A.n_seg = n_seg; A.warm = warm;
     A.pool = w.pool; A.pool_blocks = pool_blocks; A.next = w.next; A.alloc = w.alloc;
     A.seg_first = w.seg_first; A.seg_count = w.seg_count; A.seg_in = w.seg_in; A.seg_out = w.seg_out; A.overflow = w.overflow;
-    A.repair = w.repair; A.n_chunks = n_chunks; A.redo = nullptr;
+    A.n_chunks = n_chunks; A.redo = nullptr;
     const bool vec16 = (((uintptr_t)price | (uintptr_t)rsi) & 15) == 0 && ld_price % 4 == 0 && ld_rsi % 4 == 0;
-    auto kern = vec16 ? chunk_scan_kernel<true, false> : chunk_scan_kernel<false, false>;
+    auto kern = vec16 ? chunk_scan_kernel<true> : chunk_scan_kernel<false>;
     const size_t smem = sizeof(WarpShared) * SW_WARPS;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: cudaFuncSetAttribute");
@@ -1432,7 +1453,7 @@ extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const fl
     A.indiv = indiv; A.items = items; A.n_items = n_seg; A.n_seg = n_seg; A.warm = warm;
     A.pool = w.pool; A.pool_blocks = pool_blocks; A.next = w.next; A.alloc = w.alloc;
     A.seg_first = w.seg_first; A.seg_count = w.seg_count; A.seg_in = w.seg_in; A.seg_out = w.seg_out; A.overflow = w.overflow;
-    A.repair = w.repair; A.n_chunks = n_chunks; A.redo = nullptr;
+    A.n_chunks = n_chunks; A.redo = nullptr;
     return finish_chunks(A, w, items, n_seg, seg_base, pop, max_repair_rounds, cfg_host, stats, events, event_cap, lane_invalid,
                          overflow_host_or_null, st);
 }

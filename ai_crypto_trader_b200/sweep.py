@@ -409,8 +409,8 @@ class TilePlan:
         if chunks is None:
             chunks = self.chunks_for(pop, n_bars, n_symbols, device, warm, max_chunks, n_slots=len(self.slots))
         self.K = int(chunks)
-        # a lane that holds one position across many chunks needs one repair round per boundary
-        self.max_repair_rounds = int(max_repair_rounds) if max_repair_rounds is not None else min(self.K, 64)
+        # 0 = no repair, 1 = the bounded pass on the critical path, 2 = that and the unbounded pass beside the metrics
+        self.max_repair_rounds = int(max_repair_rounds) if max_repair_rounds is not None else 2
         self.n_seg = pop * self.K
         # every segment owns at least one block, and a repaired segment abandons its first chain
         self.pred_blocks = float(pred.sum()) * n_symbols / 256

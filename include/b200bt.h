@@ -269,9 +269,12 @@ int b200bt_sweep(const float* price, int64_t ld_price,
 
 /* Time-chunked form of b200bt_sweep (same results; csrc/sweep_chunked.cu).  Expensive lanes are split
  * into n_chunks time chunks scanned concurrently, each started `warm` bars early from the flat state;
- * the chunk-boundary states are verified; chunks whose assumed state was wrong are re-scanned from the
- * true state in up to max_repair_rounds rounds (each round synchronises the stream for a 4-byte count);
- * a lane that still has a mismatch (or lost events to a full pool) is flagged in lane_invalid[pop][S]
+ * the chunk-boundary states are verified lane by lane and a chunk whose assumed state was wrong is re-scanned from the
+ * true state until its trajectory meets the recorded one again (the rest of the recorded events is then kept).
+ * max_repair_rounds: 0 = no repair, 1 = one chunk-parallel pass (every wrong chunk re-scanned once, trusting its
+ * predecessor's recorded end state), >= 2 = that pass plus a lane-sequential one beside the metrics kernels that finishes
+ * the lanes whose re-scans run through chunk after chunk; nothing is read back.
+ * A lane that still has a mismatch (or lost events to a full pool) is flagged in lane_invalid[pop][S]
  * (stats of flagged lanes are NOT written: re-evaluate those individuals with b200bt_sweep, passing them
  * as `order`).  One work item per (individual, chunk); `segment` = seg_base[individual] + chunk.
  *  items      [n_items] device      seg_base, n_chunks  [pop] device int32      n_seg = sum of n_chunks
