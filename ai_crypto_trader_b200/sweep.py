@@ -379,7 +379,7 @@ class TilePlan:
 
     THREADS = int(os.environ.get("B200BT_LS_THREADS", 256))     # individuals per CTA (csrc/sweep_chunked.cu LS_THREADS)
     CTAS_PER_SM = int(os.environ.get("B200BT_LS_CTAS", 3))     # resident CTAs of lane_scan_kernel per SM (__launch_bounds__(256, 3))
-    WARM = 2048          # warm-up bars of a speculative chunk
+    WARM = 1536          # warm-up bars of a speculative chunk
 
     @classmethod
     def chunks_for(cls, pop: int, n_bars: int, n_symbols: int, device, warm: int = WARM, max_chunks: int = 64,
@@ -387,9 +387,10 @@ class TilePlan:
         """About 2.5 work items per resident warp slot (the scan is persistent: warps take (warp-slot, chunk, symbol) items
         from a counter, the most expensive first; more chunks balance better but every chunk pays its warm-up and its share of
         the per-chunk metrics overhead), chunks at least 3 warm-ups long.  Measured on configs[1] (3 CTAs/SM): a plateau of
-        7.4-7.45 ms for K = 26..30 and warm-ups of 1536..3072 bars; K = 34 7.7 ms, K = 24 7.6 ms.  A short warm-up is affordable
-        because a mis-speculated chunk is re-scanned only until it meets its recorded trajectory again (chunk_scan_item,
-        REPAIR): at 2048 bars ~10 % of the chunks start in the wrong state and take ~3500 bars each to come back."""
+        7.15-7.25 ms for K = 26..30 and warm-ups of 1024..3072 bars; K = 34 +0.3 ms, K = 24 +0.15 ms.  A short warm-up is
+        affordable because a mis-speculated chunk is re-scanned only until it meets its recorded trajectory again
+        (chunk_scan_item, REPAIR): at 2048 bars ~10 % of the chunks start in the wrong state and take ~3500 bars each to come
+        back (at 8192 bars: 2 % and ~7700 bars)."""
         kmax = max(1, min(max_chunks, n_bars // max(3 * warm, 2048)))
         slots = _sm_count(device) * cls.CTAS_PER_SM
         groups = -(-(n_slots if n_slots is not None else pop) // cls.THREADS) * n_symbols

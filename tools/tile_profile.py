@@ -8,7 +8,7 @@ from ai_crypto_trader_b200 import synth
 from ai_crypto_trader_b200.sweep import MarketData, PopulationSweep, decode_population
 S, N, POP = 10, 1_000_000, 1024
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-warm = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+warm = int(sys.argv[2]) if len(sys.argv) > 2 else 1536
 m = MarketData(synth.synth_ohlcv(S, N)); sw = PopulationSweep(m, mode="fused")
 pop = synth.random_population(POP, seed=42)
 indiv = torch.from_numpy(decode_population(pop, sw.period_row).view(np.uint8)).cuda()
