@@ -26,11 +26,23 @@ inline int cuda_status(cudaError_t e, const char* what) {
         }                                      \
     } while (0)
 
+// B200BT_TRACE_LAUNCHES=1 (debugging a stall): every launch is named on stderr and waited for, so the last name without a
+// "done" is the kernel that does not finish.
+inline bool trace_launches() {
+    static const bool v = getenv("B200BT_TRACE_LAUNCHES") != nullptr;
+    return v;
+}
+
 #define B200BT_LAUNCH_CHECK(what)                                       \
     do {                                                                \
         ::b200bt::g_launches.fetch_add(1, std::memory_order_relaxed);   \
         cudaError_t e__ = cudaGetLastError();                           \
         if (e__ != cudaSuccess) return ::b200bt::cuda_status(e__, what); \
+        if (::b200bt::trace_launches()) {                               \
+            fprintf(stderr, "[b200bt] %s ...", what); fflush(stderr);   \
+            e__ = cudaDeviceSynchronize();                              \
+            fprintf(stderr, " done (%d)\n", (int)e__); fflush(stderr);  \
+        }                                                               \
     } while (0)
 
 constexpr unsigned FULL = 0xffffffffu;

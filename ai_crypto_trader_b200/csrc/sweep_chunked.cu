@@ -398,6 +398,7 @@ struct LaneScanArgs {
     uint2* pool; int pool_blocks; int* next; unsigned* alloc;
     int* seg_first; unsigned* seg_count; int2* seg_in; int2* seg_out; int* overflow;
     unsigned* work;      // work-item counter of the persistent scan (zero at launch)
+    int* stalls;         // [0] tiles that did not arrive in time (their items go to the exact fallback), [1..8] the first one's details
 };
 
 __device__ __forceinline__ int sym_of_block(unsigned bx, int S) { return (int)(bx % (unsigned)S); }
@@ -443,10 +444,13 @@ static_assert(LS_ZONE == ZONE_BLOCK && LS_T == ZONE_TILE, "zone map layout (comm
 // and 18 % of the instructions computing cp.async addresses -- and the bytes moved per machine stay what they were,
 // because a CTA-wide tile staged P + 1 rows for 256 machines and a warp stages 3 for 32.
 // One work item: the 32 machines of warp-slot `wslot` (thread slots wslot * 32 ...) on symbol `sym`, chunk `c`.
+constexpr long long LS_WAIT_CYCLES = 40ll * 1000 * 1000;     // ~20 ms at 1.9 GHz; a tile normally lands within microseconds
+
+// -> false: a tile of this item did not arrive (see the wait below); the warp must not take another item
 template <bool ZONES>
-__device__ __forceinline__ void lane_scan_item(const LaneScanArgs& A, const bool vec16, const int wslot, const int sym, const int c,
+__device__ __forceinline__ bool lane_scan_item(const LaneScanArgs& A, const bool vec16, const int wslot, const int sym, const int c,
                                                float* const wtile, float2* const wzone, unsigned long long* const full,
-                                               float (*ls_mul)[LS_THREADS], const void* (*ls_src_w)[3]) {
+                                               float (*ls_mul)[LS_THREADS], const void* (*ls_src_w)[3], int& ring_stage, unsigned& ring_parity) {
     constexpr int ZB = LS_T / LS_ZONE;                  // zone blocks per tile
     constexpr int FG = LS_T / 4;                        // 4-bar groups per tile
     constexpr int ZR = ZB + FG;                         // float2 per staged row: coarse ranges, then fine ranges
@@ -467,14 +471,11 @@ __device__ __forceinline__ void lane_scan_item(const LaneScanArgs& A, const bool
         m[4 * LS_THREADS] = sc.hiS_c; m[5 * LS_THREADS] = sc.loS_c; m[6 * LS_THREADS] = sc.hiS_d; m[7 * LS_THREADS] = sc.loS_d;
     }
     __syncwarp();
-    if (lane == 0) {
-        // (re)arm the ring's barriers: every copy of the previous item has landed and been waited for
-#pragma unroll
-        for (int s = 0; s < LS_STAGES; ++s) { mbar_inval(&full[s]); mbar_init(&full[s], 1); }
-        mbar_fence_init();
-        fence_proxy_async();
-    }
-    __syncwarp();
+    // The ring's barriers are initialised ONCE per warp (lane_scan_kernel) and their phases roll on from item to item: every
+    // copy of the previous item has landed and been waited for, so the ring continues at (ring_stage, ring_parity).  (The
+    // first persistent form invalidated and re-initialised the barriers at every item; about once in 10^4 launches a tile
+    // then never completed -- a re-initialisation racing with the copy engine's last update of the barrier it had just
+    // completed is the suspected cause -- which is also why the wait below is bounded.)
 
     const int n = (int)A.N;
     const int T0 = (int)chunk_begin(A.N, c, A.K);       // first recorded bar (multiple of SW_GROUP, hence of LS_T)
@@ -487,7 +488,7 @@ __device__ __forceinline__ void lane_scan_item(const LaneScanArgs& A, const bool
 
     // the warp's distinct RSI rows: staged row 1 + j holds the j-th of them (in lane order of first use)
     const unsigned amask = __ballot_sync(FULL, active);
-    if (amask == 0u) return;                            // an empty warp (padding of the last CTA)
+    if (amask == 0u) return true;                       // an empty warp (padding of the last CTA)
     const unsigned peers = __match_any_sync(FULL, active ? iv.rsi_row : -1 - lane);
     const int leader = __ffs(peers) - 1;
     const unsigned heads = __ballot_sync(FULL, active && lane == leader);
@@ -500,7 +501,7 @@ __device__ __forceinline__ void lane_scan_item(const LaneScanArgs& A, const bool
             A.seg_out[seg] = make_int2(0, -1);
             A.seg_count[seg] = 0xffffffffu;
         }
-        return;
+        return true;
     }
     // lane L <= n_rsi issues the copies of staged row L (0 = price)
     const unsigned src_lane = __fns(heads, 0, lane);                    // lane of the (lane)-th head (1-based), or ~0u
@@ -552,7 +553,7 @@ __device__ __forceinline__ void lane_scan_item(const LaneScanArgs& A, const bool
             if (lane == 0) mbar_arrive(&full[stage]);     // (release: the stores above are visible after the wait)
         }
     };
-    for (int it = 0; it < LS_STAGES && it < n_tiles; ++it) issue(tl_begin + it, it);
+    for (int it = 0; it < LS_STAGES && it < n_tiles; ++it) issue(tl_begin + it, (ring_stage + it) % LS_STAGES);
 
     // machine state (per thread)
     int pos = 0, entry_bar = 0;
@@ -608,10 +609,25 @@ __device__ __forceinline__ void lane_scan_item(const LaneScanArgs& A, const bool
         }
     };
 
-    int stage = 0;
-    unsigned parity = 0;
+    int stage = ring_stage;
+    unsigned parity = ring_parity;
     for (int it = 0; it < n_tiles; ++it) {
-        mbar_wait(&full[stage], parity);
+        // A copy that never completes must not hang the GPU: the wait is bounded.  On a timeout the item is given up -- its
+        // chunks are marked as having lost their events, so the repair pass re-scans them (or the lane takes the exact
+        // fallback) -- and the warp retires without touching its ring again (copies may still be in flight into it); the
+        // other warps take the remaining items.
+        if (__any_sync(FULL, !mbar_wait_bounded(&full[stage], parity, LS_WAIT_CYCLES))) {
+            if (active) {
+                A.seg_in[seg] = make_int2(0, -1);
+                A.seg_out[seg] = make_int2(0, -1);
+                A.seg_count[seg] = 0xffffffffu;
+            }
+            if (lane == 0 && A.stalls && atomicAdd(A.stalls, 1) == 0) {
+                A.stalls[1] = (int)blockIdx.x; A.stalls[2] = (int)(threadIdx.x >> 5); A.stalls[3] = wslot * 65536 + sym * 256 + c;
+                A.stalls[4] = it; A.stalls[5] = n_tiles; A.stalls[6] = stage * 2 + (int)parity; A.stalls[7] = tl_begin; A.stalls[8] = n_rsi;
+            }
+            return false;
+        }
         const int t0 = (tl_begin + it) * LS_T;
         if (active) {
             if (t0 == T0) { A.seg_in[seg] = make_int2(pos, pos != 0 ? entry_bar : -1); rec = true; }
@@ -659,7 +675,9 @@ __device__ __forceinline__ void lane_scan_item(const LaneScanArgs& A, const bool
         if (it + LS_STAGES < n_tiles) issue(tl_begin + it + LS_STAGES, stage);
         if (++stage == LS_STAGES) { stage = 0; parity ^= 1u; }
     }
-    if (!active) return;
+    ring_stage = stage;
+    ring_parity = parity;
+    if (!active) return true;
     A.seg_out[seg] = make_int2(pos, pos != 0 ? entry_bar : -1);
     if (c == A.K - 1 && pos != 0)   // force-close at the last bar (:849-876)
     {
@@ -678,6 +696,7 @@ __device__ __forceinline__ void lane_scan_item(const LaneScanArgs& A, const bool
         ++count;
     }
     A.seg_count[seg] = dead ? 0xffffffffu : count;
+    return true;
 }
 
 // Persistent form: the grid is one resident set of CTAs; every WARP takes work items -- (warp-slot, chunk, symbol), the
@@ -699,8 +718,12 @@ lane_scan_kernel(const LaneScanArgs A, const bool vec16) {   // by value, not __
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < LS_STAGES; ++s) mbar_init(&ls_full[warp][s], 1);
+        mbar_fence_init();
+        fence_proxy_async();
     }
     __syncwarp();
+    int ring_stage = 0;            // the warp's position in its tile ring, carried from item to item
+    unsigned ring_parity = 0;
     const int per_slot = A.K * A.S;
     const int n_items = (A.n_slots / 32) * per_slot;
     for (;;) {
@@ -710,8 +733,9 @@ lane_scan_kernel(const LaneScanArgs A, const bool vec16) {   // by value, not __
         if (item >= n_items) break;
         const int wslot = item / per_slot, rest = item - wslot * per_slot;
         const int c = rest / A.S, sym = rest - c * A.S;
-        lane_scan_item<ZONES>(A, vec16, wslot, sym, c, wtile, wzone, ls_full[warp], ls_mul, ls_src[warp]);
+        const bool ok = lane_scan_item<ZONES>(A, vec16, wslot, sym, c, wtile, wzone, ls_full[warp], ls_mul, ls_src[warp], ring_stage, ring_parity);
         __syncwarp();
+        if (!ok) break;
     }
 }
 
@@ -1277,12 +1301,19 @@ int finish_chunks(const ChunkScanArgs& A, const ChunkWorkspace& w, const b200bt_
                            events, event_cap, st)))
         return rc;
     if (overflow_host_or_null) {
-        // [0] = the event pool overflowed, [1] = lanes that went through the fallback, [2] = pool blocks handed out (read by
-        // the host after its next sync)
+        // [0] = the event pool overflowed, [1] = lanes that went through the fallback, [2] = pool blocks handed out, [3] = tiles
+        // of the thread-per-lane scan that did not arrive in time (read by the host after its next sync)
         e = cudaMemcpyAsync(overflow_host_or_null, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(overflow_host_or_null + 1, w.n_fix + 2, sizeof(int), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(overflow_host_or_null + 2, w.alloc, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(overflow_host_or_null + 3, w.n_repair + 64, sizeof(int), cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return cuda_status(e, "sweep_chunked: overflow readback");
+    }
+    if (trace_launches()) {
+        int d[9];
+        if (cudaMemcpy(d, w.n_repair + 64, sizeof(d), cudaMemcpyDeviceToHost) == cudaSuccess && d[0])
+            fprintf(stderr, "[b200bt] lane_scan: %d tile(s) timed out; first: block %d warp %d item(wslot,sym,c) %d,%d,%d tile %d of %d stage %d parity %d tl_begin %d rows %d\n",
+                    d[0], d[1], d[2], d[3] >> 16, (d[3] >> 8) & 255, d[3] & 255, d[4], d[5], d[6] >> 1, d[6] & 1, d[7], d[8]);
     }
     return B200BT_OK;
 }
@@ -1435,6 +1466,7 @@ extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const fl
     const int64_t n_items = (int64_t)(n_slots / 32) * K * S;
     B200BT_REQUIRE(n_items < (1ll << 30), B200BT_ELIMIT, "sweep_tiled: too many work items");
     L.work = w.n_repair + REPAIR_COUNTERS - 1;      // (a counter no repair round uses; zeroed with the rest above)
+    L.stalls = reinterpret_cast<int*>(w.n_repair + 64);   // (counters 64..72, zeroed with the rest)
     // persistent grid: one resident set of CTAs (warps take work items from the counter), no more CTAs than items need
     int dev = 0, sms = 0, per_sm = 0;
     e = cudaGetDevice(&dev);

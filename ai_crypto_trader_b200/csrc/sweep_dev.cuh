@@ -411,6 +411,15 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// bounded form: false when the phase has not completed `cycles` SM clocks after the first failed poll (the caller gives the
+// work up and has it redone by the exact fallback instead of spinning for ever on a copy that does not arrive)
+__device__ __forceinline__ bool mbar_wait_bounded(unsigned long long* bar, unsigned parity, long long cycles) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity))
+        if (clock64() - t0 > cycles) return false;
+    return true;
+}
 // global -> shared bulk copy (TMA engine, 16-byte aligned, size a multiple of 16), completion counted on `bar`
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -310,7 +310,7 @@ _FLAG_SLOTS = 256
 
 def _pinned_flags() -> torch.Tensor:
     """Pinned int32 [256][4]: per plan (slice) of a sweep, [0] = the event pool overflowed, [1] = lanes that went through
-    the exact fallback, [2] = pool blocks handed out.  The kernels' flags are copied here asynchronously; the host looks at them only after a stream
+    the exact fallback, [2] = pool blocks handed out, [3] = scan tiles that timed out.  The kernels' flags are copied here asynchronously; the host looks at them only after a stream
     synchronisation it does anyway (page-locking memory is slow: one table shared by every plan)."""
     global _PINNED_FLAGS
     if _PINNED_FLAGS is None:
@@ -675,6 +675,12 @@ class PopulationSweep:
     def last_invalid_lanes(self) -> int:
         """(individual, symbol) lanes of the last evaluation that went through the exact fallback."""
         return int(sum(int(f[1]) for f in self._sync_flags()))
+
+    @property
+    def last_scan_stalls(self) -> int:
+        """Tiles of the last thread-per-lane scan whose bulk copy did not complete in time (their chunks were re-scanned by the
+        repair pass or their lanes re-run by the exact fallback; 0 in normal operation)."""
+        return int(sum(int(f[3]) for f in self._sync_flags()))
 
     @property
     def last_pool_overflow(self) -> bool:

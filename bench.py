@@ -53,6 +53,18 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+_T0 = time.perf_counter()
+
+
+_LAST_PHASE = [""]
+
+
+def _phase(msg: str) -> None:
+    """Progress marker on stderr (the JSON line is the only thing on stdout): where a run is, should it ever stall."""
+    _LAST_PHASE[0] = msg
+    print(f"[bench +{time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -270,6 +282,24 @@ def cpu_baseline_inline():
     return py
 
 
+def cpu_baseline_child(timeout_s: float = 420.0, attempts: int = 2):
+    """cpu_baseline_inline() in a child interpreter (`bench.py --cpu-baseline-only` prints its dict as one JSON line)."""
+    why = "not run"
+    for attempt in range(attempts):
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-only"], stdout=subprocess.PIPE,
+                               stderr=subprocess.PIPE, text=True, timeout=timeout_s, start_new_session=True)
+            if r.returncode == 0:
+                return json.loads(r.stdout.strip().splitlines()[-1])
+            why = f"exit code {r.returncode}: {r.stderr.strip()[-300:]}"
+        except subprocess.TimeoutExpired:
+            why = f"no result within {timeout_s:.0f} s"
+        except Exception as e:
+            why = f"{type(e).__name__}: {e}"
+        _phase(f"cpu_baseline attempt {attempt + 1} failed: {why}")
+    return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "", "unavailable": why}
+
+
 def configs0_frame():
     """10 000 synthetic 1-minute bars ending in a sell-off (the constant technical signal then trades, as in the parity
     fixtures tests/golden/bt_reference.*)."""
@@ -315,7 +345,7 @@ def parity_spot_check(sweep, my_pop, ohlcv, minute0, lanes=64):
             "what": "n_records + trade_hash bit-exact, score rel 1e-9 vs oracle/sim_oracle.c on the timed population (rank 0 shard)"}
 
 
-def run_extras(args, world, rank, dev, sweep, population, pop_local, timed_sweeps, barrier, evals_per_step_global):
+def run_extras(args, world, rank, dev, sweep, population, pop_local, timed_sweeps, barrier, evals_per_step_global, out=None):
     """Keys beside the headline, every rank taking part (same collectives in the same order):
       evolved_population_value  configs[1] throughput on the generation-3 population of a GA run (the GA drives the
                                 trade-record count, the sweep's cost driver, up)
@@ -331,7 +361,7 @@ def run_extras(args, world, rank, dev, sweep, population, pop_local, timed_sweep
     from ai_crypto_trader_b200.genetic_algorithm import DeviceGeneticAlgorithm, GeneticAlgorithm
     from ai_crypto_trader_b200.monte_carlo import PathEngine, risk_statistics
     from ai_crypto_trader_b200.sweep import MarketData, PopulationSweep, decode_population
-    out = {}
+    out = {} if out is None else out          # (the caller's dict: legs that finished survive a later one that stalls)
 
     def wall(fn):
         """fn() between two barriers; seconds, max over ranks."""
@@ -345,6 +375,7 @@ def run_extras(args, world, rank, dev, sweep, population, pop_local, timed_sweep
         return float(t.item()), r
 
     # ---- configs[1] on an evolved population ---------------------------------------------------------
+    _phase("extras: evolved population (configs[1], generation 3)")
     fit = ShardedFitness(sweep.evaluate, device=dev)
     ga = GeneticAlgorithm(synth.param_ranges(), fit, population_size=len(population), generations=3, random_seed=42)
     ga.run(seeded_individuals=population)              # reference operators (host), fitness = the sharded sweep
@@ -359,6 +390,7 @@ def run_extras(args, world, rank, dev, sweep, population, pop_local, timed_sweep
         "note": "same workload and timing as `value`, population = generation 3 of GeneticAlgorithm(seed 42) started from the timed random population"}
 
     # ---- configs[4]: one GA generation at population 10 000 x 50 symbols x 1M bars --------------------
+    _phase("extras: configs[4] generation")
     S5, POP5, GENS = 50, 10_000, 3
     close = np.stack([synth.synth_symbol(s, args.bars)["close"] for s in range(S5)])
     market5 = MarketData.from_close(torch.from_numpy(close).to(dev))
@@ -392,6 +424,7 @@ def run_extras(args, world, rank, dev, sweep, population, pop_local, timed_sweep
     torch.cuda.empty_cache()
 
     # ---- configs[3]: the evolution loop, 100 generations, population 4096, 20 symbols, RSI on 1m / 5m / 15m -------------
+    _phase("extras: configs[3] evolution loop")
     import importlib.util
     spec = importlib.util.spec_from_file_location("evolution_c4", str(ROOT / "tools" / "evolution_c4.py"))
     c4mod = importlib.util.module_from_spec(spec)
@@ -405,6 +438,7 @@ def run_extras(args, world, rank, dev, sweep, population, pop_local, timed_sweep
     torch.cuda.empty_cache()
 
     # ---- configs[2]: Monte-Carlo risk, 1M GBM paths x 10 000 steps, VaR + max drawdown ------------------
+    _phase("extras: configs[2] Monte-Carlo")
     n_paths, steps = 1_000_000, 10_000
     eng = PathEngine()
     ret = np.random.default_rng(7).normal(5e-4, 0.02, 60)
@@ -436,16 +470,43 @@ def main():
     ap.add_argument("--bars", type=int, default=N_BARS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-extras", action="store_true", help="only the headline (configs[1]) legs")
+    ap.add_argument("--cpu-baseline-only", action="store_true", help="(internal) print the cpu_baseline dict and exit")
+    ap.add_argument("--reference-child", action="store_true", help="(internal) the worker of --impl reference")
     ap.add_argument("--mode", default="auto", choices=["auto", "fused", "chunked", "tiled"], help="sweep kernel path (auto = product default)")
     args = ap.parse_args()
+    if args.cpu_baseline_only:
+        print(json.dumps(cpu_baseline_inline()), flush=True)
+        return
     if args.impl == "reference":
-        run_reference_arm(args)
+        if args.reference_child or int(os.environ.get("RANK", "0")) != 0:
+            run_reference_arm(args)
+            return
+        # the pool of forked workers runs in a child interpreter with a deadline (see cpu_baseline_child)
+        why = "not run"
+        for attempt in range(2):
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--reference-child", "--gpus", str(args.gpus),
+                                    "--steps", str(args.steps), "--warmup", str(args.warmup)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                                   text=True, timeout=900, start_new_session=True, env=dict(os.environ, RANK="0"))
+                if r.returncode == 0 and r.stdout.strip():
+                    print(r.stdout.strip().splitlines()[-1], flush=True)
+                    return
+                why = f"exit code {r.returncode}: {r.stderr.strip()[-300:]}"
+            except subprocess.TimeoutExpired:
+                why = "no result within 900 s"
+            _phase(f"reference arm attempt {attempt + 1} failed: {why}")
+        print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
         return
     assert args.warmup >= 3 or os.environ.get("B200BT_ALLOW_SHORT_WARMUP"), "timing rules: warm-up >= 3"
-    # CPU baseline first (rank 0, N=1 only): fork-based worker pool before CUDA is initialised
+    # A stalled run must end with a traceback, not with the caller's patience: every thread's stack goes to stderr.
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("B200BT_BENCH_WATCHDOG_S", 1500)), exit=True)
+    # CPU baseline first (rank 0, N=1 only), in a child process of its own (a pool of forked workers; no CUDA in it) with a
+    # deadline: a CPU leg that stalls costs the run its cpu_baseline key, not its result
     cpu_baseline = None
     if int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_baseline_inline()
+        _phase("cpu_baseline (child process)")
+        cpu_baseline = cpu_baseline_child()
 
     import numpy as np
     import torch
@@ -541,6 +602,7 @@ def main():
         return float(t.item()), ms_k, n_launch, (sampler.stop(t_wall0, t_wall1) if sampler else None)
 
     # ---- device-resident leg ------------------------------------------------
+    _phase("timed sweeps (device-resident)")
     ms_total, ms_kernel, launches, clocks = timed_sweeps(indiv_dev, order_dev, plan, sample_clocks=True)
     scan_ms_live = timed_sweeps.scan_ms
     evals_per_step_global = pop_global * S * N
@@ -549,6 +611,7 @@ def main():
 
     # ---- parity spot check of the timed population (rank 0): 64 lanes against the C oracle ----
     parity = None
+    _phase("parity spot check")
     if rank == 0:
         parity = parity_spot_check(sweep, my_pop, ohlcv_host.numpy(), market.minute0, lanes=64)
 
@@ -565,6 +628,7 @@ def main():
         return f, sw.h2d_bytes + mk.h2d_bytes, sw.d2h_bytes    # (the sweep reads close prices: the other OHLCV fields stay on the host)
 
     e2e_steps = max(3, min(args.steps, 5))
+    _phase("end-to-end leg")
     f_e2e, h2d, d2h = e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -582,9 +646,27 @@ def main():
                        fit_random.cpu().numpy(), rtol=1e-12, atol=0, equal_nan=True)
 
     # ---- the rest of the metric: evolved population, configs[4] generation wall time, configs[2] Monte-Carlo ----
-    extras = {}
+    # (under a deadline: the headline above is complete at this point, and a leg beside it that stalls -- on any rank: the
+    # legs are collective -- must not take the line with it; the thread is abandoned and the process leaves through os._exit)
+    extras, abandoned = {}, False
     if not args.skip_extras:
-        extras = run_extras(args, world, rank, dev, sweep, population, pop_local, timed_sweeps, barrier, evals_per_step_global)
+        box = {}
+
+        def _extras():
+            torch.cuda.set_device(local_rank)
+            run_extras(args, world, rank, dev, sweep, population, pop_local, timed_sweeps, barrier, evals_per_step_global, out=box.setdefault("partial", {}))
+            box["out"] = box["partial"]
+        th = threading.Thread(target=_extras, daemon=True)
+        th.start()
+        th.join(float(os.environ.get("B200BT_BENCH_EXTRAS_S", 600)))
+        if th.is_alive() or "out" not in box:
+            abandoned = True
+            extras = dict(box.get("partial", {}))
+            extras["extras_unavailable"] = f"the legs beside the headline did not finish within their deadline (last phase: {_LAST_PHASE[0]})"
+            _phase("extras abandoned")
+            faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        else:
+            extras = box["out"]
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
@@ -635,7 +717,7 @@ def main():
         }
         line.update(extras)
         if cpu_baseline is not None:
-            if "configs0_backtest" in cpu_baseline:
+            if "configs0_backtest" in cpu_baseline and not abandoned:
                 # the same configs[0] backtest through the GPU path (indicators, backtest_ref kernel, stats dict)
                 import asyncio
                 from ai_crypto_trader_b200.backtesting import StrategyTester
@@ -648,6 +730,11 @@ def main():
                 cpu_baseline["configs0_backtest"]["gpu_trades"] = int(st0["total_trades"])
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
+    _phase("done")
+    faulthandler.cancel_dump_traceback_later()
+    if abandoned:
+        sys.stdout.flush()
+        os._exit(0)          # (a thread is still inside a CUDA / NCCL call)
     if world > 1:
         dist.destroy_process_group()
 
