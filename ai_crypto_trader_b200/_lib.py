@@ -126,6 +126,7 @@ _SIGNATURES = {
                                        _vp, _i64, C.POINTER(SweepConfig), _vp, _vp, _i64, _vp, _vp, _vp]),
     "b200bt_sweep_tiled_workspace_bytes": (C.c_int64, [_i, _i, _i, _i]),
     "b200bt_sweep_scan_timing": (C.c_int, [_vp, _vp]),
+    "b200bt_sweep_scan_wait_cycles": (C.c_int, [_i64]),
     "b200bt_zone_map_floats": (C.c_int64, [_i, _i, _i64]),
     "b200bt_zone_map": (C.c_int, [_vp, _i64, _vp, _i64, _i, _i, _i64, _vp, _vp]),
     "b200bt_sweep_tiled": (C.c_int, [_vp, _i64, _vp, _i64, _i, _i, _i64, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i,

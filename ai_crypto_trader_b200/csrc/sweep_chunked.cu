@@ -399,6 +399,7 @@ struct LaneScanArgs {
     int* seg_first; unsigned* seg_count; int2* seg_in; int2* seg_out; int* overflow;
     unsigned* work;      // work-item counter of the persistent scan (zero at launch)
     int* stalls;         // [0] tiles that did not arrive in time (their items go to the exact fallback), [1..8] the first one's details
+    long long wait_cycles;   // bound of a tile wait in SM clocks (LS_WAIT_CYCLES; b200bt_sweep_scan_wait_cycles overrides, for tests)
 };
 
 __device__ __forceinline__ int sym_of_block(unsigned bx, int S) { return (int)(bx % (unsigned)S); }
@@ -445,6 +446,18 @@ static_assert(LS_ZONE == ZONE_BLOCK && LS_T == ZONE_TILE, "zone map layout (comm
 // because a CTA-wide tile staged P + 1 rows for 256 machines and a warp stages 3 for 32.
 // One work item: the 32 machines of warp-slot `wslot` (thread slots wslot * 32 ...) on symbol `sym`, chunk `c`.
 constexpr long long LS_WAIT_CYCLES = 40ll * 1000 * 1000;     // ~20 ms at 1.9 GHz; a tile normally lands within microseconds
+
+// the 32 machines of (warp-slot, symbol, chunk) are not scanned: their chunk is marked as having lost its events, which sends
+// the chunk to the repair pass or the lane to the exact fallback
+__device__ __forceinline__ void lane_scan_give_up(const LaneScanArgs& A, const int wslot, const int sym, const int c) {
+    const int k = wslot * 32 + (int)(threadIdx.x & 31);
+    const int slot = k < A.n_slots ? (A.slots ? A.slots[k] : (k < A.pop ? k : -1)) : -1;
+    if (slot < 0) return;
+    const int seg = sym * (A.pop * A.K) + slot * A.K + c;
+    A.seg_in[seg] = make_int2(0, -1);
+    A.seg_out[seg] = make_int2(0, -1);
+    A.seg_count[seg] = 0xffffffffu;
+}
 
 // -> false: a tile of this item did not arrive (see the wait below); the warp must not take another item
 template <bool ZONES>
@@ -614,14 +627,13 @@ __device__ __forceinline__ bool lane_scan_item(const LaneScanArgs& A, const bool
     for (int it = 0; it < n_tiles; ++it) {
         // A copy that never completes must not hang the GPU: the wait is bounded.  On a timeout the item is given up -- its
         // chunks are marked as having lost their events, so the repair pass re-scans them (or the lane takes the exact
-        // fallback) -- and the warp retires without touching its ring again (copies may still be in flight into it); the
-        // other warps take the remaining items.
-        if (__any_sync(FULL, !mbar_wait_bounded(&full[stage], parity, LS_WAIT_CYCLES))) {
-            if (active) {
-                A.seg_in[seg] = make_int2(0, -1);
-                A.seg_out[seg] = make_int2(0, -1);
-                A.seg_count[seg] = 0xffffffffu;
-            }
+        // fallback) -- and the warp never touches its ring again (copies may still be in flight into it): it goes on taking
+        // items only to give them up as well (lane_scan_kernel), while the other warps scan theirs.
+        // (wait_cycles < 0 is the test hook: the warp gives up at its (-wait_cycles)-th tile as if the tile had not arrived)
+        const bool lost = A.wait_cycles < 0 ? (it + 1 == (int)-A.wait_cycles || !mbar_wait_bounded(&full[stage], parity, LS_WAIT_CYCLES))
+                                            : !mbar_wait_bounded(&full[stage], parity, A.wait_cycles);
+        if (__any_sync(FULL, lost)) {
+            lane_scan_give_up(A, wslot, sym, c);
             if (lane == 0 && A.stalls && atomicAdd(A.stalls, 1) == 0) {
                 A.stalls[1] = (int)blockIdx.x; A.stalls[2] = (int)(threadIdx.x >> 5); A.stalls[3] = wslot * 65536 + sym * 256 + c;
                 A.stalls[4] = it; A.stalls[5] = n_tiles; A.stalls[6] = stage * 2 + (int)parity; A.stalls[7] = tl_begin; A.stalls[8] = n_rsi;
@@ -724,6 +736,7 @@ lane_scan_kernel(const LaneScanArgs A, const bool vec16) {   // by value, not __
     __syncwarp();
     int ring_stage = 0;            // the warp's position in its tile ring, carried from item to item
     unsigned ring_parity = 0;
+    bool retired = false;          // a tile of this warp's ring did not arrive: the ring is not used again
     const int per_slot = A.K * A.S;
     const int n_items = (A.n_slots / 32) * per_slot;
     for (;;) {
@@ -733,9 +746,9 @@ lane_scan_kernel(const LaneScanArgs A, const bool vec16) {   // by value, not __
         if (item >= n_items) break;
         const int wslot = item / per_slot, rest = item - wslot * per_slot;
         const int c = rest / A.S, sym = rest - c * A.S;
-        const bool ok = lane_scan_item<ZONES>(A, vec16, wslot, sym, c, wtile, wzone, ls_full[warp], ls_mul, ls_src[warp], ring_stage, ring_parity);
+        if (retired) { lane_scan_give_up(A, wslot, sym, c); continue; }     // (every item is either scanned or marked)
+        retired = !lane_scan_item<ZONES>(A, vec16, wslot, sym, c, wtile, wzone, ls_full[warp], ls_mul, ls_src[warp], ring_stage, ring_parity);
         __syncwarp();
-        if (!ok) break;
     }
 }
 
@@ -1411,6 +1424,11 @@ extern "C" int64_t b200bt_sweep_tiled_workspace_bytes(int pool_blocks, int S, in
 
 // measurement hook: a pair of caller-owned CUDA events recorded around the scan kernel of the next b200bt_sweep_tiled calls
 static cudaEvent_t g_scan_ev[2] = {nullptr, nullptr};
+static long long g_wait_cycles = 0;
+extern "C" int b200bt_sweep_scan_wait_cycles(int64_t cycles) {
+    g_wait_cycles = cycles;
+    return B200BT_OK;
+}
 extern "C" int b200bt_sweep_scan_timing(void* start_event, void* stop_event) {
     g_scan_ev[0] = (cudaEvent_t)start_event;
     g_scan_ev[1] = (cudaEvent_t)stop_event;
@@ -1467,6 +1485,7 @@ extern "C" int b200bt_sweep_tiled(const float* price, int64_t ld_price, const fl
     B200BT_REQUIRE(n_items < (1ll << 30), B200BT_ELIMIT, "sweep_tiled: too many work items");
     L.work = w.n_repair + REPAIR_COUNTERS - 1;      // (a counter no repair round uses; zeroed with the rest above)
     L.stalls = reinterpret_cast<int*>(w.n_repair + 64);   // (counters 64..72, zeroed with the rest)
+    L.wait_cycles = g_wait_cycles != 0 ? g_wait_cycles : LS_WAIT_CYCLES;
     // persistent grid: one resident set of CTAs (warps take work items from the counter), no more CTAs than items need
     int dev = 0, sms = 0, per_sm = 0;
     e = cudaGetDevice(&dev);

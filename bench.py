@@ -37,8 +37,8 @@ BYTES_PER_EVAL = 8  # price 4 B + RSI 4 B per (individual, symbol, 
 # the committed `ncu --set full` capture named in "source"; "scan_share" = the kernel's share of the sweep's kernel time in
 # the committed launch list of this bench command.  Valid for exactly that workload (the kernels are deterministic).
 NCU_C2 = {
-    "tiled": {"warp_inst": 3.2410e9, "threads_per_inst": 13.63, "dram_bytes": 4.647e9 + 1.025e9, "scan_share": 0.572,
-              "issue_active_pct": 69.3, "alu_pipe_pct": 53.9,
+    "tiled": {"warp_inst": 3.2099e9, "threads_per_inst": 13.70, "dram_bytes": 4.613e9 + 1.032e9, "scan_share": 0.579,
+              "issue_active_pct": 69.4, "alu_pipe_pct": 54.7,
               "source": "profiles/r2_lane_scan_ncu.txt (ncu --set full), profiles/r2_launches.csv (launch list of `bench.py --steps 2 --warmup 3 --skip-extras`)"},
 }
 

@@ -332,6 +332,12 @@ int b200bt_sweep_tiled(const float* price, int64_t ld_price, const float* rsi, i
  * this process record on their stream immediately before and after the scan kernel (lane_scan_kernel); NULL, NULL switches
  * it off.  The caller reads cudaEventElapsedTime after synchronising.  Not thread-safe (one measuring thread). */
 int b200bt_sweep_scan_timing(void* start_event, void* stop_event);
+/* Bound of one tile wait of the scan kernel in SM clocks (0 = the default, ~20 ms).  A tile whose bulk copy does not complete
+ * within the bound is not waited for any longer: the work item is marked as lost (its chunks are re-scanned by the repair pass
+ * or its lanes re-run by the exact fallback), the warp stops using its tile ring, and overflow_host[3] counts the event.  Results
+ * do not depend on it.  A negative value -k is the test hook: every warp gives up at the k-th tile of an item as if it had
+ * not arrived. */
+int b200bt_sweep_scan_wait_cycles(int64_t cycles);
 
 /* fitness[i] = mean over symbols of stats[i][s].score  (float64, device). */
 int b200bt_fitness_reduce(const b200bt_lane_stats* stats, int pop, int S,

@@ -293,6 +293,33 @@ def test_chunked_sweep_in_population_slices_with_duplicates(torch_cuda):
     _check_lanes_vs_oracle(chunked, population, ohlcv, cap)
 
 
+def test_scan_tiles_that_do_not_arrive_are_redone_exactly(torch_cuda):
+    """The scan's wait for a tile is bounded; a tile that does not arrive in time costs its work item, which is re-scanned by
+    the repair pass or re-run by the exact fallback.  The test hook makes every warp give up at the third tile of an item."""
+    from ai_crypto_trader_b200 import _lib, synth
+    from ai_crypto_trader_b200.sweep import MarketData, PopulationSweep
+    ohlcv = synth.synth_ohlcv(2, 200_000, first_symbol=2)
+    market = MarketData(ohlcv)
+    population = synth.random_population(200, seed=77)
+    fused = PopulationSweep(market, mode="fused")
+    f_f = fused.evaluate(population)
+    tiled = PopulationSweep(market, mode="tiled", chunk_options=dict(warm=1024, chunks=6))
+    lib = _lib.load()
+    lib.b200bt_sweep_scan_wait_cycles(-3)
+    try:
+        f_t = tiled.evaluate(population)
+        stalls, invalid = tiled.last_scan_stalls, tiled.last_invalid_lanes
+        h_t = tiled.lane_stats()["trade_hash"].copy()
+    finally:
+        lib.b200bt_sweep_scan_wait_cycles(0)
+    assert stalls > 0 and invalid > 0                     # the path really ran
+    np.testing.assert_array_equal(h_t, fused.lane_stats()["trade_hash"])
+    np.testing.assert_allclose(f_t, f_f, rtol=1e-9, atol=1e-11)
+    f_t2 = tiled.evaluate(population)                     # and the default bound is back
+    assert tiled.last_scan_stalls == 0
+    np.testing.assert_allclose(f_t2, f_f, rtol=1e-9, atol=1e-11)
+
+
 @pytest.mark.parametrize("n_bars,opts", [
     (300_000, dict(warm=4096)),                                        # wave-fitted K, verified boundaries
     (300_001, dict(warm=4096, chunks=7)),                              # ragged last tile
