@@ -521,6 +521,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the JSON line and nothing else
         dist.init_process_group("nccl", device_id=dev)
 
     pop_local, S, N = args.pop_per_gpu, args.symbols, args.bars
