@@ -1062,7 +1062,7 @@ __global__ void fix_items_kernel(const b200bt_chunk_item* __restrict__ items, in
     if (redo[it.individual]) out[atomicAdd(n_out, 1)] = it;
 }
 
-// Individuals with a lane the chunked evaluation could not settle (a boundary still inconsistent after the repair rounds, a
+// Individuals with a lane the chunked evaluation could not settle (a boundary still inconsistent after the repair passes, a
 // full event pool, a warp not packed for the thread-per-lane scan): listed on the device for the exact fallback.
 __global__ void redo_list_kernel(int pop, int S, const unsigned char* __restrict__ invalid, int32_t* __restrict__ list,
                                  int* __restrict__ n_list, int* __restrict__ n_invalid_lanes) {

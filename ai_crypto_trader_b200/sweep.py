@@ -664,7 +664,7 @@ class PopulationSweep:
                       plan.workspace.data_ptr(), plan.workspace.numel(), C.byref(self.cfg), stats.data_ptr(),
                       _lib.ptr(events), self.event_cap, plan.invalid.data_ptr(), plan.overflow.data_ptr(), st)
 
-    # Lanes the time-chunked kernels flagged (a boundary still inconsistent after the repair rounds, a full event pool, a warp
+    # Lanes the time-chunked kernels flagged (a boundary still inconsistent after the repair passes, a full event pool, a warp
     # not packed for the thread-per-lane scan) are re-evaluated by the fused kernel ON THE DEVICE, inside b200bt_sweep_chunked /
     # b200bt_sweep_tiled: an evaluation reads nothing back.  These two look at the flags of the last evaluation afterwards.
     def _sync_flags(self):

@@ -282,16 +282,32 @@ def cpu_baseline_inline():
     return py
 
 
+def _run_child(cmd, timeout_s, env=None):
+    """(return code, stdout, stderr) of a child interpreter in its own session; on a timeout the whole process group it
+    started (the child and its forked pool workers) is killed and TimeoutExpired raised."""
+    import signal
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True, env=env)
+    try:
+        out, err = proc.communicate(timeout=timeout_s)
+        return proc.returncode, out, err
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(proc.pid, signal.SIGKILL)
+        except ProcessLookupError:
+            pass
+        proc.communicate()
+        raise
+
+
 def cpu_baseline_child(timeout_s: float = 420.0, attempts: int = 2):
     """cpu_baseline_inline() in a child interpreter (`bench.py --cpu-baseline-only` prints its dict as one JSON line)."""
     why = "not run"
     for attempt in range(attempts):
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-only"], stdout=subprocess.PIPE,
-                               stderr=subprocess.PIPE, text=True, timeout=timeout_s, start_new_session=True)
-            if r.returncode == 0:
-                return json.loads(r.stdout.strip().splitlines()[-1])
-            why = f"exit code {r.returncode}: {r.stderr.strip()[-300:]}"
+            rc, out, err = _run_child([sys.executable, os.path.abspath(__file__), "--cpu-baseline-only"], timeout_s)
+            if rc == 0:
+                return json.loads(out.strip().splitlines()[-1])
+            why = f"exit code {rc}: {err.strip()[-300:]}"
         except subprocess.TimeoutExpired:
             why = f"no result within {timeout_s:.0f} s"
         except Exception as e:
@@ -485,13 +501,12 @@ def main():
         why = "not run"
         for attempt in range(2):
             try:
-                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--reference-child", "--gpus", str(args.gpus),
-                                    "--steps", str(args.steps), "--warmup", str(args.warmup)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
-                                   text=True, timeout=900, start_new_session=True, env=dict(os.environ, RANK="0"))
-                if r.returncode == 0 and r.stdout.strip():
-                    print(r.stdout.strip().splitlines()[-1], flush=True)
+                rc, out, err = _run_child([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--reference-child", "--gpus", str(args.gpus),
+                                           "--steps", str(args.steps), "--warmup", str(args.warmup)], 900, env=dict(os.environ, RANK="0"))
+                if rc == 0 and out.strip():
+                    print(out.strip().splitlines()[-1], flush=True)
                     return
-                why = f"exit code {r.returncode}: {r.stderr.strip()[-300:]}"
+                why = f"exit code {rc}: {err.strip()[-300:]}"
             except subprocess.TimeoutExpired:
                 why = "no result within 900 s"
             _phase(f"reference arm attempt {attempt + 1} failed: {why}")

@@ -64,3 +64,33 @@ def test_shard_bounds_cover_the_range():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert all(hi - lo <= per for lo, hi, per in spans)
+
+
+@pytest.mark.parametrize("n,order_by", [(1024, "row_cost"), (333, "row_cost"), (31, "row_thresholds"), (1024, "row_thresholds"),
+                                        (70, "identity")])
+def test_pack_warps_seats_every_individual_once_and_keeps_two_rows_per_warp(n, order_by):
+    """Thread slots of the thread-per-lane scan (sweep.pack_warps): whole warps, every individual seated exactly once, at
+    most WARP_RSI_ROWS distinct bank rows per warp (the kernel flags a warp that breaks the rule; only the identity order
+    may), the most expensive warps dispatched first."""
+    from ai_crypto_trader_b200.sweep import WARP_RSI_ROWS, pack_warps
+    pop = synth.random_population(n, seed=n)
+    pred = predicted_events(pop, 1_000_000)
+    slots = pack_warps(pop, pred, order_by)
+    assert slots.dtype == np.int32 and slots.size % 32 == 0
+    seated = slots[slots >= 0]
+    assert sorted(seated.tolist()) == list(range(n))
+    warps = slots.reshape(-1, 32)
+    rows = np.array([int(p["rsi_period"]) for p in pop])
+    if order_by != "identity":
+        for w in warps:
+            assert len(set(rows[w[w >= 0]].tolist())) <= WARP_RSI_ROWS
+        cost = np.where(warps >= 0, pred[np.maximum(warps, 0)], 0.0).sum(axis=1)
+        assert np.all(np.diff(cost) <= 1e-9)                  # dispatch order: most expensive first
+        # packing is dense: empty seats only where a third row would have entered a warp
+        assert warps.shape[0] <= -(-n // 32) + len(set(rows.tolist()))
+    # an explicit row per individual (several timeframes) overrides the period
+    rows2 = rows + 100 * (np.arange(n) % 3)
+    s2 = pack_warps(pop, pred, "row_cost", rows=rows2).reshape(-1, 32)
+    for w in s2:
+        assert len(set(rows2[w[w >= 0]].tolist())) <= WARP_RSI_ROWS
+    assert sorted(s2[s2 >= 0].tolist()) == list(range(n))

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small workload for compute-sanitizer (memcheck / racecheck / initcheck): every kernel family once, at sizes a
-40-100x slowdown still finishes.  The sweep legs force the speculative paths (no warm-up -> repair rounds on the main
+40-100x slowdown still finishes.  The sweep legs force the speculative paths (no warm-up -> repair passes on the main
 and on the side stream, a pool that overflows -> fused fallback) because that is where the bump allocator, the
 linked event pool and the overlapped repair stream live.  Results are checked against the C oracle, so a sanitizer
 run that "passes" also computed the right thing.
