@@ -293,6 +293,39 @@ def test_chunked_sweep_in_population_slices_with_duplicates(torch_cuda):
     _check_lanes_vs_oracle(chunked, population, ohlcv, cap)
 
 
+def test_scan_timing_hook_brackets_the_scan_kernel(torch_cuda):
+    """b200bt_sweep_scan_timing: the library records the caller's two events around lane_scan_kernel on the launching stream
+    (bench.py's roofline divides by that duration); NULL, NULL switches it off."""
+    torch = torch_cuda
+    from ai_crypto_trader_b200 import _lib, synth
+    from ai_crypto_trader_b200.sweep import MarketData, PopulationSweep
+    market = MarketData(synth.synth_ohlcv(2, 200_000, first_symbol=4))
+    population = synth.random_population(128, seed=5)
+    tiled = PopulationSweep(market, mode="tiled", chunk_options=dict(warm=1024, chunks=6))
+    tiled.evaluate(population)
+    e0, e1, a, b = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+    for e in (e0, e1):
+        e.record()                                   # (makes torch create the cudaEvent_t)
+    handle = lambda e: (e.cuda_event.value if hasattr(e.cuda_event, "value") else int(e.cuda_event))
+    lib = _lib.load()
+    try:
+        assert lib.b200bt_sweep_scan_timing(handle(e0), handle(e1)) == 0
+        a.record()
+        tiled.evaluate(population)
+        b.record()
+    finally:
+        lib.b200bt_sweep_scan_timing(None, None)
+    torch.cuda.synchronize()
+    scan_ms, sweep_ms = e0.elapsed_time(e1), a.elapsed_time(b)
+    assert 0.0 < scan_ms < sweep_ms
+    e1.record()                                      # hook off: the next sweep leaves the events alone
+    torch.cuda.synchronize()
+    t_before = e0.elapsed_time(e1)
+    tiled.evaluate(population)
+    torch.cuda.synchronize()
+    assert e0.elapsed_time(e1) == t_before
+
+
 def test_scan_tiles_that_do_not_arrive_are_redone_exactly(torch_cuda):
     """The scan's wait for a tile is bounded; a tile that does not arrive in time costs its work item, which is re-scanned by
     the repair pass or re-run by the exact fallback.  The test hook makes every warp give up at the third tile of an item."""
