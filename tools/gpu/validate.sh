@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-O=gpurun_out/r3k; mkdir -p $O
+O=gpurun_out/validate; mkdir -p $O
 ( time timeout 240 python -m pytest tests -m gpu -q --durations=6 ) > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
 ( time timeout 120 python __graft_entry__.py --smoke ) > $O/smoke.log 2>&1; echo "smoke rc=$?" >> $O/smoke.log
 ( time timeout 300 python bench.py --steps 10 --warmup 3 ) > $O/bench.json 2> $O/bench.err
