@@ -408,10 +408,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    while (!mbar_try_wait(bar, parity)) {}
-}
-// bounded form: false when the phase has not completed `cycles` SM clocks after the first failed poll (the caller gives the
+// bounded wait (there is no unbounded one): false when the phase has not completed `cycles` SM clocks after the first failed poll (the caller gives the
 // work up and has it redone by the exact fallback instead of spinning for ever on a copy that does not arrive)
 __device__ __forceinline__ bool mbar_wait_bounded(unsigned long long* bar, unsigned parity, long long cycles) {
     if (mbar_try_wait(bar, parity)) return true;
