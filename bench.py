@@ -282,6 +282,16 @@ def cpu_baseline_inline():
     return py
 
 
+def _claim_stdout() -> int:
+    """The JSON line must be the only thing on stdout, but libraries write there too (NCCL prints its version line to fd 1
+    whatever NCCL_DEBUG_FILE says): file descriptor 1 is pointed at stderr for the rest of the process and the original
+    is returned for the one os.write of the result."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
 def _run_child(cmd, timeout_s, env=None):
     """(return code, stdout, stderr) of a child interpreter in its own session; on a timeout the whole process group it
     started (the child and its forked pool workers) is killed and TimeoutExpired raised."""
@@ -513,6 +523,7 @@ def main():
         print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
         return
     assert args.warmup >= 3 or os.environ.get("B200BT_ALLOW_SHORT_WARMUP"), "timing rules: warm-up >= 3"
+    result_fd = _claim_stdout()
     # A stalled run must end with a traceback, not with the caller's patience: every thread's stack goes to stderr.
     import faulthandler
     faulthandler.dump_traceback_later(int(os.environ.get("B200BT_BENCH_WATCHDOG_S", 1500)), exit=True)
@@ -745,7 +756,9 @@ def main():
                 cpu_baseline["configs0_backtest"]["gpu_path_ms"] = (time.perf_counter() - t0) * 1e3
                 cpu_baseline["configs0_backtest"]["gpu_trades"] = int(st0["total_trades"])
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line), flush=True)
+        payload = (json.dumps(line) + "\n").encode()
+        while payload:
+            payload = payload[os.write(result_fd, payload):]
     _phase("done")
     faulthandler.cancel_dump_traceback_later()
     if abandoned:

@@ -63,3 +63,17 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     r2 = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2"], stdout=subprocess.PIPE,
                         stderr=subprocess.PIPE, text=True, timeout=120, cwd=str(ROOT), env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r2.returncode == 0 and r2.stdout.strip() == ""
+
+
+def test_claimed_stdout_carries_only_the_result_line():
+    """bench._claim_stdout: whatever the process (or a C library) prints to fd 1 afterwards lands on stderr."""
+    code = ("import os, sys, json; sys.path.insert(0, %r); import bench\n"
+            "fd = bench._claim_stdout()\n"
+            "print('a python print'); os.system('echo a child of the shell')\n"
+            "os.write(1, b'a C library writing to fd 1\\n')\n"
+            "os.write(fd, (json.dumps({'value': 1}) + '\\n').encode())\n") % str(ROOT)
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"value": 1}\n'
+    for s in ("a python print", "a child of the shell", "a C library writing to fd 1"):
+        assert s in r.stderr
