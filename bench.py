@@ -286,10 +286,13 @@ def _claim_stdout() -> int:
     """The JSON line must be the only thing on stdout, but libraries write there too (NCCL prints its version line to fd 1
     whatever NCCL_DEBUG_FILE says): file descriptor 1 is pointed at stderr for the rest of the process and the original
     is returned for the one os.write of the result."""
-    sys.stdout.flush()
-    real = os.dup(1)
-    os.dup2(2, 1)
-    return real
+    try:
+        sys.stdout.flush()
+        real = os.dup(1)
+        os.dup2(2, 1)
+        return real
+    except OSError:
+        return 1                # (no such descriptor to duplicate: write the line to fd 1 as it is)
 
 
 def _run_child(cmd, timeout_s, env=None):
@@ -757,8 +760,12 @@ def main():
                 cpu_baseline["configs0_backtest"]["gpu_trades"] = int(st0["total_trades"])
             line["cpu_baseline"] = cpu_baseline
         payload = (json.dumps(line) + "\n").encode()
-        while payload:
-            payload = payload[os.write(result_fd, payload):]
+        try:
+            while payload:
+                payload = payload[os.write(result_fd, payload):]
+        except OSError:
+            sys.__stdout__.write(payload.decode())
+            sys.__stdout__.flush()
     _phase("done")
     faulthandler.cancel_dump_traceback_later()
     if abandoned:
